@@ -20,7 +20,8 @@ class OrcParams(C.Structure):
                 ("bvx_min", C.c_double), ("bvx_max", C.c_double), ("bvy_min", C.c_double), ("bvy_max", C.c_double),
                 ("leg_sq", C.c_double), ("ang_max", C.c_double),
                 ("has_fen", C.c_int), ("max_iter", C.c_int), ("tol", C.c_double),
-                ("select_obs", C.c_int), ("goal_shift", C.c_int), ("close_radius", C.c_double)]
+                ("select_obs", C.c_int), ("goal_shift", C.c_int), ("close_radius", C.c_double),
+                ("split_abs", C.c_int)]
 
 
 def build(force: bool = False) -> str:

@@ -57,6 +57,7 @@ typedef struct {
     int select_obs;      /* modi: apply detection-range selection */
     int goal_shift;      /* sig_step, modi: detour heuristic */
     double close_radius; /* close_2_goal threshold */
+    int split_abs;       /* solve with the smooth two-row form of s*|dtheta|+v (see prob_eval) */
 } orc_params;
 
 typedef struct {
@@ -68,7 +69,9 @@ typedef struct {
     double cir[KMAX][3];
     double elp[KMAX][5];
     double last_u[2];
-    int n, m;            /* m counts the reference rows; DD variable bounds are appended after them */
+    int n, m;            /* solver rows: reference rows, DD variable-bound rows, then the 3 split rows */
+    int mref;            /* reference rows only */
+    int split;
 } orc_problem;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -337,12 +340,41 @@ static void dd_eval(const orc_problem *pb, const double *u, double *f, double *g
     }
 }
 
-static void prob_eval(const orc_problem *pb, const double *u, double *f, double *grad, double *c, double *jac) {
+static void ref_eval(const orc_problem *pb, const double *u, double *f, double *grad, double *c, double *jac) {
     if (pb->P->form == 2) dd_eval(pb, u, f, grad, c, jac); else lip_eval(pb, u, f, grad, c, jac);
 }
 
+/* Solver-side view of the rows.  With pb->split the non-smooth row  s*|dtheta| + v  in [v_min, v_max]
+ * (MPC_LIP_modi.py:493, MPC_DD_sig_step.py:416) is replaced by the two smooth rows  v + s*dtheta <= v_max  and
+ * v - s*dtheta <= v_max  (the second appended after all other rows).  The feasible set is identical: the lower
+ * bound v_min is implied by the v_bx row (LIP) / the variable bound on v (DD), which carry the same limits. */
+static void prob_eval(const orc_problem *pb, const double *u, double *f, double *grad, double *c, double *jac) {
+    ref_eval(pb, u, f, grad, c, jac);
+    if (!pb->split || (!c && !jac)) return;
+    const int n = pb->n, K = pb->nc + pb->ne, mb = pb->m - 3;
+    const double s = pb->P->s_turn;
+    for (int i = 0; i < 3; i++) {
+        if (pb->P->form == 2) {
+            int rf = i * (K + 1) + K;
+            if (c) { c[rf] = u[2 * i] + s * u[2 * i + 1]; c[mb + i] = u[2 * i] - s * u[2 * i + 1]; }
+            if (jac) {
+                for (int j = 0; j < n; j++) jac[rf * n + j] = jac[(mb + i) * n + j] = 0.0;
+                jac[rf * n + 2 * i] = 1.0; jac[rf * n + 2 * i + 1] = s;
+                jac[(mb + i) * n + 2 * i] = 1.0; jac[(mb + i) * n + 2 * i + 1] = -s;
+            }
+        } else {
+            int rv = i * (5 + K), rd = rv + 3 + K, rf = rv + 4 + K;
+            if (c) { double v = c[rv], d = c[rd]; c[rf] = v + s * d; c[mb + i] = v - s * d; }
+            if (jac) for (int j = 0; j < n; j++) {
+                double a = jac[rv * n + j], b = jac[rd * n + j];
+                jac[rf * n + j] = a + s * b; jac[(mb + i) * n + j] = a - s * b;
+            }
+        }
+    }
+}
+
 /* rows in reference order (+ DD variable-bound rows at the end) */
-static int prob_bounds(const orc_problem *pb, double *cl, double *cu) {
+static int ref_bounds(const orc_problem *pb, double *cl, double *cu) {
     const orc_params *P = pb->P;
     int row = 0, K = pb->nc + pb->ne;
     if (P->form == 2) {
@@ -366,6 +398,17 @@ static int prob_bounds(const orc_problem *pb, double *cl, double *cu) {
         if (P->has_fen) { cl[row] = P->bvx_min; cu[row] = P->bvx_max; row++; }
     }
     return row;
+}
+
+static int prob_bounds(const orc_problem *pb, double *cl, double *cu) {
+    int rows = ref_bounds(pb, cl, cu);
+    if (!pb->split) return rows;
+    int K = pb->nc + pb->ne, mb = pb->m - 3;
+    for (int i = 0; i < 3; i++) {
+        int rf = pb->P->form == 2 ? i * (K + 1) + K : i * (5 + K) + 4 + K;
+        cl[rf] = -INFINITY; cl[mb + i] = -INFINITY; cu[mb + i] = cu[rf];
+    }
+    return pb->m;
 }
 
 /* goal shift + selection: fills pb from raw inputs */
@@ -412,7 +455,9 @@ static void prob_setup(orc_problem *pb, const orc_params *P, const double *xk, c
     }
     pb->n = P->form == 2 ? 6 : 15;
     int K = pb->nc + pb->ne;
-    pb->m = P->form == 2 ? 3 * (K + 1) + 6 : 3 * (4 + K + (P->has_fen ? 1 : 0));
+    pb->mref = P->form == 2 ? 3 * (K + 1) : 3 * (4 + K + (P->has_fen ? 1 : 0));
+    pb->split = P->has_fen && P->split_abs;
+    pb->m = pb->mref + (P->form == 2 ? 6 : 0) + (pb->split ? 3 : 0);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -692,6 +737,7 @@ static void ipm_solve(const orc_problem *pb, const double *u0, orc_result *R) {
             double c_now = row_violation(S, c, cl, cu);
             double entry = 0; for (int r = 0; r < m; r++) entry += fabs(c[r] - S->s[r]);
             if (S->nf < FILT_MAX) { S->filt[S->nf].theta = (1 - 1e-5) * theta; S->filt[S->nf].phi = phi - 1e-5 * theta; S->nf++; }
+            iters++;   /* entering restoration counts as an iteration (guards against cycling) */
             int ok = restore(pb, S, cl, cu, fmax(0.1 * c_now, 1e-9), &iters, P->max_iter);
             prob_eval(pb, S->x, &f, g, c, jac);
             double vnow = row_violation(S, c, cl, cu);
@@ -727,7 +773,7 @@ void orc_default_params(int form, orc_params *P) {
     memset(P, 0, sizeof(*P));
     P->form = form;
     P->q = 1.0; P->bvx_min = 0.4; P->bvx_max = 0.8; P->bvy_min = 0.15; P->leg_sq = 0.09; P->ang_max = M_PI / 16;
-    P->tol = 1e-8;
+    P->tol = 1e-8; P->split_abs = 1;
     if (form == 0) { P->p = 2.0; P->r = 15.0; P->gamma = 0.4; P->s_turn = 0.014 * 180 / M_PI; P->bvy_max = 0.3; P->max_iter = 20; P->goal_shift = 1; P->close_radius = 0.35; }
     else if (form == 1) { P->p = 0.0; P->r = 50.0; P->gamma = 0.2; P->s_turn = 0.024 * 180 / M_PI; P->bvy_max = 0.35; P->has_fen = 1; P->max_iter = 30; P->select_obs = 1; P->goal_shift = 1; P->close_radius = 0.15; }
     else { P->p = 0.0; P->r = 50.0; P->gamma = 0.2; P->s_turn = 0.024 * 180 / M_PI; P->bvy_max = 0.35; P->has_fen = 1; P->t_smooth = 2.0; P->max_iter = 40; P->close_radius = 0.35; }
@@ -737,7 +783,7 @@ void orc_default_params(int form, orc_params *P) {
 void orc_setup_info(const orc_params *P, const double *xk, const double *goal, int leg, int nc, const double *cir,
                     int ne, const double *elp, int *out, double *goal_eff) {
     orc_problem pb; prob_setup(&pb, P, xk, goal, leg, nc, cir, ne, elp, NULL);
-    out[0] = pb.n; out[1] = P->form == 2 ? pb.m - 6 : pb.m; out[2] = pb.nc; out[3] = pb.ne;
+    out[0] = pb.n; out[1] = pb.mref; out[2] = pb.nc; out[3] = pb.ne;
     goal_eff[0] = pb.goal[0]; goal_eff[1] = pb.goal[1];
 }
 
@@ -747,9 +793,9 @@ void orc_eval(const orc_params *P, const double *xk, const double *goal, int leg
               double *cl, double *cu) {
     orc_problem pb; prob_setup(&pb, P, xk, goal, leg, nc, cir, ne, elp, last_u);
     double cc[MMAX], jj[MMAX * NMAX], l[MMAX], h[MMAX];
-    prob_eval(&pb, u, f, grad, cc, jj);
-    prob_bounds(&pb, l, h);
-    int mref = P->form == 2 ? pb.m - 6 : pb.m;
+    ref_eval(&pb, u, f, grad, cc, jj);
+    ref_bounds(&pb, l, h);
+    int mref = pb.mref;
     if (c) memcpy(c, cc, mref * sizeof(double));
     if (jac) memcpy(jac, jj, mref * pb.n * sizeof(double));
     if (cl) memcpy(cl, l, mref * sizeof(double));
