@@ -1,0 +1,128 @@
+/*
+ * dcbf_mpc.h -- C ABI of the B200-native batched D-CBF ALIP/LIP MPC solver.
+ *
+ * One shared object (libdcbf_mpc.so), plain pointers and sizes, no torch types.  Every entry point replaces a
+ * piece of the reference planner that runs once per re-plan on the CPU (paths relative to the reference repo):
+ *
+ *   dcbf_default_params  <- constants hard-coded in MPCCBF.__init__ / LIP_Prob.__init__
+ *                           (MPC_LIP_sig_step.py:16-44,340-353; MPC_LIP_modi.py:16-45,397-411;
+ *                            MPC_DD_sig_step.py:14-40,323-338) and the Ipopt options at the call sites
+ *                           (MPC_LIP_sig_step.py:266-275, MPC_LIP_modi.py:284-293, MPC_DD_sig_step.py:181-189)
+ *   dcbf_set_fields      <- obstacle lists handed to the MPCCBF constructors (obs_cbf / cir_cbf, elp_cbf)
+ *   dcbf_eval            <- LIP_Prob.objective / gradient / constraints / jacobian
+ *                           (MPC_LIP_sig_step.py:372-496, MPC_LIP_modi.py:430-583, MPC_DD_sig_step.py:351-477)
+ *                           plus the Lagrangian Hessian the reference never forms
+ *   dcbf_solve           <- MPCCBF.solveMPCCBF + the plan re-roll of gen_control_test / gen_dd_control
+ *                           (MPC_LIP_sig_step.py:89-111,184-278; MPC_LIP_modi.py:90-115,197-301,325-338;
+ *                            MPC_DD_sig_step.py:70-99,123-193) i.e. the cyipopt.Problem(...).solve(u0) call
+ *   dcbf_rollout         <- the plan -> apply -> re-plan loop of MPC_LIP_sig_step.py:565-575
+ *   dcbf_solve_host      <- same as dcbf_solve for callers that hold host (numpy) buffers
+ *
+ * Conventions
+ *   - all floating point data is FP64, row-major, densely packed; index data is int32
+ *   - "device" pointers must be valid on the context's device; "host" pointers are ordinary host memory
+ *   - work is enqueued on the CUDA stream passed as `void* stream` (a cudaStream_t; NULL = default stream);
+ *     device-pointer calls do not synchronise
+ *   - return value: 0 on success, negative dcbf_status on error; nothing throws; there is no CPU fallback
+ *   - plan variables use the reference's layouts: state x = (px, py, vx, vy, theta) [DD: (x, y, theta)],
+ *     foot/turn plan p_k = (foot_x, foot_y, dtheta) (= W(u_k - A x_k), MPC_LIP_sig_step.py:302-306),
+ *     decision vector u in R^15 with the representative u_k := x_{k+1} (DD: u = (v0, w0, v1, w1, v2, w2))
+ *   - solver status keeps Ipopt's integers: 0 solved, 1 acceptable, 2 infeasible problem detected,
+ *     -1 iteration cap, -2 restoration failed, -3 step computation failed, -13 invalid number
+ */
+#ifndef DCBF_MPC_H
+#define DCBF_MPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCBF_ABI_VERSION 1
+#define DCBF_MAX_OBS 16 /* circles and ellipses each, per field */
+
+enum dcbf_formulation { DCBF_SIG_STEP = 0, DCBF_MODI = 1, DCBF_DD = 2 };
+
+enum dcbf_status {
+    DCBF_OK = 0,
+    DCBF_ERR_ARG = -1,      /* NULL / out-of-range argument */
+    DCBF_ERR_CUDA = -2,     /* a CUDA runtime call failed (see dcbf_last_error) */
+    DCBF_ERR_NO_FIELDS = -3 /* dcbf_set_fields has not been called */
+};
+
+typedef struct dcbf_params {
+    int32_t formulation; /* dcbf_formulation */
+    int32_t max_iter;    /* interior-point iteration cap */
+    int32_t select_obs;  /* 1: keep obstacles with dist^2 - r^2 <= detect_sq only (MPC_LIP_modi.py:325-338) */
+    int32_t goal_shift;  /* 1: 15-degree detour heuristic (MPC_LIP_sig_step.py:229-253) */
+    int32_t has_fen;     /* 1: speed/turn coupling row s*|dtheta| + v (MPC_LIP_modi.py:493) */
+    int32_t close_any;   /* 1: close_2_goal if any step is inside close_radius (sig_step), 0: first step only */
+    int32_t reserved0, reserved1;
+    double w_p, w_q, w_r, w_t;                                        /* cost weights p, q, r, t */
+    double gamma, s_turn;                                             /* D-CBF decay, turn coupling */
+    double bvx_min, bvx_max, bvy_min, bvy_max, leg_sq, ang_max;       /* row bounds */
+    double detect_sq, close_radius;
+    double tol, constr_viol_tol, mu_init;                             /* Ipopt: tol, constr_viol_tol, mu_init */
+} dcbf_params;
+
+typedef struct dcbf_ctx dcbf_ctx;
+
+int dcbf_abi_version(void);
+int dcbf_default_params(int formulation, dcbf_params *out);
+int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out);
+void dcbf_destroy(dcbf_ctx *ctx);
+const char *dcbf_last_error(const dcbf_ctx *ctx);
+
+/* Obstacle fields shared by the scenarios of a batch (device pointers, copied into the context):
+ * cir[F][Kc][3] = (cx, cy, r) and elp[F][Ke][5] = (cx, cy, a, b, phi), already inflated by the safety margin. */
+int dcbf_set_fields(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir_dev, int32_t Ke, const double *elp_dev,
+                    void *stream);
+
+/* Rows of one NLP in the reference order.  m = 3*(4+Kc) sig_step, 3*(5+Kc+Ke) modi, 3*(Kc+Ke+1) dd; n = 9 (dd: 6).
+ * No obstacle selection is applied here (every obstacle of the field is a row). */
+int dcbf_num_rows(const dcbf_ctx *ctx);
+int dcbf_num_vars(const dcbf_ctx *ctx);
+
+/* K1: callbacks at a point z[B][n] of the reduced space (z = (p0, p1, p2); dd: z = u).
+ * goal[B][2] is used as given (no goal shift).  Outputs (any may be NULL): f[B], grad[B][n], c[B][m],
+ * jac[B][m][n], cl[B][m], cu[B][m], hess[B][n][n] = Hessian of  f + sum_r lambda_r c_r  (lambda[B][m], NULL => 0). */
+int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+              const double *last_u, const double *z, const double *lambda, double *f, double *grad, double *c,
+              double *jac, double *cl, double *cu, double *hess, void *stream);
+
+/* K1+K2: one re-plan per scenario.  Inputs: x0[B][5|3], goal[B][2], leg[B] (+1/-1; dd: ignored, may be NULL),
+ * field[B] (NULL => field 0 for every scenario), warm[B][15|6] = the reference's u0 (MPC_LIP_sig_step.py:185-189
+ * builds it from the previous plan; the caller passes the final vector), last_u[B][2] (dd only).
+ * Outputs (any may be NULL): u[B][15|6], x_plan[B][3][5|3], p_plan[B][3][3] (LIP only), status[B], iters[B],
+ * obj[B], viol[B] (max row violation), close2goal[B] (uint8). */
+int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+               const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
+               int32_t *iters, double *obj, double *viol, uint8_t *close2goal, void *stream);
+
+/* K3: closed loop of `steps` re-plans per scenario without leaving the GPU (LIP formulations).  Each step:
+ * solve, apply the first foot placement exactly (x <- x_plan[0]), flip the stance leg, warm start from the shifted
+ * plan [x_2, x_3, x_3]; stop early on close_2_goal.  Outputs (any may be NULL): x_final[B][5], steps_done[B],
+ * n_infeasible[B] (re-plans that ended with status 2), total_iters[B],
+ * traj[B][steps][8] = (px, py, vx, vy, theta, foot_x, foot_y, status) after each step (NaN once stopped). */
+int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, const double *goal, const int32_t *leg,
+                 const int32_t *field, double *x_final, int32_t *steps_done, int32_t *n_infeasible,
+                 int32_t *total_iters, double *traj, void *stream);
+
+/* dcbf_solve for host buffers: copies inputs to the device, solves, copies results back and synchronises.
+ * Obstacle fields still come from dcbf_set_fields_host / dcbf_set_fields. */
+int dcbf_set_fields_host(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir_host, int32_t Ke, const double *elp_host);
+int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg,
+                    const int32_t *field, const double *warm, const double *last_u, double *u, double *x_plan,
+                    double *p_plan, int32_t *status, int32_t *iters, double *obj, double *viol, uint8_t *close2goal);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t dcbf_launch_count(const dcbf_ctx *ctx);
+
+/* FP64 FMA microbenchmark on the context's device: returns achieved TFLOP/s (2 flop per DFMA), <0 on error. */
+double dcbf_fp64_peak_tflops(dcbf_ctx *ctx, int32_t repeats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCBF_MPC_H */

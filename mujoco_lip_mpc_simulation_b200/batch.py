@@ -1,0 +1,237 @@
+"""Batched host API over the C ABI: thousands to millions of D-CBF MPC re-plans per call.
+
+`DcbfSolver` owns one `dcbf_ctx` (one formulation, one device).  Device entry points take torch CUDA tensors
+(FP64 / int32, contiguous) and enqueue on the current torch stream; `solve_host` takes numpy arrays and goes
+through `dcbf_solve_host` (H2D copy, kernel, D2H copy, synchronise).  PyTorch is used for device memory and
+streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FORMS = {"sig_step": 0, "modi": 1, "dd": 2}
+
+
+def default_params(form) -> _lib.DcbfParams:
+    P = _lib.DcbfParams()
+    rc = _lib.load().dcbf_default_params(FORMS[form] if isinstance(form, str) else int(form), C.byref(P))
+    if rc != 0:
+        raise ValueError(f"dcbf_default_params({form}) -> {rc}")
+    return P
+
+
+@dataclass
+class SolveResult:
+    u: "torch.Tensor | np.ndarray"          # [B,15] (dd: [B,6])  reference decision vector, u_k := x_{k+1}
+    x_plan: "torch.Tensor | np.ndarray"     # [B,3,5] (dd: [B,3,3])
+    p_plan: "torch.Tensor | np.ndarray | None"   # [B,3,3] foot_x, foot_y, dtheta (LIP only)
+    status: "torch.Tensor | np.ndarray"     # [B] int32, Ipopt status integers
+    iters: "torch.Tensor | np.ndarray"
+    obj: "torch.Tensor | np.ndarray"
+    viol: "torch.Tensor | np.ndarray"
+    close2goal: "torch.Tensor | np.ndarray"
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+class DcbfSolver:
+    def __init__(self, form="sig_step", device: int | None = None, params: _lib.DcbfParams | None = None, **overrides):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DcbfSolver needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.P = params if params is not None else default_params(form)
+        for k, v in overrides.items():
+            setattr(self.P, k, v)
+        self.form = int(self.P.formulation)
+        self.dd = self.form == 2
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self._ctx = C.c_void_p()
+        rc = self.lib.dcbf_create(C.byref(self.P), self.device, C.byref(self._ctx))
+        if rc != 0:
+            raise RuntimeError(f"dcbf_create failed ({rc})")
+        self.F = self.Kc = self.Ke = 0
+        self._keep = []
+
+    # ------------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.dcbf_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.dcbf_last_error(self._ctx)
+            raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.tdev).cuda_stream
+
+    def _dev(self, a, dtype):
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.tdev, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=self.tdev).contiguous()
+
+    @property
+    def n(self):
+        return 6 if self.dd else 9
+
+    @property
+    def nx(self):
+        return 3 if self.dd else 5
+
+    @property
+    def nu(self):
+        return 6 if self.dd else 15
+
+    @property
+    def m(self):
+        return int(self.lib.dcbf_num_rows(self._ctx))
+
+    @property
+    def launches(self):
+        return int(self.lib.dcbf_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------------------------------------------
+    def set_fields(self, cir, elp=None):
+        """cir [F,Kc,3] (cx,cy,r) and elp [F,Ke,5] (cx,cy,a,b,phi), already inflated (obs_cbf of the reference)."""
+        cir = self._dev(np.zeros((1, 0, 3)) if cir is None else cir, torch.float64)
+        if cir.dim() == 2:
+            cir = cir[None]
+        F = cir.shape[0]
+        elp = self._dev(np.zeros((F, 0, 5)) if elp is None else elp, torch.float64)
+        if elp.dim() == 2:
+            elp = elp[None]
+        assert elp.shape[0] == F
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_set_fields(self._ctx, F, cir.shape[1], _ptr(cir) if cir.numel() else None, elp.shape[1],
+                                          _ptr(elp) if elp.numel() else None, self._stream())
+        self._check(rc, "dcbf_set_fields")
+        self.F, self.Kc, self.Ke = F, int(cir.shape[1]), int(elp.shape[1])
+        self._keep = [cir, elp]
+
+    def _inputs(self, x0, goal, leg, field, last_u):
+        x0 = self._dev(x0, torch.float64).reshape(-1, self.nx)
+        B = x0.shape[0]
+        goal = self._dev(goal, torch.float64).reshape(-1, 2)
+        if goal.shape[0] != B:
+            goal = goal.expand(B, 2).contiguous()
+        leg = None if leg is None else self._dev(leg, torch.int32).reshape(-1)
+        if leg is not None and leg.shape[0] != B:
+            leg = leg.expand(B).contiguous()
+        field = None if field is None else self._dev(field, torch.int32).reshape(-1)
+        last_u = None if last_u is None else self._dev(last_u, torch.float64).reshape(B, 2)
+        return B, x0, goal, leg, field, last_u
+
+    def solve(self, x0, goal, leg, warm, field=None, last_u=None) -> SolveResult:
+        B, x0, goal, leg, field, last_u = self._inputs(x0, goal, leg, field, last_u)
+        warm = self._dev(warm, torch.float64).reshape(B, self.nu)
+        kw = dict(device=self.tdev)
+        u = torch.empty((B, self.nu), dtype=torch.float64, **kw)
+        xp = torch.empty((B, 3, self.nx), dtype=torch.float64, **kw)
+        pp = None if self.dd else torch.empty((B, 3, 3), dtype=torch.float64, **kw)
+        st = torch.empty(B, dtype=torch.int32, **kw)
+        it = torch.empty(B, dtype=torch.int32, **kw)
+        obj = torch.empty(B, dtype=torch.float64, **kw)
+        viol = torch.empty(B, dtype=torch.float64, **kw)
+        cl = torch.empty(B, dtype=torch.uint8, **kw)
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_solve(self._ctx, B, _ptr(x0), _ptr(goal), _ptr(leg), _ptr(field), _ptr(warm), _ptr(last_u),
+                                     _ptr(u), _ptr(xp), _ptr(pp), _ptr(st), _ptr(it), _ptr(obj), _ptr(viol), _ptr(cl),
+                                     self._stream())
+        self._check(rc, "dcbf_solve")
+        return SolveResult(u, xp, pp, st, it, obj, viol, cl.bool())
+
+    def solve_into(self, B, x0, goal, leg, field, warm, last_u, out: SolveResult):
+        """Allocation-free variant for benchmarking: all arguments are resident tensors."""
+        rc = self.lib.dcbf_solve(self._ctx, B, _ptr(x0), _ptr(goal), _ptr(leg), _ptr(field), _ptr(warm), _ptr(last_u),
+                                 _ptr(out.u), _ptr(out.x_plan), _ptr(out.p_plan), _ptr(out.status), _ptr(out.iters),
+                                 _ptr(out.obj), _ptr(out.viol), _ptr(out.close2goal), self._stream())
+        self._check(rc, "dcbf_solve")
+
+    def evaluate(self, x0, goal, leg, z, lam=None, field=None, last_u=None, want_hess=True):
+        B, x0, goal, leg, field, last_u = self._inputs(x0, goal, leg, field, last_u)
+        n, m = self.n, self.m
+        z = self._dev(z, torch.float64).reshape(B, n)
+        lam = None if lam is None else self._dev(lam, torch.float64).reshape(B, m)
+        kw = dict(device=self.tdev, dtype=torch.float64)
+        f, grad = torch.empty(B, **kw), torch.empty((B, n), **kw)
+        c, jac = torch.empty((B, m), **kw), torch.empty((B, m, n), **kw)
+        cl, cu = torch.empty((B, m), **kw), torch.empty((B, m), **kw)
+        hess = torch.empty((B, n, n), **kw) if want_hess else None
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_eval(self._ctx, B, _ptr(x0), _ptr(goal), _ptr(leg), _ptr(field), _ptr(last_u), _ptr(z),
+                                    _ptr(lam), _ptr(f), _ptr(grad), _ptr(c), _ptr(jac), _ptr(cl), _ptr(cu), _ptr(hess),
+                                    self._stream())
+        self._check(rc, "dcbf_eval")
+        return dict(f=f, grad=grad, c=c, jac=jac, cl=cl, cu=cu, hess=hess)
+
+    def rollout(self, steps, x0, goal, leg, field=None, want_traj=True):
+        B, x0, goal, leg, field, _ = self._inputs(x0, goal, leg, field, None)
+        kw = dict(device=self.tdev)
+        xf = torch.empty((B, 5), dtype=torch.float64, **kw)
+        sd = torch.empty(B, dtype=torch.int32, **kw)
+        ni = torch.empty(B, dtype=torch.int32, **kw)
+        ti = torch.empty(B, dtype=torch.int32, **kw)
+        traj = torch.empty((B, steps, 8), dtype=torch.float64, **kw) if want_traj else None
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_rollout(self._ctx, B, int(steps), _ptr(x0), _ptr(goal), _ptr(leg), _ptr(field), _ptr(xf),
+                                       _ptr(sd), _ptr(ni), _ptr(ti), _ptr(traj), self._stream())
+        self._check(rc, "dcbf_rollout")
+        return dict(x_final=xf, steps_done=sd, n_infeasible=ni, total_iters=ti, traj=traj)
+
+    # ------------------------------------------------------------------------------------------------------
+    def set_fields_host(self, cir, elp=None):
+        cir = np.ascontiguousarray(np.zeros((1, 0, 3)) if cir is None else cir, dtype=np.float64)
+        if cir.ndim == 2:
+            cir = cir[None]
+        F = cir.shape[0]
+        elp = np.ascontiguousarray(np.zeros((F, 0, 5)) if elp is None else elp, dtype=np.float64)
+        if elp.ndim == 2:
+            elp = elp[None]
+        rc = self.lib.dcbf_set_fields_host(self._ctx, F, cir.shape[1], _ptr(cir) if cir.size else None, elp.shape[1],
+                                           _ptr(elp) if elp.size else None)
+        self._check(rc, "dcbf_set_fields_host")
+        self.F, self.Kc, self.Ke = F, int(cir.shape[1]), int(elp.shape[1])
+
+    def solve_host(self, x0, goal, leg, warm, field=None, last_u=None, out: SolveResult | None = None) -> SolveResult:
+        """numpy in / numpy out through dcbf_solve_host (copies + kernel + copies, synchronous)."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        x0 = f64(x0).reshape(-1, self.nx)
+        B = x0.shape[0]
+        goal = f64(np.broadcast_to(f64(goal).reshape(-1, 2), (B, 2)))
+        leg = None if leg is None else np.ascontiguousarray(np.broadcast_to(np.asarray(leg, dtype=np.int32).reshape(-1), (B,)))
+        field = None if field is None else np.ascontiguousarray(field, dtype=np.int32)
+        warm = f64(warm).reshape(B, self.nu)
+        last_u = None if last_u is None else f64(last_u).reshape(B, 2)
+        if out is None:
+            out = SolveResult(np.empty((B, self.nu)), np.empty((B, 3, self.nx)), None if self.dd else np.empty((B, 3, 3)),
+                              np.empty(B, np.int32), np.empty(B, np.int32), np.empty(B), np.empty(B), np.empty(B, np.uint8))
+        rc = self.lib.dcbf_solve_host(self._ctx, B, _ptr(x0), _ptr(goal), _ptr(leg), _ptr(field), _ptr(warm), _ptr(last_u),
+                                      _ptr(out.u), _ptr(out.x_plan), _ptr(out.p_plan), _ptr(out.status), _ptr(out.iters),
+                                      _ptr(out.obj), _ptr(out.viol), _ptr(out.close2goal))
+        self._check(rc, "dcbf_solve_host")
+        return out
+
+    def fp64_peak_tflops(self, repeats: int = 3) -> float:
+        return float(self.lib.dcbf_fp64_peak_tflops(self._ctx, repeats))

@@ -1,0 +1,346 @@
+// dcbf_kernels.cu -- sm_100a kernels and the C ABI of include/dcbf_mpc.h.
+//
+// Kernels (one problem per thread, FP64 CUDA-core pipe; no tensor cores: the KKT systems are 9x9 / 6x6):
+//   prep_fields_kernel   obstacle lists -> quadratic-form records (ellipse trig hoisted out of the solve)
+//   eval_kernel          K1: objective, gradient, rows, Jacobian, Lagrangian Hessian at given points
+//   solve_kernel         K1+K2: full interior-point solve per lane
+//   rollout_kernel       K3: plan -> apply -> re-plan closed loop per lane
+//   fp64_peak_kernel     dependent-free DFMA loop used as the roofline denominator
+// There is no CPU fallback anywhere in this file: every entry point launches on the context's device or fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "dcbf_lanes.cuh"
+
+using namespace dcbf;
+
+#ifndef DCBF_BLOCK
+#define DCBF_BLOCK 128
+#endif
+
+struct dcbf_ctx {
+    dcbf_params P;
+    Consts K;
+    int device;
+    int F, Kc, Ke;
+    double *cir_rec, *elp_rec;   // prepared fields (device)
+    int64_t launches;
+    char err[256];
+    // staging for the host-buffer entry points
+    void *h_pin; size_t h_pin_bytes;
+    void *d_buf; size_t d_buf_bytes;
+    double *d_cir_raw, *d_elp_raw; size_t raw_bytes;
+    cudaStream_t stream;
+};
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return DCBF_ERR_CUDA;                                                                       \
+        }                                                                                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void prep_fields_kernel(int F, int Kc, const double *__restrict__ cir, int Ke, const double *__restrict__ elp,
+                                   double *__restrict__ cir_rec, double *__restrict__ elp_rec) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < F * Kc) prep_circle(cir + 3 * (size_t)t, cir_rec + DCBF_CIR_REC * (size_t)t);
+    if (t < F * Ke) prep_ellipse(elp + 5 * (size_t)t, elp_rec + DCBF_ELP_REC * (size_t)t);
+}
+
+__global__ void __launch_bounds__(DCBF_BLOCK) solve_lip_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) solve_lip_lane(P, K, in, out, b);
+}
+__global__ void __launch_bounds__(DCBF_BLOCK) solve_dd_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) solve_dd_lane(P, K, in, out, b);
+}
+__global__ void __launch_bounds__(DCBF_BLOCK) eval_lip_kernel(dcbf_params P, Consts K, int B, BatchIn in, EvalPtrs ev) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) eval_lip_lane(P, K, in, ev, b);
+}
+__global__ void __launch_bounds__(DCBF_BLOCK) eval_dd_kernel(dcbf_params P, Consts K, int B, BatchIn in, EvalPtrs ev) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) eval_dd_lane(P, K, in, ev, b);
+}
+__global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, Consts K, int B, int steps, BatchIn in, RolloutOut out) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) rollout_lip_lane(P, K, in, out, steps, b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP64 peak microbenchmark: 8 independent DFMA chains per thread
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ===============================================================================================================
+// C ABI
+// ===============================================================================================================
+extern "C" {
+
+int dcbf_abi_version(void) { return DCBF_ABI_VERSION; }
+
+int dcbf_default_params(int formulation, dcbf_params *P) {
+    if (!P || formulation < 0 || formulation > 2) return DCBF_ERR_ARG;
+    memset(P, 0, sizeof(*P));
+    const double PI = 3.14159265358979323846;
+    P->formulation = formulation;
+    P->w_q = 1.0;
+    P->bvx_min = 0.4; P->bvx_max = 0.8; P->bvy_min = 0.15; P->leg_sq = 0.09; P->ang_max = PI / 16.0;
+    P->detect_sq = 16.0;
+    P->tol = 1e-8; P->constr_viol_tol = 1e-4; P->mu_init = 0.1;
+    // The reference caps Ipopt's L-BFGS iterations at 20 / 30 / 40 (MPC_LIP_sig_step.py:269, MPC_LIP_modi.py:287,
+    // MPC_DD_sig_step.py:183).  Those caps are not comparable with exact-Hessian Newton iterations; the default here
+    // is a safety cap only (DESIGN.md "iteration caps").
+    P->max_iter = 200;
+    if (formulation == DCBF_SIG_STEP) {
+        P->w_p = 2.0; P->w_r = 15.0; P->gamma = 0.4; P->s_turn = 0.014 * 180.0 / PI; P->bvy_max = 0.3;
+        P->goal_shift = 1; P->close_radius = 0.35; P->close_any = 1;
+    } else if (formulation == DCBF_MODI) {
+        P->w_p = 0.0; P->w_r = 50.0; P->gamma = 0.2; P->s_turn = 0.024 * 180.0 / PI; P->bvy_max = 0.35;
+        P->has_fen = 1; P->select_obs = 1; P->goal_shift = 1; P->close_radius = 0.15;
+    } else {
+        P->w_p = 0.0; P->w_r = 50.0; P->gamma = 0.2; P->s_turn = 0.024 * 180.0 / PI; P->bvy_max = 0.35;
+        P->has_fen = 1; P->w_t = 2.0; P->close_radius = 0.35;
+    }
+    return DCBF_OK;
+}
+
+int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
+    if (!params || !out) return DCBF_ERR_ARG;
+    if (params->formulation < 0 || params->formulation > 2) return DCBF_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DCBF_ERR_CUDA;
+    dcbf_ctx *ctx = new (std::nothrow) dcbf_ctx();
+    if (!ctx) return DCBF_ERR_ARG;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->P = *params;
+    ctx->K = make_consts();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
+    *out = ctx;
+    return DCBF_OK;
+}
+
+void dcbf_destroy(dcbf_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *dcbf_last_error(const dcbf_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+int64_t dcbf_launch_count(const dcbf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dcbf_num_vars(const dcbf_ctx *ctx) { return !ctx ? DCBF_ERR_ARG : (ctx->P.formulation == DCBF_DD ? 6 : 9); }
+int dcbf_num_rows(const dcbf_ctx *ctx) {
+    if (!ctx) return DCBF_ERR_ARG;
+    const int K = ctx->Kc + ctx->Ke;
+    if (ctx->P.formulation == DCBF_DD) return 3 * (K + 1);
+    return 3 * (4 + K + (ctx->P.has_fen ? 1 : 0));
+}
+
+int dcbf_set_fields(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir_dev, int32_t Ke, const double *elp_dev, void *stream) {
+    if (!ctx || F < 1 || Kc < 0 || Ke < 0 || Kc > DCBF_MAX_OBS || Ke > DCBF_MAX_OBS) return DCBF_ERR_ARG;
+    if ((Kc > 0 && !cir_dev) || (Ke > 0 && !elp_dev)) return DCBF_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaFree(ctx->cir_rec)); CK(cudaFree(ctx->elp_rec));
+    ctx->cir_rec = ctx->elp_rec = nullptr;
+    CK(cudaMalloc(&ctx->cir_rec, sizeof(double) * DCBF_CIR_REC * (size_t)F * (Kc > 0 ? Kc : 1)));
+    CK(cudaMalloc(&ctx->elp_rec, sizeof(double) * DCBF_ELP_REC * (size_t)F * (Ke > 0 ? Ke : 1)));
+    const int n = F * (Kc > Ke ? Kc : Ke);
+    if (n > 0) {
+        prep_fields_kernel<<<(n + 255) / 256, 256, 0, st>>>(F, Kc, cir_dev, Ke, elp_dev, ctx->cir_rec, ctx->elp_rec);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    ctx->F = F; ctx->Kc = Kc; ctx->Ke = Ke;
+    return DCBF_OK;
+}
+
+static int grid_for(const dcbf_ctx *ctx, int B) {
+    int g = (B + DCBF_BLOCK - 1) / DCBF_BLOCK;
+    return g < 1 ? 1 : g;
+}
+
+int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+              const double *last_u, const double *z, const double *lambda, double *f, double *grad, double *c, double *jac,
+              double *cl, double *cu, double *hess, void *stream) {
+    if (!ctx || B < 0 || !x0 || !goal || !z) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    if (B == 0) return DCBF_OK;
+    CK(cudaSetDevice(ctx->device));
+    BatchIn in = {x0, goal, nullptr, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
+    EvalPtrs ev = {z, lambda, f, grad, c, jac, cl, cu, hess, dcbf_num_rows(ctx)};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->P.formulation == DCBF_DD) eval_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, ev);
+    else eval_lip_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, ev);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
+int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+               const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
+               int32_t *iters, double *obj, double *viol, uint8_t *close2goal, void *stream) {
+    if (!ctx || B < 0 || !x0 || !goal || !warm) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    if (B == 0) return DCBF_OK;
+    CK(cudaSetDevice(ctx->device));
+    BatchIn in = {x0, goal, warm, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
+    SolveOut out = {u, x_plan, p_plan, obj, viol, status, iters, close2goal};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->P.formulation == DCBF_DD) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
+    else solve_lip_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
+int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, const double *goal, const int32_t *leg,
+                 const int32_t *field, double *x_final, int32_t *steps_done, int32_t *n_infeasible, int32_t *total_iters,
+                 double *traj, void *stream) {
+    if (!ctx || B < 0 || steps < 1 || !x0 || !goal) return DCBF_ERR_ARG;
+    if (ctx->P.formulation == DCBF_DD) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    if (B == 0) return DCBF_OK;
+    CK(cudaSetDevice(ctx->device));
+    BatchIn in = {x0, goal, nullptr, nullptr, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
+    RolloutOut out = {x_final, traj, steps_done, n_infeasible, total_iters};
+    rollout_lip_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, (cudaStream_t)stream>>>(ctx->P, ctx->K, B, steps, in, out);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------------------------
+static int ensure_staging(dcbf_ctx *ctx, size_t bytes) {
+    if (ctx->h_pin_bytes < bytes) {
+        if (ctx->h_pin) CK(cudaFreeHost(ctx->h_pin));
+        ctx->h_pin = nullptr; ctx->h_pin_bytes = 0;
+        CK(cudaMallocHost(&ctx->h_pin, bytes));
+        ctx->h_pin_bytes = bytes;
+    }
+    if (ctx->d_buf_bytes < bytes) {
+        CK(cudaFree(ctx->d_buf));
+        ctx->d_buf = nullptr; ctx->d_buf_bytes = 0;
+        CK(cudaMalloc(&ctx->d_buf, bytes));
+        ctx->d_buf_bytes = bytes;
+    }
+    return DCBF_OK;
+}
+
+int dcbf_set_fields_host(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir_host, int32_t Ke, const double *elp_host) {
+    if (!ctx || F < 1 || Kc < 0 || Ke < 0 || Kc > DCBF_MAX_OBS || Ke > DCBF_MAX_OBS) return DCBF_ERR_ARG;
+    if ((Kc > 0 && !cir_host) || (Ke > 0 && !elp_host)) return DCBF_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(ctx->d_cir_raw)); CK(cudaFree(ctx->d_elp_raw));
+    ctx->d_cir_raw = ctx->d_elp_raw = nullptr;
+    const size_t cb = sizeof(double) * 3 * (size_t)F * Kc, eb = sizeof(double) * 5 * (size_t)F * Ke;
+    if (cb) { CK(cudaMalloc(&ctx->d_cir_raw, cb)); CK(cudaMemcpyAsync(ctx->d_cir_raw, cir_host, cb, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (eb) { CK(cudaMalloc(&ctx->d_elp_raw, eb)); CK(cudaMemcpyAsync(ctx->d_elp_raw, elp_host, eb, cudaMemcpyHostToDevice, ctx->stream)); }
+    int rc = dcbf_set_fields(ctx, F, Kc, ctx->d_cir_raw, Ke, ctx->d_elp_raw, ctx->stream);
+    if (rc != DCBF_OK) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DCBF_OK;
+}
+
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+                    const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
+                    int32_t *iters, double *obj, double *viol, uint8_t *close2goal) {
+    if (!ctx || B < 0 || !x0 || !goal || !warm) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    if (B == 0) return DCBF_OK;
+    CK(cudaSetDevice(ctx->device));
+    const bool dd = ctx->P.formulation == DCBF_DD;
+    const size_t nx = dd ? 3 : 5, nu = dd ? 6 : 15, b = (size_t)B;
+    // layout of the staging block: inputs first (one H2D copy), outputs after (one D2H copy)
+    size_t off = 0;
+    const size_t o_x0 = off; off = al(off + 8 * nx * b);
+    const size_t o_goal = off; off = al(off + 16 * b);
+    const size_t o_warm = off; off = al(off + 8 * nu * b);
+    const size_t o_lastu = off; off = al(off + 16 * b);
+    const size_t o_leg = off; off = al(off + 4 * b);
+    const size_t o_field = off; off = al(off + 4 * b);
+    const size_t in_bytes = off;
+    const size_t o_u = off; off = al(off + 8 * nu * b);
+    const size_t o_xp = off; off = al(off + 8 * 3 * nx * b);
+    const size_t o_pp = off; off = al(off + 8 * 9 * b);
+    const size_t o_obj = off; off = al(off + 8 * b);
+    const size_t o_viol = off; off = al(off + 8 * b);
+    const size_t o_st = off; off = al(off + 4 * b);
+    const size_t o_it = off; off = al(off + 4 * b);
+    const size_t o_cl = off; off = al(off + b);
+    const size_t total = off;
+    int rc = ensure_staging(ctx, total);
+    if (rc != DCBF_OK) return rc;
+    char *hp = (char *)ctx->h_pin, *dp = (char *)ctx->d_buf;
+    memcpy(hp + o_x0, x0, 8 * nx * b);
+    memcpy(hp + o_goal, goal, 16 * b);
+    memcpy(hp + o_warm, warm, 8 * nu * b);
+    if (last_u) memcpy(hp + o_lastu, last_u, 16 * b);
+    if (leg) memcpy(hp + o_leg, leg, 4 * b);
+    if (field) memcpy(hp + o_field, field, 4 * b);
+    CK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = dcbf_solve(ctx, B, (double *)(dp + o_x0), (double *)(dp + o_goal), leg ? (int32_t *)(dp + o_leg) : nullptr,
+                    field ? (int32_t *)(dp + o_field) : nullptr, (double *)(dp + o_warm), last_u ? (double *)(dp + o_lastu) : nullptr,
+                    (double *)(dp + o_u), (double *)(dp + o_xp), dd ? nullptr : (double *)(dp + o_pp), (int32_t *)(dp + o_st),
+                    (int32_t *)(dp + o_it), (double *)(dp + o_obj), (double *)(dp + o_viol), (uint8_t *)(dp + o_cl), ctx->stream);
+    if (rc != DCBF_OK) return rc;
+    CK(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (u) memcpy(u, hp + o_u, 8 * nu * b);
+    if (x_plan) memcpy(x_plan, hp + o_xp, 8 * 3 * nx * b);
+    if (p_plan && !dd) memcpy(p_plan, hp + o_pp, 8 * 9 * b);
+    if (obj) memcpy(obj, hp + o_obj, 8 * b);
+    if (viol) memcpy(viol, hp + o_viol, 8 * b);
+    if (status) memcpy(status, hp + o_st, 4 * b);
+    if (iters) memcpy(iters, hp + o_it, 4 * b);
+    if (close2goal) memcpy(close2goal, hp + o_cl, b);
+    return DCBF_OK;
+}
+
+double dcbf_fp64_peak_tflops(dcbf_ctx *ctx, int32_t repeats) {
+    if (!ctx) return -1.0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int r = 0; r < (repeats < 1 ? 1 : repeats) + 1; r++) {
+        cudaEventRecord(e0, ctx->stream);
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, ctx->stream);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        ctx->launches++;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) * 1e-12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// hostsim.cpp -- TEST-ONLY host build of the per-lane solver code (csrc/dcbf_core.cuh, dcbf_lanes.cuh).
+//
+// There is no GPU in the build container; this file compiles the exact lane functions the CUDA kernels call with g++
+// so that the algorithm can be debugged and checked against the oracle in the `-m "not gpu"` tests.  It is NOT part
+// of the product: nothing in the package loads it, the C ABI (libdcbf_mpc.so) has no CPU path, and no benchmark
+// number is ever taken from it.
+#include <cstdlib>
+#include <vector>
+
+#include "../../mujoco_lip_mpc_simulation_b200/csrc/dcbf_lanes.cuh"
+
+using namespace dcbf;
+
+static void prep(int F, int Kc, const double *cir, int Ke, const double *elp, std::vector<double> &cr, std::vector<double> &er) {
+    cr.assign((size_t)DCBF_CIR_REC * F * (Kc > 0 ? Kc : 1), 0.0);
+    er.assign((size_t)DCBF_ELP_REC * F * (Ke > 0 ? Ke : 1), 0.0);
+    for (int t = 0; t < F * Kc; t++) prep_circle(cir + 3 * (size_t)t, cr.data() + DCBF_CIR_REC * (size_t)t);
+    for (int t = 0; t < F * Ke; t++) prep_ellipse(elp + 5 * (size_t)t, er.data() + DCBF_ELP_REC * (size_t)t);
+}
+
+extern "C" {
+
+int hostsim_solve(const dcbf_params *P, int B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+                  int F, int Kc, const double *cir, int Ke, const double *elp, const double *warm, const double *last_u,
+                  double *u, double *x_plan, double *p_plan, int32_t *status, int32_t *iters, double *obj, double *viol,
+                  uint8_t *close2goal) {
+    std::vector<double> cr, er;
+    prep(F, Kc, cir, Ke, elp, cr, er);
+    const Consts K = make_consts();
+    BatchIn in = {x0, goal, warm, last_u, leg, field, cr.data(), er.data(), Kc, Ke};
+    SolveOut out = {u, x_plan, p_plan, obj, viol, status, iters, close2goal};
+    for (int b = 0; b < B; b++) {
+        if (P->formulation == DCBF_DD) solve_dd_lane(*P, K, in, out, b);
+        else solve_lip_lane(*P, K, in, out, b);
+    }
+    return 0;
+}
+
+int hostsim_eval(const dcbf_params *P, int B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+                 int F, int Kc, const double *cir, int Ke, const double *elp, const double *last_u, const double *z,
+                 const double *lambda, int m, double *f, double *grad, double *c, double *jac, double *cl, double *cu, double *hess) {
+    std::vector<double> cr, er;
+    prep(F, Kc, cir, Ke, elp, cr, er);
+    const Consts K = make_consts();
+    BatchIn in = {x0, goal, nullptr, last_u, leg, field, cr.data(), er.data(), Kc, Ke};
+    EvalPtrs ev = {z, lambda, f, grad, c, jac, cl, cu, hess, m};
+    for (int b = 0; b < B; b++) {
+        if (P->formulation == DCBF_DD) eval_dd_lane(*P, K, in, ev, b);
+        else eval_lip_lane(*P, K, in, ev, b);
+    }
+    return 0;
+}
+
+int hostsim_rollout(const dcbf_params *P, int B, int steps, const double *x0, const double *goal, const int32_t *leg,
+                    const int32_t *field, int F, int Kc, const double *cir, int Ke, const double *elp, double *x_final,
+                    int32_t *steps_done, int32_t *n_infeasible, int32_t *total_iters, double *traj) {
+    std::vector<double> cr, er;
+    prep(F, Kc, cir, Ke, elp, cr, er);
+    const Consts K = make_consts();
+    BatchIn in = {x0, goal, nullptr, nullptr, leg, field, cr.data(), er.data(), Kc, Ke};
+    RolloutOut out = {x_final, traj, steps_done, n_infeasible, total_iters};
+    for (int b = 0; b < B; b++) rollout_lip_lane(*P, K, in, out, steps, b);
+    return 0;
+}
+
+}  // extern "C"

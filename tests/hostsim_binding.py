@@ -1,0 +1,131 @@
+"""TEST-ONLY ctypes binding of tests/hostsim/libhostsim.so: the per-lane CUDA solver code compiled for the host so
+that the algorithm can be checked against the oracle without a GPU.  Not a product path (see hostsim.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "..", "mujoco_lip_mpc_simulation_b200", "csrc")
+
+
+class DcbfParams(C.Structure):
+    _fields_ = [("formulation", C.c_int32), ("max_iter", C.c_int32), ("select_obs", C.c_int32), ("goal_shift", C.c_int32),
+                ("has_fen", C.c_int32), ("close_any", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+                ("w_p", C.c_double), ("w_q", C.c_double), ("w_r", C.c_double), ("w_t", C.c_double),
+                ("gamma", C.c_double), ("s_turn", C.c_double),
+                ("bvx_min", C.c_double), ("bvx_max", C.c_double), ("bvy_min", C.c_double), ("bvy_max", C.c_double),
+                ("leg_sq", C.c_double), ("ang_max", C.c_double), ("detect_sq", C.c_double), ("close_radius", C.c_double),
+                ("tol", C.c_double), ("constr_viol_tol", C.c_double), ("mu_init", C.c_double)]
+
+
+FORMS = {"sig_step": 0, "modi": 1, "dd": 2}
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "hostsim", "libhostsim.so")
+        srcs = [os.path.join(_HERE, "hostsim", "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in ("dcbf_core.cuh", "dcbf_lanes.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["sh", os.path.join(_HERE, "hostsim", "build.sh")])
+        _LIB = C.CDLL(so)
+    return _LIB
+
+
+def default_params(form) -> DcbfParams:
+    """Python mirror of dcbf_default_params (csrc/dcbf_kernels.cu); checked against the C ABI in the gpu tests."""
+    import math
+    f = FORMS[form] if isinstance(form, str) else int(form)
+    P = DcbfParams()
+    P.formulation = f
+    P.w_q = 1.0
+    P.bvx_min, P.bvx_max, P.bvy_min, P.leg_sq, P.ang_max = 0.4, 0.8, 0.15, 0.09, math.pi / 16
+    P.detect_sq = 16.0
+    P.tol, P.constr_viol_tol, P.mu_init = 1e-8, 1e-4, 0.1
+    P.max_iter = 200
+    if f == 0:
+        P.w_p, P.w_r, P.gamma, P.s_turn, P.bvy_max = 2.0, 15.0, 0.4, 0.014 * 180 / math.pi, 0.3
+        P.goal_shift, P.close_radius, P.close_any = 1, 0.35, 1
+    elif f == 1:
+        P.w_p, P.w_r, P.gamma, P.s_turn, P.bvy_max = 0.0, 50.0, 0.2, 0.024 * 180 / math.pi, 0.35
+        P.has_fen, P.select_obs, P.goal_shift, P.close_radius = 1, 1, 1, 0.15
+    else:
+        P.w_p, P.w_r, P.gamma, P.s_turn, P.bvy_max = 0.0, 50.0, 0.2, 0.024 * 180 / math.pi, 0.35
+        P.has_fen, P.w_t, P.close_radius = 1, 2.0, 0.35
+    return P
+
+
+def _d(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, typ=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(typ))
+
+
+def _fields(cir, elp):
+    cir = _d(np.zeros((1, 0, 3)) if cir is None else cir)
+    if cir.ndim == 2:
+        cir = cir[None]
+    F = cir.shape[0]
+    elp = _d(np.zeros((F, 0, 5)) if elp is None else elp)
+    if elp.ndim == 2:
+        elp = elp[None]
+    return F, cir, elp
+
+
+def solve(P, x0, goal, leg, cir, elp, warm, field=None, last_u=None):
+    dd = P.formulation == 2
+    nx, nu = (3, 6) if dd else (5, 15)
+    x0 = _d(x0).reshape(-1, nx)
+    B = len(x0)
+    goal = _d(np.broadcast_to(np.asarray(goal, dtype=np.float64).reshape(-1, 2), (B, 2)))
+    leg = np.ascontiguousarray(np.broadcast_to(np.asarray(leg, dtype=np.int32), (B,)), dtype=np.int32)
+    F, cir, elp = _fields(cir, elp)
+    field = None if field is None else np.ascontiguousarray(field, dtype=np.int32)
+    warm, last_u = _d(warm).reshape(B, nu), _d(last_u)
+    u, xp, pp = np.zeros((B, nu)), np.zeros((B, 3, nx)), np.zeros((B, 3, 3))
+    obj, viol = np.zeros(B), np.zeros(B)
+    st, it, cl = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.uint8)
+    lib().hostsim_solve(C.byref(P), B, _p(x0), _p(goal), _p(leg, C.c_int32), _p(field, C.c_int32), F, cir.shape[1], _p(cir),
+                        elp.shape[1], _p(elp), _p(warm), _p(last_u), _p(u), _p(xp), _p(pp), _p(st, C.c_int32),
+                        _p(it, C.c_int32), _p(obj), _p(viol), _p(cl, C.c_uint8))
+    return dict(u=u, x_plan=xp, p_plan=pp, f=obj, status=st, iters=it, viol=viol, close2goal=cl.astype(bool))
+
+
+def evaluate(P, x0, goal, leg, cir, elp, z, lam=None, field=None, last_u=None):
+    dd = P.formulation == 2
+    nx, n = (3, 6) if dd else (5, 9)
+    x0 = _d(x0).reshape(-1, nx)
+    B = len(x0)
+    goal = _d(np.broadcast_to(np.asarray(goal, dtype=np.float64).reshape(-1, 2), (B, 2)))
+    leg = np.ascontiguousarray(np.broadcast_to(np.asarray(leg, dtype=np.int32), (B,)), dtype=np.int32)
+    F, cir, elp = _fields(cir, elp)
+    K = cir.shape[1] + elp.shape[1]
+    m = 3 * (K + 1) if dd else 3 * (4 + K + (1 if P.has_fen else 0))
+    field = None if field is None else np.ascontiguousarray(field, dtype=np.int32)
+    z, lam, last_u = _d(z).reshape(B, n), _d(lam), _d(last_u)
+    f, grad, c, jac = np.zeros(B), np.zeros((B, n)), np.zeros((B, m)), np.zeros((B, m, n))
+    cl, cu, hess = np.zeros((B, m)), np.zeros((B, m)), np.zeros((B, n, n))
+    lib().hostsim_eval(C.byref(P), B, _p(x0), _p(goal), _p(leg, C.c_int32), _p(field, C.c_int32), F, cir.shape[1], _p(cir),
+                       elp.shape[1], _p(elp), _p(last_u), _p(z), _p(lam), m, _p(f), _p(grad), _p(c), _p(jac), _p(cl), _p(cu), _p(hess))
+    return dict(f=f, grad=grad, c=c, jac=jac, cl=cl, cu=cu, hess=hess)
+
+
+def rollout(P, steps, x0, goal, leg, cir, elp, field=None):
+    x0 = _d(x0).reshape(-1, 5)
+    B = len(x0)
+    goal = _d(np.broadcast_to(np.asarray(goal, dtype=np.float64).reshape(-1, 2), (B, 2)))
+    leg = np.ascontiguousarray(np.broadcast_to(np.asarray(leg, dtype=np.int32), (B,)), dtype=np.int32)
+    F, cir, elp = _fields(cir, elp)
+    field = None if field is None else np.ascontiguousarray(field, dtype=np.int32)
+    xf, traj = np.zeros((B, 5)), np.zeros((B, steps, 8))
+    sd, ni, ti = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    lib().hostsim_rollout(C.byref(P), B, steps, _p(x0), _p(goal), _p(leg, C.c_int32), _p(field, C.c_int32), F, cir.shape[1],
+                          _p(cir), elp.shape[1], _p(elp), _p(xf), _p(sd, C.c_int32), _p(ni, C.c_int32), _p(ti, C.c_int32), _p(traj))
+    return dict(x_final=xf, steps_done=sd, n_infeasible=ni, total_iters=ti, traj=traj)
