@@ -1,0 +1,187 @@
+"""ORACLE (test infrastructure) -- freeze golden vectors from the *reference's own code*.
+
+Run in the build container only (needs /root/reference):   python -m oracle.gen_golden
+Writes small .npz fixtures under tests/golden/:
+
+  callbacks_{sig_step,modi,dd}.npz
+      Random points pushed through the reference classes' LIP_Prob.objective / gradient / constraints / jacobian
+      (MPC_LIP_sig_step.py:372-496, MPC_LIP_modi.py:430-583, MPC_DD_sig_step.py:351-477) and through
+      MPCCBF.solveMPCCBF with a recording cyipopt stub, which pins the bound vectors cl/cu, the detour goal, the
+      warm-start rule and (modi) the obstacle selection exactly as the reference builds them.
+  solves_{sig_step,modi,dd}.npz
+      Optima for scenarios of the bench distribution: solved by the C oracle, then *verified with the reference's
+      callbacks*: feasibility of every row and the KKT residual  min_{lam>=0} |grad f - J_act^T lam| / |grad f|
+      evaluated with the reference's gradient and Jacobian at the returned point.  Only verified KKT points
+      (and certified-infeasible problems) are kept.  Real cyipopt is not installed, so Ipopt's own iterates are
+      not part of the pin ("cyipopt unavailable").
+  config1_closed_loop.npz
+      The reference's __main__ scenario (MPC_LIP_sig_step.py:553-575), 5 closed-loop re-plans.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+from scipy.optimize import nnls
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mujoco_lip_mpc_simulation_b200 import scenarios  # noqa: E402
+from oracle import c_oracle, lip_np, ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _lists(a):
+    return [list(map(float, r)) for r in a]
+
+
+def gen_callbacks(form: str, n_cases: int, seed: int):
+    rng = np.random.default_rng(seed)
+    mod = ref_loader.load({"sig_step": "MPC_LIP_sig_step", "modi": "MPC_LIP_modi", "dd": "MPC_DD_sig_step"}[form])
+    rec = {k: [] for k in ("xk", "goal", "leg", "cir", "elp", "u", "last_u", "f", "grad", "c", "jac", "cl", "cu",
+                           "goal_eff", "u0", "warm_in", "sel_c", "sel_e")}
+    sc = scenarios.make_batch(form, n_cases, seed=seed, n_fields=n_cases, num_obs=4 if form == "sig_step" else 6)
+    for b in range(n_cases):
+        cir, elp = sc.cir[sc.field[b]], sc.elp[sc.field[b]]
+        xk, goal, leg = sc.x0[b], sc.goal[b], int(sc.leg[b])
+        if form == "sig_step":
+            planner = mod.MPCCBF([list(goal)], cir, cir, [-0.5, 10.5])
+            guess = None if b % 2 == 0 else [xk + rng.normal(size=5) * 0.05 for _ in range(3)]
+            planner.solveMPCCBF(np.matrix(xk).T, leg, guess)
+            warm_in = np.zeros(15) if guess is None else np.concatenate(guess)
+        elif form == "modi":
+            planner = mod.MPCCBF([list(goal)], _lists(cir), _lists(cir), _lists(elp), _lists(elp), [-0.5, 10.5])
+            planner.select_obs(np.matrix(xk).T)
+            warm_in = np.tile(xk, 3) + rng.normal(size=15) * 0.05
+            planner.solveMPCCBF(np.matrix(xk).T, leg, warm_in)
+        else:
+            planner = mod.MPCCBF([list(goal)], _lists(cir), _lists(cir), _lists(elp), _lists(elp), [-0.5, 10.5])
+            warm_in = sc.warm[b]
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                planner.solveMPCCBF(np.matrix(xk).T, warm_in, list(sc.last_u[b]))
+        LP = ref_loader.LAST_PROBLEM
+        prob = LP["obj"]
+        n = LP["n"]
+        u = LP["u0"] + rng.normal(size=n) * (0.05 if form == "dd" else 0.2)
+        rec["xk"].append(xk); rec["goal"].append(goal); rec["leg"].append(leg)
+        rec["cir"].append(cir); rec["elp"].append(elp); rec["u"].append(u)
+        rec["last_u"].append(sc.last_u[b] if sc.last_u is not None else np.zeros(2))
+        rec["f"].append(float(prob.objective(u)))
+        rec["grad"].append(np.ravel(np.asarray(prob.gradient(u), dtype=np.float64)))
+        c = np.ravel(np.asarray(prob.constraints(u), dtype=np.float64))
+        J = np.asarray(prob.jacobian(u), dtype=np.float64).reshape(len(c), n)
+        # pad rows to the unselected row count so that the arrays stack (modi selection drops rows)
+        rec["c"].append(c); rec["jac"].append(J)
+        rec["cl"].append(LP["cl"]); rec["cu"].append(LP["cu"])
+        rec["goal_eff"].append(LP["goal"]); rec["u0"].append(LP["u0"]); rec["warm_in"].append(warm_in)
+        if form == "modi":
+            rec["sel_c"].append(np.array([any(np.allclose(o, s) for s in planner.sel_cir) for o in cir]))
+            rec["sel_e"].append(np.array([any(np.allclose(o, s) for s in planner.sel_elp) for o in elp]))
+        else:
+            rec["sel_c"].append(np.ones(len(cir), bool)); rec["sel_e"].append(np.ones(len(elp), bool))
+    out = {}
+    for k, v in rec.items():
+        try:
+            out[k] = np.stack([np.asarray(x) for x in v])
+        except ValueError:
+            out[k] = np.array(v, dtype=object)
+    np.savez_compressed(os.path.join(OUT, f"callbacks_{form}.npz"), **out, allow_pickle=True)
+    print(form, "callbacks:", n_cases, "cases")
+
+
+def kkt_with_reference(form, prob_obj, u, cl, cu):
+    """feasibility + KKT residual of u, evaluated with the reference's own callbacks."""
+    g = np.ravel(np.asarray(prob_obj.gradient(u), dtype=np.float64))
+    c = np.ravel(np.asarray(prob_obj.constraints(u), dtype=np.float64))
+    J = np.asarray(prob_obj.jacobian(u), dtype=np.float64).reshape(len(c), len(u))
+    viol = max(0.0, float(np.max(cl - c)), float(np.max(np.where(np.isfinite(cu), c - cu, -1.0))))
+    lo = np.isfinite(cl) & (c - cl <= 1e-6)
+    hi = np.isfinite(cu) & (cu - c <= 1e-6)
+    A = np.concatenate([J[lo], -J[hi]]).T
+    if A.shape[1] == 0:
+        return viol, float(np.linalg.norm(g) / max(1.0, np.linalg.norm(g)))
+    _, rn = nnls(A, g, maxiter=2000)
+    return viol, float(rn / max(1.0, np.linalg.norm(g)))
+
+
+def gen_solves(form: str, n_cases: int, seed: int):
+    mod = ref_loader.load({"sig_step": "MPC_LIP_sig_step", "modi": "MPC_LIP_modi", "dd": "MPC_DD_sig_step"}[form])
+    sc = scenarios.make_batch(form, n_cases, seed=seed, n_fields=n_cases)
+    P = c_oracle.params(form, max_iter=500)
+    elp = sc.elp if sc.elp.shape[1] else None
+    res = c_oracle.solve_batch(P, sc.x0, sc.goal, sc.leg, sc.cir, elp, sc.warm, field=sc.field, last_u=sc.last_u, threads=8)
+    keep, kkt, viol = [], [], []
+    for b in range(n_cases):
+        cir, e = sc.cir[sc.field[b]], sc.elp[sc.field[b]]
+        xk, goal, leg = sc.x0[b], sc.goal[b], int(sc.leg[b])
+        # build the reference problem object exactly as the reference does (recording stub; the SLSQP result is unused)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            if form == "sig_step":
+                planner = mod.MPCCBF([list(goal)], cir, cir, [-0.5, 10.5])
+                planner.solveMPCCBF(np.matrix(xk).T, leg, None)
+            elif form == "modi":
+                planner = mod.MPCCBF([list(goal)], _lists(cir), _lists(cir), _lists(e), _lists(e), [-0.5, 10.5])
+                planner.select_obs(np.matrix(xk).T)
+                planner.solveMPCCBF(np.matrix(xk).T, leg, sc.warm[b])
+            else:
+                planner = mod.MPCCBF([list(goal)], _lists(cir), _lists(cir), _lists(e), _lists(e), [-0.5, 10.5])
+                planner.solveMPCCBF(np.matrix(xk).T, sc.warm[b], list(sc.last_u[b]))
+        LP = ref_loader.LAST_PROBLEM
+        if res["status"][b] == 0:
+            v, r = kkt_with_reference(form, LP["obj"], res["u"][b], LP["cl"], LP["cu"])
+            if form == "dd":
+                v = max(v, float(np.max(np.asarray(LP["lb"]) - res["u"][b])), float(np.max(res["u"][b] - np.asarray(LP["ub"]))))
+            ok = v <= 1e-6 and r <= 1e-5
+        elif res["status"][b] == 2:
+            v, r, ok = float(res["viol"][b]), np.nan, True
+        else:
+            v, r, ok = np.nan, np.nan, False
+        keep.append(ok); kkt.append(r); viol.append(v)
+    keep = np.array(keep)
+    print(form, "solves: kept", int(keep.sum()), "of", n_cases, "| status", {int(k): int((res['status'][keep] == k).sum()) for k in np.unique(res['status'][keep])},
+          "| max kkt", np.nanmax(np.array(kkt)[keep & (res['status'] == 0)]))
+    sel = np.where(keep)[0]
+    np.savez_compressed(os.path.join(OUT, f"solves_{form}.npz"),
+                        x0=sc.x0[sel], goal=sc.goal[sel], leg=sc.leg[sel], cir=sc.cir[sc.field[sel]], elp=sc.elp[sc.field[sel]],
+                        warm=sc.warm[sel], last_u=(sc.last_u[sel] if sc.last_u is not None else np.zeros((len(sel), 2))),
+                        u=res["u"][sel], p_plan=res["p_plan"][sel], x_plan=res["x_plan"][sel], f=res["f"][sel],
+                        status=res["status"][sel], viol_ref=np.array(viol)[sel], kkt_ref=np.array(kkt)[sel])
+
+
+def gen_config1():
+    sc = scenarios.config1()
+    P = c_oracle.params("sig_step", max_iter=500)
+    mod = ref_loader.load("MPC_LIP_sig_step")
+    planner = mod.MPCCBF([[10, 10]], sc.cir[0], sc.cir[0], [-0.5, 10.5])
+    state, leg, guess = sc.x0[0].copy(), 1, None
+    rows = []
+    for _ in range(5):
+        u0 = lip_np.sig_step_warm_start(state, guess)
+        r = c_oracle.solve(P, state, [10, 10], leg, sc.cir[0], None, u0)
+        planner.solveMPCCBF(np.matrix(state).T, leg, guess)   # records the reference's own problem object
+        LP = ref_loader.LAST_PROBLEM
+        assert np.allclose(LP["u0"], u0)
+        v, k = kkt_with_reference("sig_step", LP["obj"], r["u"], LP["cl"], LP["cu"])
+        rows.append(dict(state=state.copy(), leg=leg, u0=u0, p0=r["p_plan"][0].copy(), f=r["f"], x_plan=r["x_plan"].copy(),
+                         status=r["status"], viol_ref=v, kkt_ref=k))
+        guess = [r["x_plan"][0], r["x_plan"][1], r["x_plan"][2]]
+        state, leg = r["x_plan"][0].copy(), -leg
+    np.savez_compressed(os.path.join(OUT, "config1_closed_loop.npz"), cir=sc.cir[0],
+                        **{k: np.array([row[k] for row in rows]) for k in rows[0]})
+    print("config1:", [np.round(r["p0"], 6).tolist() for r in rows], "max kkt", max(r["kkt_ref"] for r in rows))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    for form, seed in (("sig_step", 101), ("modi", 102), ("dd", 103)):
+        gen_callbacks(form, 24, seed)
+    gen_config1()
+    for form, seed in (("sig_step", 201), ("modi", 202), ("dd", 203)):
+        gen_solves(form, 96, seed)
