@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- D-CBF ALIP MPC solves/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+A "step" is one pass of the hot path (dcbf_solve: problem assembly + interior-point solve) over one batch of
+synthetic scenarios.  Workload at every N: BASELINE.json configs[1] -- the sig_step ALIP D-CBF MPC batched over
+4096 random initial states / obstacle layouts per GPU (K = 6 circles, cold start).  With
+N GPUs every rank owns its own 4096-scenario batch (weak scaling, no data-path collective); `value` is the whole-job
+rate = N * 4096 * steps / max-over-ranks(device time).
+
+  value      inputs resident in HBM, CUDA-event time of the solve kernel launches only (L2 flushed between steps)
+  e2e        the same batch through the host-buffer C-ABI call dcbf_solve_host: pinned staging, H2D copy, kernel,
+             D2H copy of the full result (u, plans, status, ...) every step
+  roofline   FP64-pipe roofline of solve_lip_kernel: algorithmic flop = sum_i iters_i * F_iter (SURVEY.md 8(d) formula)
+             over the measured kernel time, against the FP64 DFMA peak measured on this GPU by dcbf_fp64_peak_tflops
+             (MEASURED_PEAKS.json carries no FP64 figure); `hbm` sub-object: batch I/O bytes / time vs measured HBM copy
+  cpu_baseline  the oracle's C port (oracle/dcbf_oracle.c) on all host threads over the same 4096 scenarios
+
+`--impl reference` times the reference's CPU path: the reference is Python + cyipopt (not installable here: Ipopt/HSL
+absent, no network), so per the task contract the arm runs the oracle port on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "configs[1]: sig_step ALIP D-CBF MPC, 4096 random states/obstacle layouts per GPU (K=6 circles, cold start)"
+BATCH = 4096
+SEED = 0
+
+
+def f_iter(n: int, m: int, m_nl: int, m_b: int, kc: int, ke: int, form: str) -> float:
+    """Algorithmic flop per interior-point iteration, SURVEY.md 8(d) (canonical formula, evaluated not re-derived)."""
+    f_roll, f_step = (60, 6) if form == "dd" else (240, 30 if form == "sig_step" else 36)
+    f_eval = f_roll + 130 + 3 * f_step + 3 * (14 * kc + 26 * ke)
+    return (f_eval + 4 * m * n + m * n * n + m_nl * n * n + 6 * n * n + n ** 3 / 3 + 4 * n * n + 12 * (m + m_b)
+            + 1.3 * (0.6 * f_eval + 2 * m))
+
+
+F_ITER_SIG_K6 = f_iter(9, 30, 27, 0, 6, 0, "sig_step")   # = 8455
+
+
+def io_bytes_per_solve(kc: int) -> int:
+    """batch I/O of one sig_step solve: x0, goal, warm, leg, field + the obstacle records read + all outputs."""
+    return (5 + 2 + 15) * 8 + 4 + 4 + 24 * kc + (15 + 15 + 9 + 1 + 1) * 8 + 4 + 4 + 1
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port, all host threads), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mujoco_lip_mpc_simulation_b200 import scenarios
+    from oracle import c_oracle
+    cores = os.cpu_count() or 1
+    sample = 1024
+    sc = scenarios.make_batch("sig_step", BATCH, seed=SEED)
+    P = c_oracle.params("sig_step", max_iter=300)
+    sl = slice(0, sample)
+
+    def step():
+        return c_oracle.solve_batch(P, sc.x0[sl], sc.goal[sl], sc.leg[sl], sc.cir, None, sc.warm[sl], field=sc.field[sl], threads=cores)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "D-CBF ALIP MPC solves/sec", "value": val, "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_per_step": sample},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": f"first {sample} scenarios of the workload per step, oracle/dcbf_oracle.c on {cores} threads "
+                                       "(reference = Python callbacks + cyipopt/Ipopt/MA57, not installable: no Ipopt, no network)"},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also report large-batch throughput (65536 / 1M scenarios)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from mujoco_lip_mpc_simulation_b200 import scenarios
+    from mujoco_lip_mpc_simulation_b200.batch import DcbfSolver, SolveResult
+    from mujoco_lip_mpc_simulation_b200.sharding import max_over_ranks, sum_over_ranks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+
+    # ---- workload: each rank owns its own 4096-scenario batch (weak scaling) --------------------------------------
+    sc = scenarios.make_batch("sig_step", BATCH, seed=SEED + rank)
+    solver = DcbfSolver("sig_step", device=local)
+    solver.set_fields(sc.cir)
+    t = lambda a, dt: torch.as_tensor(a, dtype=dt, device=dev)  # noqa: E731
+    x0, goal, warm = t(sc.x0, torch.float64), t(sc.goal, torch.float64), t(sc.warm, torch.float64)
+    leg, field = t(sc.leg, torch.int32), t(sc.field, torch.int32)
+    B = BATCH
+    out = SolveResult(torch.empty((B, 15), dtype=torch.float64, device=dev), torch.empty((B, 3, 5), dtype=torch.float64, device=dev),
+                      torch.empty((B, 3, 3), dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+                      torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.float64, device=dev),
+                      torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.uint8, device=dev))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def device_step(ev0, ev1):
+        flush.zero_()                      # L2 flush between timed iterations (inputs are far smaller than L2)
+        ev0.record()
+        solver.solve_into(B, x0, goal, leg, field, warm, None, out)
+        ev1.record()
+
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(args.warmup):
+        device_step(w0, w1)
+    torch.cuda.synchronize()
+    fp64_peak = solver.fp64_peak_tflops(3)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- timed region 1: device-resident --------------------------------------------------------------------------
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = solver.launches
+    for e0, e1 in evs:
+        device_step(e0, e1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = solver.launches - l0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    dev_ms = max_over_ranks(float(sum(step_ms)), dev)
+    iters = out.iters.cpu().numpy().astype(np.int64)
+    status = out.status.cpu().numpy()
+    flop_per_step = float(iters.sum()) * F_ITER_SIG_K6
+
+    # ---- timed region 2: end to end through the host-buffer C-ABI call ----------------------------------------------
+    solver.set_fields_host(sc.cir)
+    hres = solver.solve_host(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)      # allocates staging once
+    for _ in range(2):
+        solver.solve_host(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field, out=hres)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solver.solve_host(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field, out=hres)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert np.array_equal(hres.status, status), "host-buffer path and device path disagree"
+    h2d = B * ((5 + 2 + 15 + 2) * 8 + 4 + 4)
+    d2h = B * ((15 + 15 + 9 + 1 + 1) * 8 + 4 + 4 + 1)
+
+    # ---- p50 single-solve latency (B = 1, launch to result, host buffers) ------------------------------------------------
+    lat = []
+    one = solver.solve_host(sc.x0[:1], sc.goal[:1], sc.leg[:1], sc.warm[:1], field=sc.field[:1])
+    for i in range(200):
+        j = i % B
+        t0 = time.perf_counter()
+        solver.solve_host(sc.x0[j:j + 1], sc.goal[j:j + 1], sc.leg[j:j + 1], sc.warm[j:j + 1], field=sc.field[j:j + 1], out=one)
+        lat.append((time.perf_counter() - t0) * 1e6)
+
+    extra = {}
+    if args.sweep and rank == 0:
+        for form, Bs in (("sig_step", 65536), ("sig_step", 1 << 20), ("modi", 65536), ("dd", 65536)):
+            s2 = scenarios.make_batch(form, Bs, seed=SEED + 1)
+            sv = DcbfSolver(form, device=local)
+            sv.set_fields(s2.cir, s2.elp if s2.elp.shape[1] else None)
+            a = [t(s2.x0, torch.float64), t(s2.goal, torch.float64), t(s2.leg, torch.int32), t(s2.warm, torch.float64)]
+            lu = None if s2.last_u is None else t(s2.last_u, torch.float64)
+            fld = t(s2.field, torch.int32)
+            best = 1e9
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                flush.zero_()
+                e0.record()
+                r = sv.solve(a[0], a[1], a[2], a[3], field=fld, last_u=lu)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            extra[f"{form}_{Bs}"] = {"solves_per_s": Bs / (best * 1e-3), "ms": best, "mean_iters": float(r.iters.float().mean())}
+
+    # ---- CPU baseline (rank 0, N = 1 only): oracle port on all host threads over the same 4096 scenarios ------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle
+        cores = os.cpu_count() or 1
+        P = c_oracle.params("sig_step", max_iter=300)
+        t0 = time.perf_counter()
+        ref = c_oracle.solve_batch(P, sc.x0, sc.goal, sc.leg, sc.cir, None, sc.warm, field=sc.field, threads=cores)
+        dt = time.perf_counter() - t0
+        agree_cls = float(np.mean((status == 2) == (ref["status"] == 2)))
+        both = (status == 0) & (ref["status"] == 0)
+        dp = np.abs(out.p_plan.cpu().numpy() - ref["p_plan"]).reshape(B, -1).max(axis=1)
+        cpu = {"value": B / dt, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"the full {B}-scenario workload once, oracle/dcbf_oracle.c (C restatement, FD Hessian) on {cores} threads",
+               "agreement": {"status_class": agree_cls, "solution_1e-4": float(np.mean(dp[both] <= 1e-4)), "both_converged": int(both.sum())}}
+
+    total_solves = sum_over_ranks(float(B * args.steps), dev)
+    if rank == 0:
+        dev_s = dev_ms * 1e-3
+        kernel_s = float(np.mean(step_ms)) * 1e-3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        achieved_tf = flop_per_step / kernel_s * 1e-12
+        io_gbs = B * io_bytes_per_solve(6) / kernel_s * 1e-9
+        line = {
+            "metric": "D-CBF ALIP MPC solves/sec", "value": total_solves / dev_s, "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "formulation": "sig_step", "n_circles": 6, "seed": SEED,
+                       "l2": "flushed between timed steps (256 MiB memset)", "max_iter": int(solver.P.max_iter)},
+            "e2e": {"value": total_solves / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "p50_solve_us": float(np.median(lat)), "p95_solve_us": float(np.percentile(lat, 95)),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                         "peak_source": "measured on this GPU by dcbf_fp64_peak_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
+                         "flop_per_iter": F_ITER_SIG_K6, "iters_per_step": int(iters.sum()),
+                         "hbm": {"achieved": io_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": io_gbs / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+            "iters": {"mean": float(iters.mean()), "p50": float(np.median(iters)), "p99": float(np.percentile(iters, 99)), "max": int(iters.max())},
+            "status_hist": {str(int(k)): int((status == k).sum()) for k in np.unique(status)},
+            "clocks": sampler.summary(),
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if extra:
+            line["sweep"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
