@@ -178,8 +178,57 @@ def gen_config1():
     print("config1:", [np.round(r["p0"], 6).tolist() for r in rows], "max kkt", max(r["kkt_ref"] for r in rows))
 
 
+def gen_helpers():
+    """closed-form helpers of the call surface, straight from the reference classes."""
+    import types
+    rng = np.random.default_rng(7)
+    sig = ref_loader.load("MPC_LIP_sig_step")
+    dd = ref_loader.load("MPC_DD_sig_step")
+    obs = np.array([[1, 1, 0.82]])
+    ps = sig.MPCCBF([[10, 10]], obs, obs, [-0.5, 10.5])
+    pd = dd.MPCCBF([[10, 10]], obs, obs, [], [], [-0.5, 10.5])
+    out = {}
+    pos, vel, hd, gp, tr = rng.normal(size=2), rng.normal(size=2), 0.3, np.array([0.13, -0.2, 0.1]), 0.25
+    xn, traj = ps.get_next_states(pos, vel, hd, gp, tr)
+    out.update(gns_in=np.concatenate([pos, vel, [hd], gp, [tr]]), gns_x=xn, gns_traj=traj)
+    out["alip_des_vel"] = np.array([ps.alip_des_vel(0.7, 1), ps.alip_des_vel(0.5, -1)])
+    xs, vd = rng.normal(size=5), rng.normal(size=2)
+    out.update(cfv_in=np.concatenate([xs, vd]), cfv_out=ps.cal_foot_with_veldes(xs, vd))
+    u5 = rng.normal(size=5)
+    out.update(sfd_in=np.concatenate([xs, u5]), sfd_out=np.ravel(ps.solve_footdisp(np.matrix(xs).T, np.matrix(u5).T)))
+    out.update(xtd_in=np.concatenate([xs, gp]), xtd_out=ps.xk_track_det(xs, gp, 0.4))
+    hl = rng.normal(size=12) * 0.2
+    out.update(tube_in=hl, tube_sig=ps.tube_func(hl, 0.05), tube_dd=pd.tube_func(hl, 0.05))
+    pdz = rng.normal(size=2)
+    out.update(cfp_in=np.concatenate([xs, pdz]), cfp_out=pd.cal_foot_with_posdes(xs, pdz))
+    # ALIP closed form: the reference module imports robot-specific files that are broken / irrelevant here
+    for name in ("fromFROST", "forwardKinematics", "helper", "pdb"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_dcbf_ref_alip", ref_loader.REFERENCE_ROOT + "/ALIP_plan/planner.py")
+    alip_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(alip_mod)
+    prm = types.SimpleNamespace(H=1.0, T=0.4, m=45.0)
+    al = alip_mod.ALIP(prm)
+    al.DRS_motion_int = lambda a, b: (np.zeros(2), np.zeros(2))   # amplitudes are 0 (planner.py:47-50); idqp never exists
+    x0, y0 = np.array([0.05, 2.0]), np.array([0.1, -1.0])
+    xt, yt = al.getTimedState(x0, y0, 0.1)
+    Ly, Lx = al.AMprediction(xt, yt, 0.1)
+    st_r = al.computeStepping(np.array([0.1, 0.1]), Ly, Lx, 0.5, 1)
+    st_l = al.computeStepping(np.array([0.1, -0.1]), Ly, Lx, 0.5, -1)
+    out.update(alip_in=np.concatenate([x0, y0, [0.1]]), alip_xt=xt, alip_yt=yt, alip_am=np.array([Ly, Lx]),
+               alip_step_r=np.array(st_r, dtype=float), alip_step_l=np.array(st_l, dtype=float),
+               alip_reg=np.array([al.regulate_lateral_step(1, 0.05), al.regulate_lateral_step(1, 0.5), al.regulate_lateral_step(-1, -0.05),
+                                  al.regulate_lateral_step(-1, -0.3), al.regulate_lateral_step(0, 0.7)]))
+    np.savez_compressed(os.path.join(OUT, "helpers.npz"), **out)
+    print("helpers:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    gen_helpers()
+    if "--helpers-only" in sys.argv:
+        sys.exit(0)
     for form, seed in (("sig_step", 101), ("modi", 102), ("dd", 103)):
         gen_callbacks(form, 24, seed)
     gen_config1()

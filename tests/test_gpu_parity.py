@@ -205,9 +205,10 @@ def test_rollout_matches_oracle_closed_loop(gpu):
             if o["status"] != 0 or traj[b, k, 7] != 0:
                 break   # after a non-converged / infeasible re-plan the two chains may legitimately part
             total += 1
-            agree += int(np.abs(traj[b, k, :5] - o["x_plan"][0]).max() <= POS_TOL)
-            if o["close2goal"]:
-                break
+            same = np.abs(traj[b, k, :5] - o["x_plan"][0]).max() <= POS_TOL
+            agree += int(same)
+            if o["close2goal"] or not same:
+                break   # a different local optimum at one step makes every later step a different problem
             guess = list(o["x_plan"])
             state, leg = o["x_plan"][0].copy(), -leg
     assert total > 100 and agree / total >= 0.99
