@@ -21,6 +21,9 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#ifdef DCBF_TRACE
+#include <stdio.h>
+#endif
 
 #include "../../include/dcbf_mpc.h"
 
@@ -180,7 +183,8 @@ DCBF_HD RowW row_full(const RowCtl &ctl, Acc<N> &A, LogAcc &LA, double c, double
     A.vmax = dmax(A.vmax, fabs(v));
     A.nrows++;
     if (ctl.phase == PH_RESTO) {
-        o.sig = v != 0.0 ? 1.0 : 0.0; o.w1 = v; o.binv = 0.0; o.y = 0.0;
+        // Newton on 0.5*sum v^2: Gauss-Newton term (sig) plus the curvature term v * Hess(c_r) (carried by y)
+        o.sig = v != 0.0 ? 1.0 : 0.0; o.w1 = v; o.binv = 0.0; o.y = v;
         return o;
     }
     const double lr = LO ? relax_lo(lo) : 0.0, hr = HI ? relax_hi(hi) : 0.0;
@@ -498,7 +502,7 @@ DCBF_HD void lip_full_step(const Consts &k, const dcbf_params &P, const Problem 
     constexpr int kn = I + 1;
     constexpr int NF = 2 * (I + 1), NT = I + 1;
     const double INF = 1e300;
-    const bool hess = (MODE == MODE_EVAL) || ctl.phase == PH_MAIN;
+    const bool hess = true;   // restoration uses the curvature of the violated rows too (objective scaled by sf = 0)
     // ---- objective at node kn -------------------------------------------------------------------------------
     {
         const double w = P.w_q + (I == 0 ? P.w_p : 0.0);
@@ -815,9 +819,40 @@ struct LipModel {
         acc_reset(A);
         LA.sum = 0.0; LA.prod = 1.0; LA.cnt = 0;
         lip_rollout(k, pb.x0, S.z, nd);
-        lip_full_step<0, MODE_SOLVE, KT>(k, P, pb, nd, S.z, S.sf, ctl, R, A, LA, nullptr);
-        lip_full_step<1, MODE_SOLVE, KT>(k, P, pb, nd, S.z, S.sf, ctl, R, A, LA, nullptr);
-        lip_full_step<2, MODE_SOLVE, KT>(k, P, pb, nd, S.z, S.sf, ctl, R, A, LA, nullptr);
+        const double sf = S.phase == PH_RESTO ? 0.0 : S.sf;
+        lip_full_step<0, MODE_SOLVE, KT>(k, P, pb, nd, S.z, sf, ctl, R, A, LA, nullptr);
+        lip_full_step<1, MODE_SOLVE, KT>(k, P, pb, nd, S.z, sf, ctl, R, A, LA, nullptr);
+        lip_full_step<2, MODE_SOLVE, KT>(k, P, pb, nd, S.z, sf, ctl, R, A, LA, nullptr);
+    }
+    // max |d f / d z| at the start point (objective scaling); no rows, no trigonometry of the headings
+    DCBF_HD double grad_inf(const Consts &k, const dcbf_params &P, const IpmState<9> &S) const {
+        double x = pb.x0[0], y = pb.x0[1], vx = pb.x0[2], vy = pb.x0[3], th = pb.x0[4];
+        double g[9];
+        DCBF_UNROLL
+        for (int i = 0; i < 9; i++) g[i] = 0.0;
+        DCBF_UNROLL
+        for (int i = 0; i < 3; i++) {
+            const double fx = S.z[FXI(i)], fy = S.z[FYI(i)];
+            const double xn = k.C * x + k.Sb * vx + k.gx[0] * fx, yn = k.C * y + k.Sb * vy + k.gx[0] * fy;
+            vx = k.bS * x + k.C * vx + k.gv[0] * fx; vy = k.bS * y + k.C * vy + k.gv[0] * fy;
+            x = xn; y = yn; th += S.z[THI(i)];
+            const double w = P.w_q + (i == 0 ? P.w_p : 0.0);
+            const double ex = x - pb.goal[0], ey = y - pb.goal[1];
+            const double ir2 = 1.0 / (ex * ex + ey * ey);
+            const double phi = th - atan2(-ey, -ex);
+            const double nx = 2.0 * w * ex + 2.0 * P.w_r * phi * (ey * ir2), ny = 2.0 * w * ey + 2.0 * P.w_r * phi * (-ex * ir2);
+            const double nt = 2.0 * P.w_r * phi;
+            DCBF_UNROLL
+            for (int l = 0; l <= i; l++) {
+                g[FXI(l)] = fma(k.gx[i - l], nx, g[FXI(l)]);
+                g[FYI(l)] = fma(k.gx[i - l], ny, g[FYI(l)]);
+                g[THI(l)] += nt;
+            }
+        }
+        double m = 0.0;
+        DCBF_UNROLL
+        for (int i = 0; i < 9; i++) m = dmax(m, fabs(g[i]));
+        return m;
     }
     DCBF_HD void pass_dir(const Consts &k, const dcbf_params &P, const IpmState<9> &S, double tau, DirStat &D) {
         LipDir d;
@@ -911,7 +946,7 @@ DCBF_HD void dd_full_step(const Consts &k, const dcbf_params &P, const Problem &
     constexpr int kn = I + 1;
     constexpr int NV = 2 * (I + 1);
     const double INF = 1e300;
-    const bool hess = (MODE == MODE_EVAL) || ctl.phase == PH_MAIN;
+    const bool hess = true;   // restoration uses the curvature of the violated rows too (objective scaled by sf = 0)
     // ---- objective: node kn and the smoothness term of step I --------------------------------------------------------
     {
         const double w = P.w_q + (I == 0 ? P.w_p : 0.0);
@@ -1145,10 +1180,22 @@ struct DdModel {
         DdSecond H2;
         DCBF_UNROLL
         for (int i = 0; i < 4; i++) { H2.qxx[i] = H2.qxy[i] = H2.qyy[i] = H2.cx[i] = H2.cy[i] = 0.0; }
-        dd_full_step<0, MODE_SOLVE, KT>(k, P, pb, nd, S.z, S.sf, ctl, R, A, LA, H2, nullptr);
-        dd_full_step<1, MODE_SOLVE, KT>(k, P, pb, nd, S.z, S.sf, ctl, R, A, LA, H2, nullptr);
-        dd_full_step<2, MODE_SOLVE, KT>(k, P, pb, nd, S.z, S.sf, ctl, R, A, LA, H2, nullptr);
-        if (S.phase == PH_MAIN) dd_add_second(k, nd, S.z, H2, A.K);
+        const double sf = S.phase == PH_RESTO ? 0.0 : S.sf;
+        dd_full_step<0, MODE_SOLVE, KT>(k, P, pb, nd, S.z, sf, ctl, R, A, LA, H2, nullptr);
+        dd_full_step<1, MODE_SOLVE, KT>(k, P, pb, nd, S.z, sf, ctl, R, A, LA, H2, nullptr);
+        dd_full_step<2, MODE_SOLVE, KT>(k, P, pb, nd, S.z, sf, ctl, R, A, LA, H2, nullptr);
+        dd_add_second(k, nd, S.z, H2, A.K);
+    }
+    DCBF_HD double grad_inf(const Consts &k, const dcbf_params &P, const IpmState<6> &S) {
+        // small problem: reuse the full pass in restoration mode (touches no row state)
+        Acc<6> A; LogAcc LA;
+        IpmState<6> T = S;
+        T.phase = PH_RESTO;
+        pass_full(k, P, T, A, LA);
+        double m = 0.0;
+        DCBF_UNROLL
+        for (int i = 0; i < 6; i++) m = dmax(m, fabs(A.grad[i]));
+        return m;
     }
     DCBF_HD void pass_dir(const Consts &k, const dcbf_params &P, const IpmState<6> &S, double tau, DirStat &D) {
         double dxn[4], dyn[4];
@@ -1200,17 +1247,13 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
     Acc<N> A;
     LogAcc LA;
     if (S.first) {
-        // objective scaling needs the gradient at the start point: one throw-away pass in restoration mode (no row state
-        // is touched, no Hessian is formed) gives it.
-        S.phase = PH_RESTO;
-        M.pass_full(k, P, S, A, LA);
-        S.phase = PH_MAIN;
-        double gmax = 0.0;
-        DCBF_UNROLL
-        for (int i = 0; i < N; i++) gmax = dmax(gmax, fabs(A.grad[i]));
+        const double gmax = M.grad_inf(k, P, S);   // gradient-based objective scaling (Ipopt nlp_scaling_max_gradient = 100)
         S.sf = gmax > 100.0 ? 100.0 / gmax : 1.0;
     }
     M.pass_full(k, P, S, A, LA);
+#ifdef DCBF_TRACE
+    printf("it %3d ph %d mu %.2e f %.6f theta %.3e vmax %.3e alpha %.3e delta %.1e lam %.1e nf %d\n", S.iters, S.phase, S.mu, A.f, A.theta, A.vmax, S.alpha, S.delta_last, S.lm_lambda, S.nf);
+#endif
     S.pending = false;
     S.reinit = false;
     S.obj = A.f;
@@ -1259,6 +1302,9 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
         double gn = 0.0;
         DCBF_UNROLL
         for (int i = 0; i < N; i++) gn = dmax(gn, fabs(A.q1[i]));
+#ifdef DCBF_TRACE
+        printf("      resto: v2 %.12e gn %.3e\n", A.v2, gn);
+#endif
         bool stationary = gn <= 1e-10 * dmax(1.0, A.vmax) || S.lm_lambda > 1e12;
         if (stationary) {
             if (A.vmax > P.constr_viol_tol) { S.status = 2; S.done = true; return true; }
@@ -1296,7 +1342,10 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             for (int i = 0; i < N; i++) { dn = dmax(dn, fabs(S.dz[i])); S.z[i] += S.dz[i]; }
             S.iters++;
             S.lm_lambda = dmax(S.lm_lambda * 0.2, 1e-12);
-            if ((dn < 1e-12 || A.v2 - V.v2 < 1e-14 * A.v2) && V.vmax > S.resto_target) S.lm_lambda = 1e13;  // stalled
+            // stagnation: the squared violation has stopped decreasing (two consecutive accepted steps with a relative
+            // decrease below 1e-4) -> the iterate is (numerically) a stationary point of the violation
+            if (A.v2 - V.v2 <= 1e-4 * A.v2) S.acc_cnt++; else S.acc_cnt = 0;
+            if ((dn < 1e-12 || S.acc_cnt >= 2) && V.vmax > S.resto_target) S.lm_lambda = 1e13;
         } else {
             S.lm_lambda *= 10.0;
         }
@@ -1334,12 +1383,16 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
         }
         if (accepted) break;
     }
+#ifdef DCBF_TRACE
+    printf("      ls: accepted %d alpha %.3e amax %.3e dphi %.3e\n", accepted, alpha, D.amax, dphi);
+#endif
     if (!accepted) {
         filter_add(S, (1.0 - 1e-5) * theta, phi - 1e-5 * theta);
         S.phase = PH_RESTO;
         S.resto_entry = A.vmax;
         S.resto_target = dmax(0.1 * A.vmax, 1e-9);
         S.lm_lambda = 1e-4;
+        S.acc_cnt = 0;
         S.iters++;
         return false;
     }

@@ -552,6 +552,7 @@ static int restore(const orc_problem *pb, ipm_t *S, const double *cl, const doub
     int n = S->n, m = S->m;
     double c[MMAX], jac[MMAX * NMAX], K[NMAX * NMAX], rhs[NMAX], xt[NMAX], ct[MMAX];
     double lam = 1e-4;
+    int stall = 0;
     prob_eval(pb, S->x, NULL, NULL, c, jac);
     for (int it = 0; it < 200 && *iters < max_iter; it++) {
         double v2 = 0, vmax = 0;
@@ -563,6 +564,12 @@ static int restore(const orc_problem *pb, ipm_t *S, const double *cl, const doub
             for (int i = 0; i < n; i++) { rhs[i] -= jac[r * n + i] * v; for (int j = 0; j <= i; j++) K[i * n + j] += jac[r * n + i] * jac[r * n + j]; }
         }
         if (vmax <= target) return 1;
+        {   /* curvature term sum_r v_r Hess(c_r): Newton instead of Gauss-Newton on 0.5*sum v^2 (nonzero-residual problem) */
+            double yv[MMAX], H2[NMAX * NMAX], sf_keep = S->sf;
+            for (int r = 0; r < m; r++) { double v = 0; if (cl[r] - c[r] > 0) v = c[r] - cl[r]; else if (c[r] - cu[r] > 0) v = c[r] - cu[r]; yv[r] = v; }
+            S->sf = 0.0; fd_hessian(pb, S, yv, H2); S->sf = sf_keep;
+            for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) K[i * n + j] += H2[i * n + j];
+        }
         double gn = 0; for (int j = 0; j < n; j++) if (fabs(rhs[j]) > gn) gn = fabs(rhs[j]);
         if (gn <= 1e-10 * fmax(1.0, vmax)) return 0;
         int ok = 0;
@@ -583,7 +590,9 @@ static int restore(const orc_problem *pb, ipm_t *S, const double *cl, const doub
                 (*iters)++;
                 prob_eval(pb, S->x, NULL, NULL, c, jac);
                 if (dn < 1e-12 && sqrt(w2) > target) return 0;
-                if (v2 - w2 < 1e-14 * v2 && sqrt(w2) > target) return 0;
+                /* stagnation: two consecutive accepted steps with a relative decrease below 1e-4 */
+                if (v2 - w2 <= 1e-4 * v2) stall++; else stall = 0;
+                if (stall >= 2 && sqrt(w2) > target) return 0;
                 break;
             }
             lam *= 10;
