@@ -31,8 +31,10 @@
 #define DCBF_HD __host__ __device__ __forceinline__
 #define DCBF_UNROLL _Pragma("unroll")
 #define DCBF_CE __host__ __device__ constexpr
+#define DCBF_MATH __host__ __device__ __noinline__
 #else
 #define DCBF_CE constexpr
+#define DCBF_MATH inline
 #define DCBF_HD inline
 #define DCBF_UNROLL
 #endif
@@ -84,13 +86,24 @@ enum { PH_MAIN = 0, PH_RESTO = 1 };
 
 DCBF_HD double dmax(double a, double b) { return a > b ? a : b; }
 DCBF_HD double dmin(double a, double b) { return a < b ? a : b; }
-DCBF_HD void dsincos(double a, double *s, double *c) {
+// Software FP64 routines (sincos, atan2, log, 1/sqrt) are each several hundred SASS instructions; one out-of-line copy
+// keeps the solver body inside the instruction cache (profiles/r01_summary.md: "no_instruction" was the top stall).
+DCBF_MATH void dsincos(double a, double *s, double *c) {
 #if defined(__CUDA_ARCH__)
     sincos(a, s, c);
 #else
     *s = sin(a);
     *c = cos(a);
 #endif
+}
+DCBF_MATH double datan2(double y, double x) { return atan2(y, x); }
+DCBF_MATH double dlog(double x) { return log(x); }
+DCBF_MATH double drsqrt(double x) { return 1.0 / sqrt(x); }
+DCBF_MATH double drcp(double x) { return 1.0 / x; }
+// alpha * a^2.3 > t^1.1 for a > 0, t >= 0 (switching condition of the filter line search) without pow()
+DCBF_HD bool switch_cond(double alpha, double a, double t) {
+    if (!(t > 0.0)) return alpha > 0.0;
+    return dlog(alpha) + 2.3 * dlog(a) > 1.1 * dlog(t);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -154,9 +167,9 @@ struct RowW { double sig, w1, binv, y; };
 struct LogAcc { double sum, prod; int cnt; };
 DCBF_HD void log_push(LogAcc &L, double gap) {
     L.prod *= gap;
-    if (++L.cnt == 6) { L.sum += log(L.prod); L.prod = 1.0; L.cnt = 0; }
+    if (++L.cnt == 6) { L.sum += dlog(L.prod); L.prod = 1.0; L.cnt = 0; }
 }
-DCBF_HD double log_total(const LogAcc &L) { return L.cnt ? L.sum + log(L.prod) : L.sum; }
+DCBF_HD double log_total(const LogAcc &L) { return L.cnt ? L.sum + dlog(L.prod) : L.sum; }
 
 // control block handed to the row helpers
 struct RowCtl {
@@ -296,7 +309,7 @@ DCBF_HD bool chol_packed(const double *K, double delta, double *L) {
         DCBF_UNROLL
         for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
         if (!(d > 1e-14)) { ok = false; d = 1.0; }
-        const double r = 1.0 / sqrt(d);
+        const double r = drsqrt(d);
         L[tri(j, j)] = r;   // store the reciprocal of the diagonal
         DCBF_UNROLL
         for (int i = j + 1; i < N; i++) {
@@ -509,7 +522,7 @@ DCBF_HD void lip_full_step(const Consts &k, const dcbf_params &P, const Problem 
         const double ex = nd.x[kn] - pb.goal[0], ey = nd.y[kn] - pb.goal[1];
         const double dx = -ex, dy = -ey;
         const double r2 = dx * dx + dy * dy, ir2 = 1.0 / r2;
-        const double phi = nd.th[kn] - atan2(dy, dx);
+        const double phi = nd.th[kn] - datan2(dy, dx);
         A.f += w * (ex * ex + ey * ey) + P.w_r * phi * phi;
         const double px = -dy * ir2, py = dx * ir2;           // d phi / d(x_k, y_k)
         const double nx = 2.0 * w * ex + 2.0 * P.w_r * phi * px;
@@ -766,7 +779,7 @@ DCBF_HD void lip_val_step(const dcbf_params &P, const Problem &pb, const LipNode
     {
         const double w = P.w_q + (I == 0 ? P.w_p : 0.0);
         const double ex = nd.x[kn] - pb.goal[0], ey = nd.y[kn] - pb.goal[1];
-        const double phi = nd.th[kn] - atan2(-ey, -ex);
+        const double phi = nd.th[kn] - datan2(-ey, -ex);
         V.f += w * (ex * ex + ey * ey) + P.w_r * phi * phi;
     }
     const double cs = nd.cs[kn], sn = nd.sn[kn];
@@ -839,7 +852,7 @@ struct LipModel {
             const double w = P.w_q + (i == 0 ? P.w_p : 0.0);
             const double ex = x - pb.goal[0], ey = y - pb.goal[1];
             const double ir2 = 1.0 / (ex * ex + ey * ey);
-            const double phi = th - atan2(-ey, -ex);
+            const double phi = th - datan2(-ey, -ex);
             const double nx = 2.0 * w * ex + 2.0 * P.w_r * phi * (ey * ir2), ny = 2.0 * w * ey + 2.0 * P.w_r * phi * (-ex * ir2);
             const double nt = 2.0 * P.w_r * phi;
             DCBF_UNROLL
@@ -953,7 +966,7 @@ DCBF_HD void dd_full_step(const Consts &k, const dcbf_params &P, const Problem &
         const double ex = nd.x[kn] - pb.goal[0], ey = nd.y[kn] - pb.goal[1];
         const double dx = -ex, dy = -ey;
         const double r2 = dx * dx + dy * dy, ir2 = 1.0 / r2;
-        const double phi = nd.th[kn] - atan2(dy, dx);
+        const double phi = nd.th[kn] - datan2(dy, dx);
         const double pv = I == 0 ? pb.last_u[0] : z[2 * (I > 0 ? I - 1 : 0)];
         const double pw = I == 0 ? pb.last_u[1] : z[2 * (I > 0 ? I - 1 : 0) + 1];
         const double dv = z[2 * I] - pv, dw = z[2 * I + 1] - pw;
@@ -1134,7 +1147,7 @@ DCBF_HD void dd_val_step(const dcbf_params &P, const Problem &pb, const DdNodes 
     {
         const double w = P.w_q + (I == 0 ? P.w_p : 0.0);
         const double ex = nd.x[kn] - pb.goal[0], ey = nd.y[kn] - pb.goal[1];
-        const double phi = nd.th[kn] - atan2(-ey, -ex);
+        const double phi = nd.th[kn] - datan2(-ey, -ex);
         const double pv = I == 0 ? pb.last_u[0] : z[2 * (I > 0 ? I - 1 : 0)];
         const double pw = I == 0 ? pb.last_u[1] : z[2 * (I > 0 ? I - 1 : 0) + 1];
         const double dv = z[2 * I] - pv, dw = z[2 * I + 1] - pw;
@@ -1375,7 +1388,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
         for (int q = 0; q < S.nf; q++)
             if (th_t >= S.filt_th[q] && ph_t >= S.filt_ph[q]) in_filter = true;
         if (in_filter) continue;
-        const bool sw = dphi < 0.0 && theta <= S.theta_min && alpha * pow(-dphi, 2.3) > pow(theta, 1.1);
+        const bool sw = dphi < 0.0 && theta <= S.theta_min && switch_cond(alpha, -dphi, theta);
         if (sw) {
             if (ph_t <= phi + 1e-8 * alpha * dphi + eps_phi) accepted = 1;
         } else if (th_t <= (1.0 - 1e-5) * theta || ph_t <= phi - 1e-5 * theta + eps_phi) {
@@ -1430,7 +1443,7 @@ DCBF_HD void setup_problem(const dcbf_params &P, Problem &pb) {
             const double *o = pb.cir + DCBF_CIR_REC * j;
             const double dc = (px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]);
             if (dc < dg && dc < 9.0 * o[2]) {
-                const double th = atan2(gy - py, gx - px), al = atan2(o[1] - py, o[0] - px);
+                const double th = datan2(gy - py, gx - px), al = datan2(o[1] - py, o[0] - px);
                 double d = th - al;
                 if (d < 0.0 && fabs(d) > PI) d += 2.0 * PI;
                 else if (d > 0.0 && fabs(d) > PI) d -= 2.0 * PI;

@@ -14,6 +14,8 @@
 #include <new>
 
 #include "dcbf_lanes.cuh"
+#include "dcbf_warp.cuh"
+#include <stdlib.h>
 
 using namespace dcbf;
 
@@ -34,6 +36,9 @@ struct dcbf_ctx {
     void *d_buf; size_t d_buf_bytes;
     double *d_cir_raw, *d_elp_raw; size_t raw_bytes;
     cudaStream_t stream;
+    int sm_count;
+    int kernel_mode;   // 0 auto, 1 per-thread, 2 warp-cooperative (env DCBF_KERNEL=thread|warp)
+    int warp_max_batch;
 };
 
 #define CK(call)                                                                                        \
@@ -71,6 +76,118 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) rollout_lip_lane(P, K, in, out, steps, b);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// warp-cooperative kernels (one problem per warp): small / medium batches and low latency
+// ---------------------------------------------------------------------------------------------------------------
+#define DCBF_WARPS_PER_CTA 4
+#ifndef DCBF_WARP_MIN_CTAS
+#define DCBF_WARP_MIN_CTAS 4
+#endif
+
+template <int NS>
+__global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) solve_lip_warp_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*T)[9] = reinterpret_cast<double (*)[9]>(smem_raw);
+    wp::WarpShared<NS> *wsm = reinterpret_cast<wp::WarpShared<NS> *>(smem_raw + sizeof(double) * wp::NFEAT * 9);
+    wp::build_T(K, T);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    wp::WarpShared<NS> &sm = wsm[wid];
+    const int nw = gridDim.x * DCBF_WARPS_PER_CTA;
+    for (int b = blockIdx.x * DCBF_WARPS_PER_CTA + wid; b < B; b += nw) {
+        double z[9], x0[5], goal_raw[2];
+        int leg;
+#pragma unroll
+        for (int i = 0; i < 5; i++) x0[i] = in.x0[5 * (size_t)b + i];
+        {
+            double u0[15];
+#pragma unroll
+            for (int i = 0; i < 15; i++) u0[i] = in.warm[15 * (size_t)b + i];
+            lip_z_from_u(K, x0, u0, z);
+        }
+        wp::WState S;
+        wp::solve_lip_warp<NS>(P, K, T, sm, in, b, lane, z, x0, goal_raw, leg, S, true);
+        // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
+        if (lane < 15) {
+            const double v = sm.nodes[lane / 5 + 1][lane % 5];
+            if (out.u) out.u[15 * (size_t)b + lane] = v;
+            if (out.x_plan) out.x_plan[15 * (size_t)b + lane] = v;
+        }
+        if (lane < 9 && out.p_plan) {
+            const int i = lane / 3, c = lane % 3;
+            out.p_plan[9 * (size_t)b + lane] = wp::zsel(z, c < 2 ? 2 * i + c : 6 + i);
+        }
+        if (lane == 0) {
+            if (out.status) out.status[b] = S.status;
+            if (out.iters) out.iters[b] = S.iters;
+            if (out.obj) out.obj[b] = S.obj;
+            if (out.viol) out.viol[b] = S.viol;
+            if (out.close) out.close[b] = wp::w_close<NS>(P, sm, goal_raw) ? 1 : 0;
+        }
+        __syncwarp();
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) rollout_lip_warp_kernel(dcbf_params P, Consts K, int B, int steps, BatchIn in, RolloutOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*T)[9] = reinterpret_cast<double (*)[9]>(smem_raw);
+    wp::WarpShared<NS> *wsm = reinterpret_cast<wp::WarpShared<NS> *>(smem_raw + sizeof(double) * wp::NFEAT * 9);
+    wp::build_T(K, T);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    wp::WarpShared<NS> &sm = wsm[wid];
+    const int nw = gridDim.x * DCBF_WARPS_PER_CTA;
+    for (int b = blockIdx.x * DCBF_WARPS_PER_CTA + wid; b < B; b += nw) {
+        double z[9], x0[5], goal_raw[2], u0[15];
+        int leg = in.leg ? in.leg[b] : 1;
+#pragma unroll
+        for (int i = 0; i < 5; i++) x0[i] = in.x0[5 * (size_t)b + i];
+        goal_raw[0] = in.goal[2 * (size_t)b]; goal_raw[1] = in.goal[2 * (size_t)b + 1];
+#pragma unroll
+        for (int i = 0; i < 15; i++) u0[i] = x0[i % 5];                      // cold start [x, x, x]
+        int done = 0, ninf = 0, tot = 0;
+        for (int st = 0; st < steps; st++) {
+            lip_z_from_u(K, x0, u0, z);
+            wp::WState S;
+            wp::solve_lip_warp<NS>(P, K, T, sm, in, b, lane, z, x0, goal_raw, leg, S, false);
+            tot += S.iters;
+            if (S.status == 2) ninf++;
+            const bool close = wp::w_close<NS>(P, sm, goal_raw);
+            if (out.traj && lane < 8) {
+                double v;
+                if (lane < 5) v = sm.nodes[1][lane];
+                else if (lane == 5) v = z[0];
+                else if (lane == 6) v = z[1];
+                else v = (double)S.status;
+                out.traj[((size_t)b * steps + st) * 8 + lane] = v;
+            }
+            // shifted warm start [x_2, x_3, x_3]; apply the first step; flip the stance leg
+#pragma unroll
+            for (int j = 0; j < 5; j++) { u0[j] = sm.nodes[2][j]; u0[5 + j] = sm.nodes[3][j]; u0[10 + j] = sm.nodes[3][j]; x0[j] = sm.nodes[1][j]; }
+            leg = -leg;
+            done = st + 1;
+            __syncwarp();
+            if (close) break;
+        }
+        if (out.traj) {
+            const double nanv = nan("");
+            for (int t = done * 8 + lane; t < steps * 8; t += 32) out.traj[(size_t)b * steps * 8 + t] = nanv;
+        }
+        if (out.x_final && lane < 5) out.x_final[5 * (size_t)b + lane] = wp::zsel(x0, lane);
+        if (lane == 0) {
+            if (out.steps_done) out.steps_done[b] = done;
+            if (out.n_infeasible) out.n_infeasible[b] = ninf;
+            if (out.total_iters) out.total_iters[b] = tot;
+        }
+        __syncwarp();
+    }
+}
+
+template <int NS>
+static size_t warp_smem_bytes() { return sizeof(double) * wp::NFEAT * 9 + sizeof(wp::WarpShared<NS>) * DCBF_WARPS_PER_CTA; }
+
 // ---------------------------------------------------------------------------------------------------------------
 // FP64 peak microbenchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------------------------------------
@@ -81,6 +198,40 @@ __global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
         x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// one problem per warp for batches that cannot fill the GPU with one problem per thread (and for single solves)
+static bool use_warp_kernel(const dcbf_ctx *ctx, int B) {
+    if (ctx->P.formulation == DCBF_DD) return false;
+    if (ctx->kernel_mode == 1) return false;
+    if (ctx->kernel_mode == 2) return true;
+    return B <= ctx->warp_max_batch;
+}
+static int warp_slots(const dcbf_ctx *ctx) {
+    const int m = 3 * (ctx->Kc + ctx->Ke + (ctx->P.has_fen ? 6 : 4));
+    return m <= 32 ? 1 : (m <= 64 ? 2 : 4);
+}
+template <int NS>
+static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
+    const size_t smem = warp_smem_bytes<NS>();
+    CK(cudaFuncSetAttribute(solve_lip_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (B + DCBF_WARPS_PER_CTA - 1) / DCBF_WARPS_PER_CTA;
+    const int cap = ctx->sm_count * 16;
+    if (grid > cap) grid = cap;
+    solve_lip_warp_kernel<NS><<<grid, 32 * DCBF_WARPS_PER_CTA, smem, st>>>(ctx->P, ctx->K, B, in, out);
+    CK(cudaGetLastError());
+    return DCBF_OK;
+}
+template <int NS>
+static int launch_rollout_warp(dcbf_ctx *ctx, int B, int steps, const BatchIn &in, const RolloutOut &out, cudaStream_t st) {
+    const size_t smem = warp_smem_bytes<NS>();
+    CK(cudaFuncSetAttribute(rollout_lip_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (B + DCBF_WARPS_PER_CTA - 1) / DCBF_WARPS_PER_CTA;
+    const int cap = ctx->sm_count * 16;
+    if (grid > cap) grid = cap;
+    rollout_lip_warp_kernel<NS><<<grid, 32 * DCBF_WARPS_PER_CTA, smem, st>>>(ctx->P, ctx->K, B, steps, in, out);
+    CK(cudaGetLastError());
+    return DCBF_OK;
 }
 
 // ===============================================================================================================
@@ -129,6 +280,13 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    const char *km = getenv("DCBF_KERNEL");
+    ctx->kernel_mode = km ? (km[0] == 't' ? 1 : (km[0] == 'w' ? 2 : 0)) : 0;
+    const char *wb = getenv("DCBF_WARP_MAX_BATCH");
+    ctx->warp_max_batch = wb ? atoi(wb) : 16384;   // measured crossover on B200: profiles/r01_summary.md
     *out = ctx;
     return DCBF_OK;
 }
@@ -172,6 +330,7 @@ int dcbf_set_fields(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir_dev,
     return DCBF_OK;
 }
 
+
 static int grid_for(const dcbf_ctx *ctx, int B) {
     int g = (B + DCBF_BLOCK - 1) / DCBF_BLOCK;
     return g < 1 ? 1 : g;
@@ -205,6 +364,11 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
     SolveOut out = {u, x_plan, p_plan, obj, viol, status, iters, close2goal};
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->P.formulation == DCBF_DD) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
+    else if (use_warp_kernel(ctx, B)) {
+        const int ns = warp_slots(ctx);
+        const int rc = ns == 1 ? launch_solve_warp<1>(ctx, B, in, out, st) : (ns == 2 ? launch_solve_warp<2>(ctx, B, in, out, st) : launch_solve_warp<4>(ctx, B, in, out, st));
+        if (rc != DCBF_OK) return rc;
+    }
     else solve_lip_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -221,7 +385,14 @@ int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, cons
     CK(cudaSetDevice(ctx->device));
     BatchIn in = {x0, goal, nullptr, nullptr, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
     RolloutOut out = {x_final, traj, steps_done, n_infeasible, total_iters};
-    rollout_lip_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, (cudaStream_t)stream>>>(ctx->P, ctx->K, B, steps, in, out);
+    if (use_warp_kernel(ctx, B)) {
+        const int ns = warp_slots(ctx);
+        cudaStream_t st = (cudaStream_t)stream;
+        const int rc = ns == 1 ? launch_rollout_warp<1>(ctx, B, steps, in, out, st) : (ns == 2 ? launch_rollout_warp<2>(ctx, B, steps, in, out, st) : launch_rollout_warp<4>(ctx, B, steps, in, out, st));
+        if (rc != DCBF_OK) return rc;
+    } else {
+        rollout_lip_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, (cudaStream_t)stream>>>(ctx->P, ctx->K, B, steps, in, out);
+    }
     CK(cudaGetLastError());
     ctx->launches++;
     return DCBF_OK;

@@ -130,6 +130,26 @@ def test_solve_matches_oracle_on_bench_distribution(gpu, form, B, seed):
     assert np.mean(rel[both] <= OBJ_TOL) >= 0.995
 
 
+@pytest.mark.parametrize("mode", ["thread", "warp"])
+@pytest.mark.parametrize("form,B,seed", [("sig_step", 2048, 21), ("modi", 2048, 22)])
+def test_both_kernel_families_match_oracle(gpu, monkeypatch, mode, form, B, seed):
+    """the per-thread kernels (large batches) and the warp-cooperative kernels (small batches, single solves) are
+    selected by batch size; force each one (DCBF_KERNEL is read by dcbf_create) and check it against the oracle."""
+    monkeypatch.setenv("DCBF_KERNEL", mode)
+    sc = scenarios.make_batch(form, B, seed=seed)
+    s = _solver(gpu, form, sc, max_iter=300)
+    res = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
+    P = c_oracle.params(form, max_iter=300)
+    ref = c_oracle.solve_batch(P, sc.x0, sc.goal, sc.leg, sc.cir, sc.elp if sc.elp.shape[1] else None, sc.warm,
+                               field=sc.field, threads=os.cpu_count() or 4)
+    same_class, both, dp, rel = _agreement(form, res, ref, B)
+    assert same_class.mean() >= 0.995 and np.mean(dp[both] <= POS_TOL) >= 0.995 and np.mean(rel[both] <= OBJ_TOL) >= 0.995
+    # closed loop through the same kernel family
+    ro = s.rollout(4, sc.x0[:256], sc.goal[:256], sc.leg[:256], field=sc.field[:256])
+    one = s.solve(sc.x0[:256], sc.goal[:256], sc.leg[:256], sc.warm[:256], field=sc.field[:256])
+    np.testing.assert_allclose(ro["traj"][:, 0, :5].cpu().numpy(), one.x_plan[:, 0].cpu().numpy(), atol=1e-12)
+
+
 def test_warm_started_resolve_is_idempotent(gpu):
     """size-independent property at config 3's full size: re-solving from the returned plan returns the same plan."""
     B = 65536
@@ -233,7 +253,7 @@ def test_error_codes(gpu):
     ctx = C.c_void_p()
     assert lib.dcbf_create(C.byref(P), 0, C.byref(ctx)) == 0
     x = torch.zeros((1, 15), dtype=torch.float64, device="cuda")
-    args = [x.data_ptr()] * 3 + [None, None, x.data_ptr(), None] + [None] * 8
+    args = [x.data_ptr(), x.data_ptr(), None, None, x.data_ptr(), None] + [None] * 8   # x0, goal, leg, field, warm, last_u, outputs
     assert lib.dcbf_solve(ctx, 1, *args[:14], None) == -3          # DCBF_ERR_NO_FIELDS
     assert lib.dcbf_solve(ctx, 1, None, *args[1:14], None) == -1    # DCBF_ERR_ARG
     assert lib.dcbf_set_fields(ctx, 1, 99, x.data_ptr(), 0, None, None) == -1
