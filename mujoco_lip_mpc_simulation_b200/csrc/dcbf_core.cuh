@@ -1326,8 +1326,31 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             return false;
         }
         if (S.iters >= P.max_iter) { S.status = -1; S.done = true; return true; }
-        DCBF_UNROLL
-        for (int i = 0; i < N; i++) { rhs[i] = -A.q1[i]; A.K[tri(i, i)] += S.lm_lambda; }
+        // Levenberg-Marquardt trials: the assembled K and right-hand side are reused while lambda is escalated
+        double L[N * (N + 1) / 2];
+        for (int rt = 0; rt < 20 && S.lm_lambda <= 1e12; rt++) {
+            if (!chol_packed<N>(A.K, S.lm_lambda, L)) { S.lm_lambda *= 10.0; continue; }
+            DCBF_UNROLL
+            for (int i = 0; i < N; i++) S.dz[i] = -A.q1[i];
+            chol_solve_packed<N>(L, S.dz);
+            ValStat V;
+            V.f = 0.0; V.theta = 0.0; V.v2 = 0.0; V.vmax = 0.0; V.ok = true; V.la.sum = 0.0; V.la.prod = 1.0; V.la.cnt = 0;
+            M.pass_value(k, P, S, 1.0, V);
+            if (V.v2 < A.v2 * (1.0 - 1e-12)) {
+                double dn = 0.0;
+                DCBF_UNROLL
+                for (int i = 0; i < N; i++) { dn = dmax(dn, fabs(S.dz[i])); S.z[i] += S.dz[i]; }
+                S.iters++;
+                S.lm_lambda = dmax(S.lm_lambda * 0.2, 1e-12);
+                // stagnation: the squared violation has stopped decreasing (two consecutive accepted steps with a relative
+                // decrease below 1e-4) -> the iterate is (numerically) a stationary point of the violation
+                if (A.v2 - V.v2 <= 1e-4 * A.v2) S.acc_cnt++; else S.acc_cnt = 0;
+                if ((dn < 1e-12 || S.acc_cnt >= 2) && V.vmax > S.resto_target) S.lm_lambda = 1e13;
+                return false;
+            }
+            S.lm_lambda *= 10.0;
+        }
+        return false;   // lambda exhausted: the next call classifies the point as stationary
     }
     // ---- factor + solve ---------------------------------------------------------------------------------------------
     double L[N * (N + 1) / 2];
@@ -1345,25 +1368,6 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
     for (int i = 0; i < N; i++) S.dz[i] = rhs[i];
     chol_solve_packed<N>(L, S.dz);
 
-    if (S.phase == PH_RESTO) {
-        ValStat V;
-        V.f = 0.0; V.theta = 0.0; V.v2 = 0.0; V.vmax = 0.0; V.ok = true; V.la.sum = 0.0; V.la.prod = 1.0; V.la.cnt = 0;
-        M.pass_value(k, P, S, 1.0, V);
-        if (V.v2 < A.v2 * (1.0 - 1e-12)) {
-            double dn = 0.0;
-            DCBF_UNROLL
-            for (int i = 0; i < N; i++) { dn = dmax(dn, fabs(S.dz[i])); S.z[i] += S.dz[i]; }
-            S.iters++;
-            S.lm_lambda = dmax(S.lm_lambda * 0.2, 1e-12);
-            // stagnation: the squared violation has stopped decreasing (two consecutive accepted steps with a relative
-            // decrease below 1e-4) -> the iterate is (numerically) a stationary point of the violation
-            if (A.v2 - V.v2 <= 1e-4 * A.v2) S.acc_cnt++; else S.acc_cnt = 0;
-            if ((dn < 1e-12 || S.acc_cnt >= 2) && V.vmax > S.resto_target) S.lm_lambda = 1e13;
-        } else {
-            S.lm_lambda *= 10.0;
-        }
-        return false;
-    }
     // ---- main phase: step sizes and filter line search -----------------------------------------------------------------
     const double tau = dmax(0.99, 1.0 - S.mu);
     DirStat D;

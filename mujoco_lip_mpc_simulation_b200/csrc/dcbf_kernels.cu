@@ -85,29 +85,45 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
 #define DCBF_WARP_MIN_CTAS 4
 #endif
 
+// lane 0 stages the scenario state and the start point z0 (from the reference's u0) in shared memory
+template <int NS>
+__device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<NS> &sm, const double *x0, const double *graw, const double *u0, int lane) {
+    if (lane == 0) {
+        double z[9];
+        lip_z_from_u(K, x0, u0, z);
+#pragma unroll
+        for (int i = 0; i < 9; i++) sm.zc[i] = z[i];
+#pragma unroll
+        for (int i = 0; i < 5; i++) sm.x0[i] = x0[i];
+        sm.graw[0] = graw[0]; sm.graw[1] = graw[1];
+    }
+    __syncwarp();
+}
+
 template <int NS>
 __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) solve_lip_warp_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*T)[9] = reinterpret_cast<double (*)[9]>(smem_raw);
-    wp::WarpShared<NS> *wsm = reinterpret_cast<wp::WarpShared<NS> *>(smem_raw + sizeof(double) * wp::NFEAT * 9);
-    wp::build_T(K, T);
-    __syncthreads();
+    wp::CtaShared &cs_ = *reinterpret_cast<wp::CtaShared *>(smem_raw);
+    wp::WarpShared<NS> *wsm = reinterpret_cast<wp::WarpShared<NS> *>(smem_raw + ((sizeof(wp::CtaShared) + 15) & ~(size_t)15));
+    wp::stage_cta(P, K, cs_);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     wp::WarpShared<NS> &sm = wsm[wid];
     const int nw = gridDim.x * DCBF_WARPS_PER_CTA;
     for (int b = blockIdx.x * DCBF_WARPS_PER_CTA + wid; b < B; b += nw) {
-        double z[9], x0[5], goal_raw[2];
-        int leg;
+        if (lane == 0) {
+            double x0[5], u0[15], g[2];
 #pragma unroll
-        for (int i = 0; i < 5; i++) x0[i] = in.x0[5 * (size_t)b + i];
-        {
-            double u0[15];
+            for (int i = 0; i < 5; i++) x0[i] = in.x0[5 * (size_t)b + i];
 #pragma unroll
             for (int i = 0; i < 15; i++) u0[i] = in.warm[15 * (size_t)b + i];
-            lip_z_from_u(K, x0, u0, z);
+            g[0] = in.goal[2 * (size_t)b]; g[1] = in.goal[2 * (size_t)b + 1];
+            stage_problem<NS>(cs_.K, sm, x0, g, u0, 0);
+        } else {
+            __syncwarp();
         }
+        const int leg = in.leg ? in.leg[b] : 1;
         wp::WState S;
-        wp::solve_lip_warp<NS>(P, K, T, sm, in, b, lane, z, x0, goal_raw, leg, S, true);
+        wp::solve_lip_warp<NS>(cs_, sm, in, b, lane, leg, S);
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
         if (lane < 15) {
             const double v = sm.nodes[lane / 5 + 1][lane % 5];
@@ -116,14 +132,14 @@ __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) s
         }
         if (lane < 9 && out.p_plan) {
             const int i = lane / 3, c = lane % 3;
-            out.p_plan[9 * (size_t)b + lane] = wp::zsel(z, c < 2 ? 2 * i + c : 6 + i);
+            out.p_plan[9 * (size_t)b + lane] = sm.zc[c < 2 ? 2 * i + c : 6 + i];
         }
         if (lane == 0) {
             if (out.status) out.status[b] = S.status;
             if (out.iters) out.iters[b] = S.iters;
             if (out.obj) out.obj[b] = S.obj;
             if (out.viol) out.viol[b] = S.viol;
-            if (out.close) out.close[b] = wp::w_close<NS>(P, sm, goal_raw) ? 1 : 0;
+            if (out.close) out.close[b] = wp::w_close<NS>(cs_.P, sm) ? 1 : 0;
         }
         __syncwarp();
     }
@@ -132,50 +148,59 @@ __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) s
 template <int NS>
 __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) rollout_lip_warp_kernel(dcbf_params P, Consts K, int B, int steps, BatchIn in, RolloutOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*T)[9] = reinterpret_cast<double (*)[9]>(smem_raw);
-    wp::WarpShared<NS> *wsm = reinterpret_cast<wp::WarpShared<NS> *>(smem_raw + sizeof(double) * wp::NFEAT * 9);
-    wp::build_T(K, T);
-    __syncthreads();
+    wp::CtaShared &cs_ = *reinterpret_cast<wp::CtaShared *>(smem_raw);
+    wp::WarpShared<NS> *wsm = reinterpret_cast<wp::WarpShared<NS> *>(smem_raw + ((sizeof(wp::CtaShared) + 15) & ~(size_t)15));
+    wp::stage_cta(P, K, cs_);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     wp::WarpShared<NS> &sm = wsm[wid];
     const int nw = gridDim.x * DCBF_WARPS_PER_CTA;
     for (int b = blockIdx.x * DCBF_WARPS_PER_CTA + wid; b < B; b += nw) {
-        double z[9], x0[5], goal_raw[2], u0[15];
         int leg = in.leg ? in.leg[b] : 1;
+        if (lane == 0) {
+            double x0[5], u0[15], g[2];
 #pragma unroll
-        for (int i = 0; i < 5; i++) x0[i] = in.x0[5 * (size_t)b + i];
-        goal_raw[0] = in.goal[2 * (size_t)b]; goal_raw[1] = in.goal[2 * (size_t)b + 1];
+            for (int i = 0; i < 5; i++) x0[i] = in.x0[5 * (size_t)b + i];
 #pragma unroll
-        for (int i = 0; i < 15; i++) u0[i] = x0[i % 5];                      // cold start [x, x, x]
+            for (int i = 0; i < 15; i++) u0[i] = x0[i % 5];                  // cold start [x, x, x]
+            g[0] = in.goal[2 * (size_t)b]; g[1] = in.goal[2 * (size_t)b + 1];
+            stage_problem<NS>(cs_.K, sm, x0, g, u0, 0);
+        } else {
+            __syncwarp();
+        }
         int done = 0, ninf = 0, tot = 0;
         for (int st = 0; st < steps; st++) {
-            lip_z_from_u(K, x0, u0, z);
             wp::WState S;
-            wp::solve_lip_warp<NS>(P, K, T, sm, in, b, lane, z, x0, goal_raw, leg, S, false);
+            wp::solve_lip_warp<NS>(cs_, sm, in, b, lane, leg, S);
             tot += S.iters;
             if (S.status == 2) ninf++;
-            const bool close = wp::w_close<NS>(P, sm, goal_raw);
+            const bool close = wp::w_close<NS>(cs_.P, sm);
             if (out.traj && lane < 8) {
                 double v;
                 if (lane < 5) v = sm.nodes[1][lane];
-                else if (lane == 5) v = z[0];
-                else if (lane == 6) v = z[1];
+                else if (lane == 5) v = sm.zc[0];
+                else if (lane == 6) v = sm.zc[1];
                 else v = (double)S.status;
                 out.traj[((size_t)b * steps + st) * 8 + lane] = v;
             }
+            __syncwarp();
             // shifted warm start [x_2, x_3, x_3]; apply the first step; flip the stance leg
+            if (lane == 0) {
+                double x0[5], u0[15], g[2] = {sm.graw[0], sm.graw[1]};
 #pragma unroll
-            for (int j = 0; j < 5; j++) { u0[j] = sm.nodes[2][j]; u0[5 + j] = sm.nodes[3][j]; u0[10 + j] = sm.nodes[3][j]; x0[j] = sm.nodes[1][j]; }
+                for (int j = 0; j < 5; j++) { u0[j] = sm.nodes[2][j]; u0[5 + j] = sm.nodes[3][j]; u0[10 + j] = sm.nodes[3][j]; x0[j] = sm.nodes[1][j]; }
+                stage_problem<NS>(cs_.K, sm, x0, g, u0, 0);
+            } else {
+                __syncwarp();
+            }
             leg = -leg;
             done = st + 1;
-            __syncwarp();
             if (close) break;
         }
         if (out.traj) {
             const double nanv = nan("");
             for (int t = done * 8 + lane; t < steps * 8; t += 32) out.traj[(size_t)b * steps * 8 + t] = nanv;
         }
-        if (out.x_final && lane < 5) out.x_final[5 * (size_t)b + lane] = wp::zsel(x0, lane);
+        if (out.x_final && lane < 5) out.x_final[5 * (size_t)b + lane] = sm.x0[lane];
         if (lane == 0) {
             if (out.steps_done) out.steps_done[b] = done;
             if (out.n_infeasible) out.n_infeasible[b] = ninf;
@@ -186,7 +211,7 @@ __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) r
 }
 
 template <int NS>
-static size_t warp_smem_bytes() { return sizeof(double) * wp::NFEAT * 9 + sizeof(wp::WarpShared<NS>) * DCBF_WARPS_PER_CTA; }
+static size_t warp_smem_bytes() { return ((sizeof(wp::CtaShared) + 15) & ~(size_t)15) + sizeof(wp::WarpShared<NS>) * DCBF_WARPS_PER_CTA; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // FP64 peak microbenchmark: 8 independent DFMA chains per thread
@@ -339,9 +364,10 @@ static int grid_for(const dcbf_ctx *ctx, int B) {
 int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
               const double *last_u, const double *z, const double *lambda, double *f, double *grad, double *c, double *jac,
               double *cl, double *cu, double *hess, void *stream) {
-    if (!ctx || B < 0 || !x0 || !goal || !z) return DCBF_ERR_ARG;
-    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
+    if (!x0 || !goal || !z) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     CK(cudaSetDevice(ctx->device));
     BatchIn in = {x0, goal, nullptr, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
     EvalPtrs ev = {z, lambda, f, grad, c, jac, cl, cu, hess, dcbf_num_rows(ctx)};
@@ -356,9 +382,10 @@ int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, co
 int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
                const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
                int32_t *iters, double *obj, double *viol, uint8_t *close2goal, void *stream) {
-    if (!ctx || B < 0 || !x0 || !goal || !warm) return DCBF_ERR_ARG;
-    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
+    if (!x0 || !goal || !warm) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     CK(cudaSetDevice(ctx->device));
     BatchIn in = {x0, goal, warm, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
     SolveOut out = {u, x_plan, p_plan, obj, viol, status, iters, close2goal};
@@ -378,10 +405,11 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
 int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, const double *goal, const int32_t *leg,
                  const int32_t *field, double *x_final, int32_t *steps_done, int32_t *n_infeasible, int32_t *total_iters,
                  double *traj, void *stream) {
-    if (!ctx || B < 0 || steps < 1 || !x0 || !goal) return DCBF_ERR_ARG;
+    if (!ctx || B < 0 || steps < 1) return DCBF_ERR_ARG;
     if (ctx->P.formulation == DCBF_DD) return DCBF_ERR_ARG;
-    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     if (B == 0) return DCBF_OK;
+    if (!x0 || !goal) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     CK(cudaSetDevice(ctx->device));
     BatchIn in = {x0, goal, nullptr, nullptr, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
     RolloutOut out = {x_final, traj, steps_done, n_infeasible, total_iters};
@@ -435,9 +463,10 @@ static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
                     const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
                     int32_t *iters, double *obj, double *viol, uint8_t *close2goal) {
-    if (!ctx || B < 0 || !x0 || !goal || !warm) return DCBF_ERR_ARG;
-    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
+    if (!x0 || !goal || !warm) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     CK(cudaSetDevice(ctx->device));
     const bool dd = ctx->P.formulation == DCBF_DD;
     const size_t nx = dd ? 3 : 5, nu = dd ? 6 : 15, b = (size_t)B;

@@ -33,15 +33,24 @@ struct WarpShared {
     double G[32 * NS][9];    // row gradients (internal variable order)
     double RW[32 * NS][4];   // sigma, w1, binv, y
     double HQ[32 * NS][3];   // y * (2a', b', 2c') of the D-CBF rows
+    double ST[32 * NS][8];   // per-row statistics staged for the column reductions
     double obs[DCBF_KT][6];  // selected obstacles: cx, cy, a', b', c', rhs
-    double Kf[45], Lf[45], q[27], grad[9], dz[9], zs[9];
+    double Kf[45], Lf[45], q[27], dz[9], zc[9], zt[9], red[8];
+    double x0[5], goal[2], graw[2];
     double nodes[4][5];      // x, y, vx, vy, th of nodes 0..3
     double trig[4][3];       // sin, cos, atan2 target of nodes 1..3
     double nobj[4][10];      // f_k, nx, ny, nt, hxx, hxy, hyy, hxt, hyt, htt of the objective at node k
     double NH[4][8];         // node Hessians xx, xy, yy, xt, yt, tt, vxt, vyt
     double legy[3];
-    double tdz[NFEAT];
     double filt_th[DCBF_FILT], filt_ph[DCBF_FILT];
+};
+
+// per-CTA constants staged in shared memory: parameters, model constants, feature map, (row, col) of the 72 entries
+struct CtaShared {
+    dcbf_params P;
+    Consts K;
+    double T[NFEAT][9];
+    int ea[72], eb[72];
 };
 
 __device__ __forceinline__ double wsum(double v) {
@@ -133,11 +142,13 @@ __device__ __forceinline__ RowBnd row_bounds(const dcbf_params &P, const RowDesc
     return b;
 }
 
-template <int NS>
+template <int NS, bool GRAD>
 __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
     e.nf = 0; e.c = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0;
+    if (GRAD) {
 #pragma unroll
-    for (int p = 0; p < 4; p++) { e.d[p] = 0.0; e.f[p] = 0; }
+        for (int p = 0; p < 4; p++) { e.d[p] = 0.0; e.f[p] = 0; }
+    }
     const int i = rd.step, kn = i + 1;
     if (rd.type == RT_CBF) {
         const double *o = sm.obs[rd.obs];
@@ -145,39 +156,41 @@ __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<
         const double ax = sm.nodes[kn][0] - o[0], ay = sm.nodes[kn][1] - o[1], bx = sm.nodes[i][0] - o[0], by = sm.nodes[i][1] - o[1];
         const double ea = o[2], eb = o[3], ec = o[4];
         e.c = (ea * ax * ax + eb * ax * ay + ec * ay * ay - o[5]) + gm1 * (ea * bx * bx + eb * bx * by + ec * by * by - o[5]);
-        e.f[0] = FN(kn, 0); e.f[1] = FN(kn, 1);
-        e.d[0] = 2.0 * ea * ax + eb * ay; e.d[1] = 2.0 * ec * ay + eb * ax;
-        e.nf = 2;
-        if (i > 0) {
-            e.f[2] = FN(i, 0); e.f[3] = FN(i, 1);
-            e.d[2] = gm1 * (2.0 * ea * bx + eb * by); e.d[3] = gm1 * (2.0 * ec * by + eb * bx);
-            e.nf = 4;
+        if (GRAD) {
+            e.f[0] = FN(kn, 0); e.f[1] = FN(kn, 1);
+            e.d[0] = 2.0 * ea * ax + eb * ay; e.d[1] = 2.0 * ec * ay + eb * ax;
+            e.nf = 2;
+            if (i > 0) {
+                e.f[2] = FN(i, 0); e.f[3] = FN(i, 1);
+                e.d[2] = gm1 * (2.0 * ea * bx + eb * by); e.d[3] = gm1 * (2.0 * ec * by + eb * bx);
+                e.nf = 4;
+            }
+            e.hq0 = 2.0 * ea; e.hq1 = eb; e.hq2 = 2.0 * ec;
         }
-        e.hq0 = 2.0 * ea; e.hq1 = eb; e.hq2 = 2.0 * ec;
     } else if (rd.type == RT_VBX || rd.type == RT_VBY || rd.type == RT_FENP || rd.type == RT_FENM) {
         const double sn = sm.trig[kn][0], cs = sm.trig[kn][1];
         const double vx = sm.nodes[kn][2], vy = sm.nodes[kn][3];
         const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
-        e.f[0] = FN(kn, 2); e.f[1] = FN(kn, 3); e.f[2] = FN(kn, 4);
-        e.nf = 3;
+        if (GRAD) { e.f[0] = FN(kn, 2); e.f[1] = FN(kn, 3); e.f[2] = FN(kn, 4); e.nf = 3; }
         if (rd.type == RT_VBY) {
-            e.c = vby; e.d[0] = -sn; e.d[1] = cs; e.d[2] = -vbx;
+            e.c = vby;
+            if (GRAD) { e.d[0] = -sn; e.d[1] = cs; e.d[2] = -vbx; }
         } else {
-            e.d[0] = cs; e.d[1] = sn; e.d[2] = vby;
+            if (GRAD) { e.d[0] = cs; e.d[1] = sn; e.d[2] = vby; }
             if (rd.type == RT_VBX) e.c = vbx;
             else {
                 const double sg = rd.type == RT_FENP ? P.s_turn : -P.s_turn;
-                e.c = vbx + sg * zsel(z, 6 + i);
-                e.f[3] = FDT(i); e.d[3] = sg; e.nf = 4;
+                e.c = vbx + sg * z[6 + i];
+                if (GRAD) { e.f[3] = FDT(i); e.d[3] = sg; e.nf = 4; }
             }
         }
     } else if (rd.type == RT_LEG) {
-        const double lx = sm.nodes[i][0] - zsel(z, 2 * i), ly = sm.nodes[i][1] - zsel(z, 2 * i + 1);
+        const double lx = sm.nodes[i][0] - z[2 * i], ly = sm.nodes[i][1] - z[2 * i + 1];
         e.c = lx * lx + ly * ly;
-        e.f[0] = FLX(i); e.f[1] = FLY(i); e.d[0] = 2.0 * lx; e.d[1] = 2.0 * ly; e.nf = 2;
+        if (GRAD) { e.f[0] = FLX(i); e.f[1] = FLY(i); e.d[0] = 2.0 * lx; e.d[1] = 2.0 * ly; e.nf = 2; }
     } else if (rd.type == RT_DTH) {
-        e.c = zsel(z, 6 + i);
-        e.f[0] = FDT(i); e.d[0] = 1.0; e.nf = 1;
+        e.c = z[6 + i];
+        if (GRAD) { e.f[0] = FDT(i); e.d[0] = 1.0; e.nf = 1; }
     }
 }
 
@@ -187,16 +200,15 @@ struct WState {   // replicated scalars of one problem
     bool pending, reinit, first;
 };
 
-struct WStats { double theta, pinf, cmin, cmax, zsum, logsum, v2, vmax, f; int nz, nrows; };
-
 // ---------------------------------------------------------------------------------------------------------------
-// rollout + per-node trigonometry and objective terms (collective)
+// rollout + per-node trigonometry and objective terms at the point z (shared memory); collective, out of line
 // ---------------------------------------------------------------------------------------------------------------
 template <int NS>
-__device__ __forceinline__ void w_nodes(const Consts &k, const dcbf_params &P, WarpShared<NS> &sm, const double *x0, const double *goal,
-                                        const double *z, int lane, double sf, bool want_hess) {
+__device__ __noinline__ void w_nodes(const CtaShared &cs_, WarpShared<NS> &sm, const double *z, int lane, double sf, bool want_hess) {
+    const Consts &k = cs_.K;
+    const dcbf_params &P = cs_.P;
     if (lane == 0) {
-        double x = x0[0], y = x0[1], vx = x0[2], vy = x0[3], th = x0[4];
+        double x = sm.x0[0], y = sm.x0[1], vx = sm.x0[2], vy = sm.x0[3], th = sm.x0[4];
         sm.nodes[0][0] = x; sm.nodes[0][1] = y; sm.nodes[0][2] = vx; sm.nodes[0][3] = vy; sm.nodes[0][4] = th;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
@@ -208,56 +220,65 @@ __device__ __forceinline__ void w_nodes(const Consts &k, const dcbf_params &P, W
         }
     }
     __syncwarp();
-    {
-        const int kn = lane % 3 + 1;
+    if (lane < 3) {
+        const int kn = lane + 1;
         const double th = sm.nodes[kn][4];
         double sn, cs;
         dsincos(th, &sn, &cs);
         const double w = P.w_q + (kn == 1 ? P.w_p : 0.0);
-        const double ex = sm.nodes[kn][0] - goal[0], ey = sm.nodes[kn][1] - goal[1];
+        const double ex = sm.nodes[kn][0] - sm.goal[0], ey = sm.nodes[kn][1] - sm.goal[1];
         const double dx = -ex, dy = -ey;
         const double r2 = dx * dx + dy * dy, ir2 = 1.0 / r2;
         const double tar = datan2(dy, dx);
         const double phi = th - tar;
-        if (lane < 3) {
-            sm.trig[kn][0] = sn; sm.trig[kn][1] = cs; sm.trig[kn][2] = tar;
-            const double px = -dy * ir2, py = dx * ir2;
-            sm.nobj[kn][0] = w * (ex * ex + ey * ey) + P.w_r * phi * phi;
-            sm.nobj[kn][1] = 2.0 * w * ex + 2.0 * P.w_r * phi * px;
-            sm.nobj[kn][2] = 2.0 * w * ey + 2.0 * P.w_r * phi * py;
-            sm.nobj[kn][3] = 2.0 * P.w_r * phi;
-            if (want_hess) {
-                const double ir4 = ir2 * ir2;
-                const double pxx = -2.0 * dx * dy * ir4, pyy = -pxx, pxy = (dx * dx - dy * dy) * ir4;
-                const double r2w = 2.0 * P.w_r * sf;
-                sm.nobj[kn][4] = sf * 2.0 * w + r2w * (px * px + phi * pxx);
-                sm.nobj[kn][5] = r2w * (px * py + phi * pxy);
-                sm.nobj[kn][6] = sf * 2.0 * w + r2w * (py * py + phi * pyy);
-                sm.nobj[kn][7] = r2w * px; sm.nobj[kn][8] = r2w * py; sm.nobj[kn][9] = r2w;
-            }
+        sm.trig[kn][0] = sn; sm.trig[kn][1] = cs; sm.trig[kn][2] = tar;
+        const double px = -dy * ir2, py = dx * ir2;
+        sm.nobj[kn][0] = w * (ex * ex + ey * ey) + P.w_r * phi * phi;
+        sm.nobj[kn][1] = 2.0 * w * ex + 2.0 * P.w_r * phi * px;
+        sm.nobj[kn][2] = 2.0 * w * ey + 2.0 * P.w_r * phi * py;
+        sm.nobj[kn][3] = 2.0 * P.w_r * phi;
+        if (want_hess) {
+            const double ir4 = ir2 * ir2;
+            const double pxx = -2.0 * dx * dy * ir4, pyy = -pxx, pxy = (dx * dx - dy * dy) * ir4;
+            const double r2w = 2.0 * P.w_r * sf;
+            sm.nobj[kn][4] = sf * 2.0 * w + r2w * (px * px + phi * pxx);
+            sm.nobj[kn][5] = r2w * (px * py + phi * pxy);
+            sm.nobj[kn][6] = sf * 2.0 * w + r2w * (py * py + phi * pyy);
+            sm.nobj[kn][7] = r2w * px; sm.nobj[kn][8] = r2w * py; sm.nobj[kn][9] = r2w;
         }
     }
     __syncwarp();
 }
 
+// column reductions of the staged row statistics: lane c < 8 reduces column c over all rows
+// columns: 0 sum, 1 max, 2 min, 3 max, 4 sum, 5 sum, 6 sum, 7 max
+template <int NS>
+__device__ __forceinline__ void reduce_stats(WarpShared<NS> &sm, int lane) {
+    __syncwarp();
+    if (lane < 8) {
+        const bool is_sum = lane == 0 || lane == 4 || lane == 5 || lane == 6, is_min = lane == 2;
+        double acc = sm.ST[0][lane];
+        for (int r = 1; r < 32 * NS; r++) {
+            const double v = sm.ST[r][lane];
+            acc = is_sum ? acc + v : (is_min ? fmin(acc, v) : fmax(acc, v));
+        }
+        sm.red[lane] = acc;
+    }
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// the solver for one problem (all 32 lanes call it with identical arguments)
+// the solver for one problem (all 32 lanes call it with identical arguments).  Inputs in sm: x0, graw, zc.
 // ---------------------------------------------------------------------------------------------------------------
 template <int NS>
-__device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const double (*T)[9], WarpShared<NS> &sm, const BatchIn &in, int b,
-                               int lane, double *z, double *x0, double *goal_raw, int &leg, WState &S, bool do_setup_inputs) {
+__device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const BatchIn &in, int b, int lane, int leg, WState &S) {
+    const dcbf_params &P = cs_.P;
+    const double (*T)[9] = cs_.T;
     // ---- problem setup -------------------------------------------------------------------------------------------
-    if (do_setup_inputs) {
-#pragma unroll
-        for (int i = 0; i < 5; i++) x0[i] = in.x0[5 * (size_t)b + i];
-        goal_raw[0] = in.goal[2 * (size_t)b]; goal_raw[1] = in.goal[2 * (size_t)b + 1];
-        leg = in.leg ? in.leg[b] : 1;
-    }
     const int fld = in.field ? in.field[b] : 0;
     const double *cir = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC;
     const double *elp = in.elp_rec + (size_t)fld * in.Ke * DCBF_ELP_REC;
-    const double px = x0[0], py = x0[1];
-    double goal[2] = {goal_raw[0], goal_raw[1]};
+    const double px = sm.x0[0], py = sm.x0[1];
     int Ks;
     {
         // one lane per obstacle: selection (MPC_LIP_modi.py:325-338), compaction, detour heuristic (MPC_LIP_sig_step.py:229-253)
@@ -284,9 +305,9 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
         }
         bool hit = false;
         double ngx = 0.0, ngy = 0.0;
+        const double gx = sm.graw[0], gy = sm.graw[1];
         if (P.goal_shift && sel && is_c) {
             const double PI = 3.14159265358979323846;
-            const double gx = goal_raw[0], gy = goal_raw[1];
             const double dg = (px - gx) * (px - gx) + (py - gy) * (py - gy);
             const double dc = (px - rec[0]) * (px - rec[0]) + (py - rec[1]) * (py - rec[1]);
             if (dc < dg && dc < 9.0 * rec[5]) {
@@ -304,10 +325,12 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
             }
         }
         const unsigned hm = __ballot_sync(FULL, hit);
+        double g0 = gx, g1 = gy;
         if (hm) {
             const int src = __ffs(hm) - 1;
-            goal[0] = __shfl_sync(FULL, ngx, src); goal[1] = __shfl_sync(FULL, ngy, src);
+            g0 = __shfl_sync(FULL, ngx, src); g1 = __shfl_sync(FULL, ngy, src);
         }
+        if (lane == 0) { sm.goal[0] = g0; sm.goal[1] = g1; }
         __syncwarp();
     }
     const bool has_fen = P.has_fen != 0;
@@ -315,13 +338,16 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
     RowDesc rd[NS];
     RowBnd rb[NS];
     double rs[NS], rzl[NS], rzu[NS], rds[NS], rel[NS], reu[NS];
+    int nz_l = 0;
 #pragma unroll
     for (int s = 0; s < NS; s++) {
         rd[s] = row_desc(s * 32 + lane, Ks, has_fen);
         if (s * 32 + lane >= m) rd[s].type = RT_NONE;
         rb[s] = row_bounds(P, rd[s], leg);
+        nz_l += (rb[s].has_lo ? 1 : 0) + (rb[s].has_hi ? 1 : 0);
         rs[s] = rzl[s] = rzu[s] = rds[s] = rel[s] = reu[s] = 0.0;
     }
+    const int nz = wsumi(nz_l), nrows = m;
     // ---- solver state ------------------------------------------------------------------------------------------------
     S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4; S.resto_target = 0.0;
     S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1;
@@ -330,8 +356,7 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
 
     for (;;) {
         const bool resto = S.phase == PH_RESTO;
-        const double sf_eff = resto ? 0.0 : S.sf;
-        w_nodes<NS>(k, P, sm, x0, goal, z, lane, S.first ? 1.0 : sf_eff, true);
+        w_nodes<NS>(cs_, sm, sm.zc, lane, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
         // objective value and gradient (lane a < 9 owns grad[a])
         const double fobj = sm.nobj[1][0] + sm.nobj[2][0] + sm.nobj[3][0];
         double grad_a = 0.0;
@@ -343,29 +368,26 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
         if (S.first) {
             const double gmax = wmax(fabs(grad_a));
             S.sf = gmax > 100.0 ? 100.0 / gmax : 1.0;
-            // the objective Hessian staged above used sf = 1: rescale
-            if (lane < 3) {
+            if (lane < 3) {   // the objective Hessian staged above used sf = 1: rescale
 #pragma unroll
                 for (int c = 4; c < 10; c++) sm.nobj[lane + 1][c] *= S.sf;
             }
             __syncwarp();
         }
-        // ---- rows: evaluate, update row state, stage gradients and weights ------------------------------------------
-        WStats st;
-        st.theta = 0.0; st.pinf = 0.0; st.cmin = 1e300; st.cmax = 0.0; st.zsum = 0.0; st.logsum = 0.0; st.v2 = 0.0; st.vmax = 0.0;
-        st.nz = 0; st.nrows = 0; st.f = fobj;
+        // ---- rows: evaluate, update row state, stage gradients, weights and statistics ------------------------------------
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             const int r = s * 32 + lane;
             RowEval e;
-            eval_row<NS>(P, sm, rd[s], z, e);
+            eval_row<NS, true>(P, sm, rd[s], sm.zc, e);
             const RowBnd &bb = rb[s];
             double sig = 0.0, w1 = 0.0, binv = 0.0, y = 0.0;
+            double t_rc = 0.0, t_cmin = 1e300, t_cmax = 0.0, t_z = 0.0, t_log = 0.0, t_v2 = 0.0, t_v = 0.0;
             if (rd[s].type != RT_NONE) {
                 double v = 0.0;
                 if (bb.has_lo && e.c < bb.lo) v = e.c - bb.lo;
                 if (bb.has_hi && e.c > bb.hi) v = e.c - bb.hi;
-                st.v2 += v * v; st.vmax = fmax(st.vmax, fabs(v)); st.nrows++;
+                t_v2 = v * v; t_v = fabs(v);
                 if (resto) {
                     sig = v != 0.0 ? 1.0 : 0.0; w1 = v; y = v;
                 } else {
@@ -396,23 +418,23 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
                         const double gap = rs[s] - lr, inv = 1.0 / gap;
                         sig += rzl[s] * inv; binv += inv; y -= rzl[s];
                         const double cz = gap * rzl[s];
-                        st.cmin = fmin(st.cmin, cz); st.cmax = fmax(st.cmax, cz); st.zsum += rzl[s]; st.nz++;
+                        t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzl[s];
                         lp *= gap; rel[s] = inv;
                     }
                     if (bb.has_hi) {
                         const double gap = hr - rs[s], inv = 1.0 / gap;
                         sig += rzu[s] * inv; binv -= inv; y += rzu[s];
                         const double cz = gap * rzu[s];
-                        st.cmin = fmin(st.cmin, cz); st.cmax = fmax(st.cmax, cz); st.zsum += rzu[s]; st.nz++;
+                        t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzu[s];
                         lp *= gap; reu[s] = inv;
                     }
-                    st.logsum += dlog(lp);
+                    t_log = dlog(lp);
                     rds[s] = rc;
-                    st.theta += fabs(rc); st.pinf = fmax(st.pinf, fabs(rc));
+                    t_rc = fabs(rc);
                     w1 = sig * rc;
                 }
             }
-            // stage (rows beyond m stage zeros so that the entry-parallel loops need no guards)
+            // stage (rows beyond m stage neutral values so that the entry-parallel loops need no guards)
             double g[9];
 #pragma unroll
             for (int a = 0; a < 9; a++) g[a] = 0.0;
@@ -429,14 +451,12 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
             for (int a = 0; a < 9; a++) sm.G[r][a] = g[a];
             sm.RW[r][0] = sig; sm.RW[r][1] = w1; sm.RW[r][2] = binv; sm.RW[r][3] = y;
             sm.HQ[r][0] = y * e.hq0; sm.HQ[r][1] = y * e.hq1; sm.HQ[r][2] = y * e.hq2;
+            sm.ST[r][0] = t_rc; sm.ST[r][1] = t_rc; sm.ST[r][2] = t_cmin; sm.ST[r][3] = t_cmax;
+            sm.ST[r][4] = t_z; sm.ST[r][5] = t_log; sm.ST[r][6] = t_v2; sm.ST[r][7] = t_v;
         }
-        __syncwarp();
-        // ---- statistics ------------------------------------------------------------------------------------------------
-        st.v2 = wsum(st.v2); st.vmax = wmax(st.vmax); st.nrows = wsumi(st.nrows);
-        if (!resto) {
-            st.theta = wsum(st.theta); st.pinf = wmax(st.pinf); st.cmin = wmin(st.cmin); st.cmax = wmax(st.cmax);
-            st.zsum = wsum(st.zsum); st.logsum = wsum(st.logsum); st.nz = wsumi(st.nz);
-        }
+        reduce_stats<NS>(sm, lane);
+        const double st_theta = sm.red[0], st_pinf = sm.red[1], st_cmin = sm.red[2], st_cmax = sm.red[3], st_zsum = sm.red[4],
+                     st_logsum = sm.red[5], st_v2 = sm.red[6], st_vmax = sm.red[7];
         // ---- node Hessians ---------------------------------------------------------------------------------------------
         {
             const double gm1 = P.gamma - 1.0;
@@ -461,61 +481,47 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
         }
         __syncwarp();
         // ---- condensed matrix and J^T vectors, entry-parallel (72 entries over 32 lanes) ---------------------------------------
-        {
+        for (int e = lane; e < 72; e += 32) {
+            const int a = cs_.ea[e], bcol = cs_.eb[e];
+            double acc = 0.0;
+            if (e < 45) {
+                for (int r = 0; r < m; r++) acc = fma(sm.RW[r][0] * sm.G[r][a], sm.G[r][bcol], acc);
+                // Lagrangian Hessian through the feature map
 #pragma unroll
-            for (int pass = 0; pass < 3; pass++) {
-                const int e = pass * 32 + lane;
-                if (e < 45) {
-                    int a = 0;
-                    while ((a + 1) * (a + 2) / 2 <= e) a++;
-                    const int bcol = e - a * (a + 1) / 2;
-                    double acc = 0.0;
-                    for (int r = 0; r < 32 * NS; r++) {
-                        if (r >= m) break;
-                        acc = fma(sm.RW[r][0] * sm.G[r][a], sm.G[r][bcol], acc);
-                    }
-                    // Lagrangian Hessian through the feature map
-#pragma unroll
-                    for (int kn = 1; kn <= 3; kn++) {
-                        const double Xa = T[FN(kn, 0)][a], Ya = T[FN(kn, 1)][a], VXa = T[FN(kn, 2)][a], VYa = T[FN(kn, 3)][a], Ta = T[FN(kn, 4)][a];
-                        const double Xb = T[FN(kn, 0)][bcol], Yb = T[FN(kn, 1)][bcol], VXb = T[FN(kn, 2)][bcol], VYb = T[FN(kn, 3)][bcol], Tb = T[FN(kn, 4)][bcol];
-                        const double *H = sm.NH[kn];
-                        const double ux = H[0] * Xb + H[1] * Yb + H[3] * Tb;
-                        const double uy = H[1] * Xb + H[2] * Yb + H[4] * Tb;
-                        const double ut = H[3] * Xb + H[4] * Yb + H[5] * Tb + H[6] * VXb + H[7] * VYb;
-                        acc += Xa * ux + Ya * uy + Ta * ut + (VXa * H[6] + VYa * H[7]) * Tb;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 3; i++)
-                        acc += sm.legy[i] * (T[FLX(i)][a] * T[FLX(i)][bcol] + T[FLY(i)][a] * T[FLY(i)][bcol]);
-                    sm.Kf[e] = acc;
-                } else if (e < 72) {
-                    const int t = e - 45, v = t / 9, a = t - 9 * v;
-                    double acc = 0.0;
-                    for (int r = 0; r < 32 * NS; r++) {
-                        if (r >= m) break;
-                        acc = fma(sm.RW[r][1 + v], sm.G[r][a], acc);
-                    }
-                    sm.q[t] = acc;
+                for (int kn = 1; kn <= 3; kn++) {
+                    const double Xa = T[FN(kn, 0)][a], Ya = T[FN(kn, 1)][a], VXa = T[FN(kn, 2)][a], VYa = T[FN(kn, 3)][a], Ta = T[FN(kn, 4)][a];
+                    const double Xb = T[FN(kn, 0)][bcol], Yb = T[FN(kn, 1)][bcol], VXb = T[FN(kn, 2)][bcol], VYb = T[FN(kn, 3)][bcol], Tb = T[FN(kn, 4)][bcol];
+                    const double *H = sm.NH[kn];
+                    const double ux = H[0] * Xb + H[1] * Yb + H[3] * Tb;
+                    const double uy = H[1] * Xb + H[2] * Yb + H[4] * Tb;
+                    const double ut = H[3] * Xb + H[4] * Yb + H[5] * Tb + H[6] * VXb + H[7] * VYb;
+                    acc += Xa * ux + Ya * uy + Ta * ut + (VXa * H[6] + VYa * H[7]) * Tb;
                 }
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+                    acc += sm.legy[i] * (T[FLX(i)][a] * T[FLX(i)][bcol] + T[FLY(i)][a] * T[FLY(i)][bcol]);
+                sm.Kf[e] = acc;
+            } else {
+                for (int r = 0; r < m; r++) acc = fma(sm.RW[r][bcol], sm.G[r][a], acc);   // bcol = 1 + vector index
+                sm.q[e - 45] = acc;
             }
         }
         __syncwarp();
         S.pending = false; S.reinit = false;
-        S.obj = st.f; S.viol = st.vmax;
-        if (!(st.f == st.f) || !(st.theta == st.theta)) { S.status = -13; break; }
+        S.obj = fobj; S.viol = st_vmax;
+        if (!(fobj == fobj) || !(st_theta == st_theta)) { S.status = -13; break; }
         // ---- convergence / barrier update / right-hand side ---------------------------------------------------------------
         double rhs_a = 0.0;
         if (!resto) {
-            if (S.first) { S.theta_max = 1e4 * fmax(1.0, st.theta); S.theta_min = 1e-4 * fmax(1.0, st.theta); S.first = false; }
+            if (S.first) { S.theta_max = 1e4 * fmax(1.0, st_theta); S.theta_min = 1e-4 * fmax(1.0, st_theta); S.first = false; }
             const double dinf = wmax(lane < 9 ? fabs(fma(S.sf, grad_a, sm.q[18 + lane])) : 0.0);
-            const double sd = fmax(100.0, 2.0 * st.zsum / (double)(st.nrows + st.nz)) * 0.01;
-            const double sc = fmax(100.0, st.zsum / (double)(st.nz > 0 ? st.nz : 1)) * 0.01;
+            const double sd = fmax(100.0, 2.0 * st_zsum / (double)(nrows + nz)) * 0.01;
+            const double sc = fmax(100.0, st_zsum / (double)(nz > 0 ? nz : 1)) * 0.01;
             double E0;
             for (;;) {
-                const double compm = fmax(fabs(st.cmax - S.mu), fabs(st.cmin - S.mu));
-                E0 = fmax(fmax(dinf / sd, st.pinf), st.cmax / sc);
-                const double Emu = fmax(fmax(dinf / sd, st.pinf), compm / sc);
+                const double compm = fmax(fabs(st_cmax - S.mu), fabs(st_cmin - S.mu));
+                E0 = fmax(fmax(dinf / sd, st_pinf), st_cmax / sc);
+                const double Emu = fmax(fmax(dinf / sd, st_pinf), compm / sc);
                 if (E0 <= tol) break;
                 if (Emu <= 10.0 * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
                     S.mu = fmax(tol * 0.1, fmin(0.2 * S.mu, S.mu * sqrt(S.mu)));
@@ -525,145 +531,163 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
                 break;
             }
             if (E0 <= tol) { S.status = 0; break; }
-            if (E0 <= 1e-6 && st.vmax <= P.constr_viol_tol) { if (++S.acc_cnt >= 15) { S.status = 1; break; } } else S.acc_cnt = 0;
+            if (E0 <= 1e-6 && st_vmax <= P.constr_viol_tol) { if (++S.acc_cnt >= 15) { S.status = 1; break; } } else S.acc_cnt = 0;
             if (S.iters >= P.max_iter) { S.status = -1; break; }
             if (lane < 9) rhs_a = -S.sf * grad_a - sm.q[lane] + S.mu * sm.q[9 + lane];
         } else {
-            if (st.vmax <= S.resto_target) { S.phase = PH_MAIN; S.reinit = true; continue; }
+            if (st_vmax <= S.resto_target) { S.phase = PH_MAIN; S.reinit = true; continue; }
             const double gn = wmax(lane < 9 ? fabs(sm.q[lane]) : 0.0);
-            const bool stationary = gn <= 1e-10 * fmax(1.0, st.vmax) || S.lm_lambda > 1e12;
+            const bool stationary = gn <= 1e-10 * fmax(1.0, st_vmax) || S.lm_lambda > 1e12;
             if (stationary) {
-                if (st.vmax > P.constr_viol_tol) { S.status = 2; break; }
+                if (st_vmax > P.constr_viol_tol) { S.status = 2; break; }
                 if (S.resto_entry <= 1e-9) { S.status = -2; break; }
                 S.phase = PH_MAIN; S.reinit = true; continue;
             }
             if (S.iters >= P.max_iter) { S.status = -1; break; }
-            if (lane < 9) { rhs_a = -sm.q[lane]; sm.Kf[tri(lane, lane)] += S.lm_lambda; }
-            __syncwarp();
+            if (lane < 9) rhs_a = -sm.q[lane];
         }
-        // ---- Cholesky (lane i owns row i), inertia correction by delta ----------------------------------------------------
-        double delta = 0.0;
-        bool ok = false;
-        for (int tr = 0; tr < 48; tr++) {
-            double Lrow[9];
-            ok = true;
+        // ---- restoration: Levenberg-Marquardt trials reuse the assembled K while lambda is escalated ---------------------------
+        // ---- main phase: one factorisation with inertia correction by delta ----------------------------------------------------
+        bool lm_accept = false;
+        double v2t = 0.0, vmt = 0.0;
+        for (int rt = 0; rt < 20; rt++) {
+            double shift = resto ? S.lm_lambda : 0.0;
+            bool ok = false;
+            for (int tr = 0; tr < 48; tr++) {
+                double Lrow[9];
+                ok = true;
 #pragma unroll
-            for (int j = 0; j < 9; j++) {
-                // lanes i >= j: s = K[i][j] - sum_{c<j} L[i][c] L[j][c]
-                double s_ = 0.0;
-                if (lane >= j && lane < 9) {
-                    s_ = sm.Kf[tri(lane, j)] + (lane == j ? delta : 0.0);
+                for (int j = 0; j < 9; j++) {
+                    double s_ = 0.0;
+                    if (lane >= j && lane < 9) {
+                        s_ = sm.Kf[tri(lane, j)] + (lane == j ? shift : 0.0);
 #pragma unroll
-                    for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[tri(j, c)], s_);
+                        for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[tri(j, c)], s_);
+                    }
+                    const double d = __shfl_sync(FULL, s_, j);
+                    if (!(d > 1e-14)) { ok = false; break; }
+                    const double rinv = drsqrt(d);
+                    Lrow[j] = lane == j ? rinv : s_ * rinv;   // diagonal stored as its reciprocal
+                    if (lane >= j && lane < 9) sm.Lf[tri(lane, j)] = Lrow[j];
+                    __syncwarp();
                 }
-                const double d = __shfl_sync(FULL, s_, j);
-                if (!(d > 1e-14)) { ok = false; break; }
-                const double rinv = drsqrt(d);
-                Lrow[j] = lane == j ? rinv : s_ * rinv;   // diagonal stored as its reciprocal
-                if (lane >= j && lane < 9) sm.Lf[tri(lane, j)] = Lrow[j];
-                __syncwarp();
+                if (ok || resto) break;
+                if (shift == 0.0) shift = S.delta_last == 0.0 ? 1e-4 : fmax(1e-20, S.delta_last * (1.0 / 3.0));
+                else shift *= (S.delta_last == 0.0 ? 100.0 : 8.0);
             }
-            if (ok) break;
-            if (delta == 0.0) delta = S.delta_last == 0.0 ? 1e-4 : fmax(1e-20, S.delta_last * (1.0 / 3.0));
-            else delta *= (S.delta_last == 0.0 ? 100.0 : 8.0);
-        }
-        if (!ok) { S.status = -3; break; }
-        if (delta > 0.0) S.delta_last = delta;
-        // ---- triangular solves: lane i holds component i ------------------------------------------------------------------
-        {
-            double bi = rhs_a;
-#pragma unroll
-            for (int c = 0; c < 9; c++) {
-                const double yc = __shfl_sync(FULL, bi * sm.Lf[tri(c, c)], c);   // y_c = b_c / L_cc
-                if (lane == c) bi = yc;
-                else if (lane > c && lane < 9) bi = fma(-sm.Lf[tri(lane, c)], yc, bi);
+            if (!ok) {
+                if (!resto) { S.status = -3; break; }
+                S.lm_lambda *= 10.0;
+                if (S.lm_lambda > 1e12) break;
+                continue;
             }
+            if (!resto && shift > 0.0) S.delta_last = shift;
+            // triangular solves: lane i holds component i
+            {
+                double bi = rhs_a;
 #pragma unroll
-            for (int c = 8; c >= 0; c--) {
-                const double xc = __shfl_sync(FULL, bi * sm.Lf[tri(c, c)], c);
-                if (lane == c) bi = xc;
-                else if (lane < c) bi = fma(-sm.Lf[tri(c, lane)], xc, bi);
+                for (int c = 0; c < 9; c++) {
+                    const double yc = __shfl_sync(FULL, bi * sm.Lf[tri(c, c)], c);   // y_c = b_c / L_cc
+                    if (lane == c) bi = yc;
+                    else if (lane > c && lane < 9) bi = fma(-sm.Lf[tri(lane, c)], yc, bi);
+                }
+#pragma unroll
+                for (int c = 8; c >= 0; c--) {
+                    const double xc = __shfl_sync(FULL, bi * sm.Lf[tri(c, c)], c);
+                    if (lane == c) bi = xc;
+                    else if (lane < c) bi = fma(-sm.Lf[tri(c, lane)], xc, bi);
+                }
+                if (lane < 9) sm.dz[lane] = bi;
             }
-            if (lane < 9) sm.dz[lane] = bi;
-        }
-        __syncwarp();
-        if (resto) {
-            // Levenberg-Marquardt trial at full step
-            double zt[9];
-#pragma unroll
-            for (int a = 0; a < 9; a++) zt[a] = z[a] + sm.dz[a];
-            w_nodes<NS>(k, P, sm, x0, goal, zt, lane, 0.0, false);
-            double v2t = 0.0, vmt = 0.0;
+            __syncwarp();
+            if (!resto) break;
+            // Levenberg-Marquardt trial at full step (violation only)
+            if (lane < 9) sm.zt[lane] = sm.zc[lane] + sm.dz[lane];
+            __syncwarp();
+            w_nodes<NS>(cs_, sm, sm.zt, lane, 0.0, false);
+            v2t = 0.0; vmt = 0.0;
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 if (rd[s].type == RT_NONE) continue;
                 RowEval e;
-                eval_row<NS>(P, sm, rd[s], zt, e);
+                eval_row<NS, false>(P, sm, rd[s], sm.zt, e);
                 double v = 0.0;
                 if (rb[s].has_lo && e.c < rb[s].lo) v = e.c - rb[s].lo;
                 if (rb[s].has_hi && e.c > rb[s].hi) v = e.c - rb[s].hi;
                 v2t += v * v; vmt = fmax(vmt, fabs(v));
             }
-            v2t = wsum(v2t); vmt = wmax(vmt);
-            if (v2t < st.v2 * (1.0 - 1e-12)) {
-                double dn = 0.0;
 #pragma unroll
-                for (int a = 0; a < 9; a++) { dn = fmax(dn, fabs(sm.dz[a])); z[a] = zt[a]; }
+            for (int o = 16; o > 0; o >>= 1) {
+                v2t += __shfl_xor_sync(FULL, v2t, o);
+                vmt = fmax(vmt, __shfl_xor_sync(FULL, vmt, o));
+            }
+            if (v2t < st_v2 * (1.0 - 1e-12)) { lm_accept = true; break; }
+            S.lm_lambda *= 10.0;
+            if (S.lm_lambda > 1e12) break;
+        }
+        if (S.status == -3) break;
+        if (resto) {
+            if (lm_accept) {
+                double dn = lane < 9 ? fabs(sm.dz[lane]) : 0.0;
+                dn = wmax(dn);
+                if (lane < 9) sm.zc[lane] = sm.zt[lane];
                 S.iters++;
                 S.lm_lambda = fmax(S.lm_lambda * 0.2, 1e-12);
-                if (st.v2 - v2t <= 1e-4 * st.v2) S.acc_cnt++; else S.acc_cnt = 0;
+                if (st_v2 - v2t <= 1e-4 * st_v2) S.acc_cnt++; else S.acc_cnt = 0;
                 if ((dn < 1e-12 || S.acc_cnt >= 2) && vmt > S.resto_target) S.lm_lambda = 1e13;
-            } else {
-                S.lm_lambda *= 10.0;
             }
             __syncwarp();
             continue;
         }
-        // ---- direction pass: ds, dz_L, dz_U, step sizes ---------------------------------------------------------------------
-        const double tau = fmax(0.99, 1.0 - S.mu);
+        // ---- direction pass (main phase): ds, dz_L, dz_U, step sizes -----------------------------------------------------------
         double amax = 1.0, az = 1.0, dphi = 0.0;
-        double dzr[9];
+        {
+            const double tau = fmax(0.99, 1.0 - S.mu);
+            if (lane < 9) dphi = S.sf * grad_a * sm.dz[lane];
 #pragma unroll
-        for (int a = 0; a < 9; a++) dzr[a] = sm.dz[a];
-        if (lane < 9) dphi = S.sf * grad_a * zsel(dzr, lane);
+            for (int s = 0; s < NS; s++) {
+                if (rd[s].type == RT_NONE) continue;
+                const int r = s * 32 + lane;
+                double jd = 0.0;
 #pragma unroll
-        for (int s = 0; s < NS; s++) {
-            if (rd[s].type == RT_NONE) continue;
-            const int r = s * 32 + lane;
-            double jd = 0.0;
-#pragma unroll
-            for (int a = 0; a < 9; a++) jd = fma(sm.G[r][a], dzr[a], jd);
-            const RowBnd &e = rb[s];
-            const double d = jd + rds[s];
-            rds[s] = d;
-            if (e.has_lo) {
-                const double inv = rel[s], gap = rs[s] - relax_lo(e.lo);
-                const double dzl = S.mu * inv - rzl[s] - rzl[s] * inv * d;
-                rel[s] = dzl;
-                dphi -= S.mu * d * inv;
-                if (d < 0.0) amax = fmin(amax, -tau * gap / d);
-                if (dzl < 0.0) az = fmin(az, -tau * rzl[s] / dzl);
+                for (int a = 0; a < 9; a++) jd = fma(sm.G[r][a], sm.dz[a], jd);
+                const RowBnd &e = rb[s];
+                const double d = jd + rds[s];
+                rds[s] = d;
+                if (e.has_lo) {
+                    const double inv = rel[s], gap = rs[s] - relax_lo(e.lo);
+                    const double dzl = S.mu * inv - rzl[s] - rzl[s] * inv * d;
+                    rel[s] = dzl;
+                    dphi -= S.mu * d * inv;
+                    if (d < 0.0) amax = fmin(amax, -tau * gap / d);
+                    if (dzl < 0.0) az = fmin(az, -tau * rzl[s] / dzl);
+                }
+                if (e.has_hi) {
+                    const double inv = reu[s], gap = relax_hi(e.hi) - rs[s];
+                    const double dzu = S.mu * inv - rzu[s] + rzu[s] * inv * d;
+                    reu[s] = dzu;
+                    dphi += S.mu * d * inv;
+                    if (d > 0.0) amax = fmin(amax, tau * gap / d);
+                    if (dzu < 0.0) az = fmin(az, -tau * rzu[s] / dzu);
+                }
             }
-            if (e.has_hi) {
-                const double inv = reu[s], gap = relax_hi(e.hi) - rs[s];
-                const double dzu = S.mu * inv - rzu[s] + rzu[s] * inv * d;
-                reu[s] = dzu;
-                dphi += S.mu * d * inv;
-                if (d > 0.0) amax = fmin(amax, tau * gap / d);
-                if (dzu < 0.0) az = fmin(az, -tau * rzu[s] / dzu);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {   // three reductions interleaved
+                amax = fmin(amax, __shfl_xor_sync(FULL, amax, o));
+                az = fmin(az, __shfl_xor_sync(FULL, az, o));
+                dphi += __shfl_xor_sync(FULL, dphi, o);
             }
         }
-        amax = wmin(amax); az = wmin(az); dphi = wsum(dphi);
-        const double theta = st.theta;
-        const double phi = S.sf * st.f - S.mu * st.logsum;
+        // ---- filter line search -------------------------------------------------------------------------------------------------
+        const double theta = st_theta;
+        const double phi = S.sf * fobj - S.mu * st_logsum;
         const double eps_phi = 10.0 * 2.2e-16 * fabs(phi);
         double alpha = amax;
         int accepted = 0;
-        double zt[9];
         for (int ls = 0; ls < DCBF_LS_MAX; ls++, alpha *= 0.5) {
-#pragma unroll
-            for (int a = 0; a < 9; a++) zt[a] = fma(alpha, dzr[a], z[a]);
-            w_nodes<NS>(k, P, sm, x0, goal, zt, lane, 0.0, false);
+            if (lane < 9) sm.zt[lane] = fma(alpha, sm.dz[lane], sm.zc[lane]);
+            __syncwarp();
+            w_nodes<NS>(cs_, sm, sm.zt, lane, 0.0, false);
             const double ft = sm.nobj[1][0] + sm.nobj[2][0] + sm.nobj[3][0];
             double th_t = 0.0, lg_t = 0.0;
             bool okv = true;
@@ -671,7 +695,7 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
             for (int s = 0; s < NS; s++) {
                 if (rd[s].type == RT_NONE) continue;
                 RowEval e;
-                eval_row<NS>(P, sm, rd[s], zt, e);
+                eval_row<NS, false>(P, sm, rd[s], sm.zt, e);
                 const double stv = rs[s] + alpha * rds[s];
                 th_t += fabs(e.c - stv);
                 double lp = 1.0;
@@ -679,9 +703,12 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
                 if (rb[s].has_hi) { const double gap = relax_hi(rb[s].hi) - stv; if (!(gap > 0.0)) okv = false; lp *= gap; }
                 lg_t += dlog(lp);
             }
-            th_t = wsum(th_t); lg_t = wsum(lg_t);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                th_t += __shfl_xor_sync(FULL, th_t, o);
+                lg_t += __shfl_xor_sync(FULL, lg_t, o);
+            }
             okv = __all_sync(FULL, okv);
-            __syncwarp();
             const double ph_t = S.sf * ft - S.mu * lg_t;
             if (!okv || !(ph_t == ph_t) || !(th_t <= S.theta_max)) continue;
             bool in_filter = false;
@@ -700,28 +727,45 @@ __device__ void solve_lip_warp(const dcbf_params &P, const Consts &k, const doub
             __syncwarp();
         }
         if (!accepted) {
-            S.phase = PH_RESTO; S.resto_entry = st.vmax; S.resto_target = fmax(0.1 * st.vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0;
+            S.phase = PH_RESTO; S.resto_entry = st_vmax; S.resto_target = fmax(0.1 * st_vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0;
             S.iters++;
             continue;
         }
-#pragma unroll
-        for (int a = 0; a < 9; a++) z[a] = zt[a];
+        if (lane < 9) sm.zc[lane] = sm.zt[lane];
+        __syncwarp();
         S.alpha = alpha; S.alpha_z = az; S.pending = true;
         S.iters++;
     }
-    // sm.nodes holds the rollout of the final z only if the last collective call was the full pass: refresh
-    w_nodes<NS>(k, P, sm, x0, goal, z, lane, 0.0, false);
+    // make sm.nodes the rollout of the final iterate
+    w_nodes<NS>(cs_, sm, sm.zc, lane, 0.0, false);
 }
 
 template <int NS>
-__device__ __forceinline__ bool w_close(const dcbf_params &P, const WarpShared<NS> &sm, const double *goal_raw) {
+__device__ __forceinline__ bool w_close(const dcbf_params &P, const WarpShared<NS> &sm) {
     bool close = false;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const double dxg = sm.nodes[i + 1][0] - goal_raw[0], dyg = sm.nodes[i + 1][1] - goal_raw[1];
+        const double dxg = sm.nodes[i + 1][0] - sm.graw[0], dyg = sm.nodes[i + 1][1] - sm.graw[1];
         if ((i == 0 || P.close_any) && sqrt(dxg * dxg + dyg * dyg) <= P.close_radius) close = true;
     }
     return close;
+}
+
+// per-CTA staging of the constants
+__device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K, CtaShared &cs_) {
+    if (threadIdx.x == 0) { cs_.P = P; cs_.K = K; }
+    for (int e = threadIdx.x; e < 72; e += blockDim.x) {
+        if (e < 45) {
+            int a = 0;
+            while ((a + 1) * (a + 2) / 2 <= e) a++;
+            cs_.ea[e] = a; cs_.eb[e] = e - a * (a + 1) / 2;
+        } else {
+            const int t = e - 45;
+            cs_.ea[e] = t % 9; cs_.eb[e] = 1 + t / 9;
+        }
+    }
+    build_T(K, cs_.T);
+    __syncthreads();
 }
 
 }  // namespace wp
