@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libdcbf_mpc.so")
-SOURCES = ["dcbf_kernels.cu", "dcbf_core.cuh", "dcbf_lanes.cuh"]
+SOURCES = ["dcbf_kernels.cu", "dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_warp.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -65,10 +65,11 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(SO_PATH):
-        raise RuntimeError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("DCBF_LIB", SO_PATH)   # experiments with alternative builds of the same sources
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")
-    lib = C.CDLL(SO_PATH)
+    lib = C.CDLL(path)
     vp, dp, ip = C.c_void_p, C.c_void_p, C.c_void_p   # device/host pointers travel as integers
     lib.dcbf_abi_version.restype = C.c_int
     lib.dcbf_default_params.argtypes = [C.c_int, C.POINTER(DcbfParams)]

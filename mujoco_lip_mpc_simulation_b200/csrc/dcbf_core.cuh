@@ -98,7 +98,13 @@ DCBF_MATH void dsincos(double a, double *s, double *c) {
 }
 DCBF_MATH double datan2(double y, double x) { return atan2(y, x); }
 DCBF_MATH double dlog(double x) { return log(x); }
-DCBF_MATH double drsqrt(double x) { return 1.0 / sqrt(x); }
+DCBF_HD double drsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);   // MUFU.RSQ64H + Newton steps, <= 1 ulp; ~4x shorter than sqrt followed by a division
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 DCBF_MATH double drcp(double x) { return 1.0 / x; }
 // alpha * a^2.3 > t^1.1 for a > 0, t >= 0 (switching condition of the filter line search) without pow()
 DCBF_HD bool switch_cond(double alpha, double a, double t) {

@@ -31,9 +31,9 @@ __device__ __forceinline__ int FDT(int i) { return 21 + i; }
 template <int NS>
 struct WarpShared {
     double G[32 * NS][9];    // row gradients (internal variable order)
+    double SG[32 * NS][9];   // sigma * row gradient
     double RW[32 * NS][4];   // sigma, w1, binv, y
     double HQ[32 * NS][3];   // y * (2a', b', 2c') of the D-CBF rows
-    double ST[32 * NS][8];   // per-row statistics staged for the column reductions
     double obs[DCBF_KT][6];  // selected obstacles: cx, cy, a', b', c', rhs
     double Kf[45], Lf[45], q[27], dz[9], zc[9], zt[9], red[8];
     double x0[5], goal[2], graw[2];
@@ -250,21 +250,16 @@ __device__ __noinline__ void w_nodes(const CtaShared &cs_, WarpShared<NS> &sm, c
     __syncwarp();
 }
 
-// column reductions of the staged row statistics: lane c < 8 reduces column c over all rows
-// columns: 0 sum, 1 max, 2 min, 3 max, 4 sum, 5 sum, 6 sum, 7 max
-template <int NS>
-__device__ __forceinline__ void reduce_stats(WarpShared<NS> &sm, int lane) {
-    __syncwarp();
-    if (lane < 8) {
-        const bool is_sum = lane == 0 || lane == 4 || lane == 5 || lane == 6, is_min = lane == 2;
-        double acc = sm.ST[0][lane];
-        for (int r = 1; r < 32 * NS; r++) {
-            const double v = sm.ST[r][lane];
-            acc = is_sum ? acc + v : (is_min ? fmin(acc, v) : fmax(acc, v));
-        }
-        sm.red[lane] = acc;
+// eight statistics reduced together (interleaved butterflies): four sums and four maxima
+struct Stat8 { double s0, s1, s2, s3, m0, m1, m2, m3; };
+__device__ __forceinline__ void reduce8(Stat8 &t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t.s0 += __shfl_xor_sync(FULL, t.s0, o); t.s1 += __shfl_xor_sync(FULL, t.s1, o);
+        t.s2 += __shfl_xor_sync(FULL, t.s2, o); t.s3 += __shfl_xor_sync(FULL, t.s3, o);
+        t.m0 = fmax(t.m0, __shfl_xor_sync(FULL, t.m0, o)); t.m1 = fmax(t.m1, __shfl_xor_sync(FULL, t.m1, o));
+        t.m2 = fmax(t.m2, __shfl_xor_sync(FULL, t.m2, o)); t.m3 = fmax(t.m3, __shfl_xor_sync(FULL, t.m3, o));
     }
-    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -374,7 +369,9 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             }
             __syncwarp();
         }
-        // ---- rows: evaluate, update row state, stage gradients, weights and statistics ------------------------------------
+        // ---- rows: evaluate, update row state, stage gradients and weights; statistics stay in registers ----------------------
+        Stat8 st8;
+        st8.s0 = st8.s1 = st8.s2 = st8.s3 = 0.0; st8.m0 = 0.0; st8.m1 = -1e300; st8.m2 = 0.0; st8.m3 = 0.0;
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             const int r = s * 32 + lane;
@@ -448,15 +445,16 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                 }
             }
 #pragma unroll
-            for (int a = 0; a < 9; a++) sm.G[r][a] = g[a];
+            for (int a = 0; a < 9; a++) { sm.G[r][a] = g[a]; sm.SG[r][a] = sig * g[a]; }
             sm.RW[r][0] = sig; sm.RW[r][1] = w1; sm.RW[r][2] = binv; sm.RW[r][3] = y;
             sm.HQ[r][0] = y * e.hq0; sm.HQ[r][1] = y * e.hq1; sm.HQ[r][2] = y * e.hq2;
-            sm.ST[r][0] = t_rc; sm.ST[r][1] = t_rc; sm.ST[r][2] = t_cmin; sm.ST[r][3] = t_cmax;
-            sm.ST[r][4] = t_z; sm.ST[r][5] = t_log; sm.ST[r][6] = t_v2; sm.ST[r][7] = t_v;
+            st8.s0 += t_rc; st8.s1 += t_z; st8.s2 += t_log; st8.s3 += t_v2;
+            st8.m0 = fmax(st8.m0, t_rc); st8.m1 = fmax(st8.m1, -t_cmin); st8.m2 = fmax(st8.m2, t_cmax); st8.m3 = fmax(st8.m3, t_v);
         }
-        reduce_stats<NS>(sm, lane);
-        const double st_theta = sm.red[0], st_pinf = sm.red[1], st_cmin = sm.red[2], st_cmax = sm.red[3], st_zsum = sm.red[4],
-                     st_logsum = sm.red[5], st_v2 = sm.red[6], st_vmax = sm.red[7];
+        reduce8(st8);
+        __syncwarp();
+        const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = st8.s2, st_v2 = st8.s3, st_pinf = st8.m0, st_cmin = -st8.m1,
+                     st_cmax = st8.m2, st_vmax = st8.m3;
         // ---- node Hessians ---------------------------------------------------------------------------------------------
         {
             const double gm1 = P.gamma - 1.0;
@@ -485,7 +483,12 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             const int a = cs_.ea[e], bcol = cs_.eb[e];
             double acc = 0.0;
             if (e < 45) {
-                for (int r = 0; r < m; r++) acc = fma(sm.RW[r][0] * sm.G[r][a], sm.G[r][bcol], acc);
+                const double *pa = &sm.SG[0][a], *pb = &sm.G[0][bcol];
+                double acc1 = 0.0;
+                int r = 0;
+                for (; r + 1 < m; r += 2) { acc = fma(pa[9 * r], pb[9 * r], acc); acc1 = fma(pa[9 * r + 9], pb[9 * r + 9], acc1); }
+                if (r < m) acc = fma(pa[9 * r], pb[9 * r], acc);
+                acc += acc1;
                 // Lagrangian Hessian through the feature map
 #pragma unroll
                 for (int kn = 1; kn <= 3; kn++) {
@@ -502,7 +505,12 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                     acc += sm.legy[i] * (T[FLX(i)][a] * T[FLX(i)][bcol] + T[FLY(i)][a] * T[FLY(i)][bcol]);
                 sm.Kf[e] = acc;
             } else {
-                for (int r = 0; r < m; r++) acc = fma(sm.RW[r][bcol], sm.G[r][a], acc);   // bcol = 1 + vector index
+                const double *pw = &sm.RW[0][bcol], *pg = &sm.G[0][a];   // bcol = 1 + vector index
+                double acc1 = 0.0;
+                int r = 0;
+                for (; r + 1 < m; r += 2) { acc = fma(pw[4 * r], pg[9 * r], acc); acc1 = fma(pw[4 * r + 4], pg[9 * r + 9], acc1); }
+                if (r < m) acc = fma(pw[4 * r], pg[9 * r], acc);
+                acc += acc1;
                 sm.q[e - 45] = acc;
             }
         }

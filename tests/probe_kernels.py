@@ -22,7 +22,9 @@ def run(form, B, mode):
           + str({int(k): int((st == k).sum()) for k in np.unique(st)}), flush=True)
     return r
 
-for form, B in (("sig_step", 1), ("sig_step", 4096), ("sig_step", 65536), ("sig_step", 1 << 20), ("modi", 65536)):
+import sys
+SHAPES = (("sig_step", 1), ("sig_step", 4096), ("sig_step", 65536), ("modi", 65536)) if len(sys.argv) > 1 else (("sig_step", 1), ("sig_step", 4096), ("sig_step", 65536), ("sig_step", 1 << 20), ("modi", 65536))
+for form, B in SHAPES:
     rt = run(form, B, "thread")
     rw = run(form, B, "warp")
     both = (rt.status == 0) & (rw.status == 0)
