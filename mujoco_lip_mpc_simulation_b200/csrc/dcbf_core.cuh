@@ -140,7 +140,7 @@ struct IpmState {
     double filt_th[DCBF_FILT], filt_ph[DCBF_FILT];
     double obj, viol;
     int nf, iters, acc_cnt, status;
-    int phase;
+    int phase, nstall;
     bool pending, reinit, first, done;
 };
 
@@ -1248,7 +1248,7 @@ template <int N>
 DCBF_HD void ipm_init(const dcbf_params &P, IpmState<N> &S) {
     S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4;
     S.resto_target = 0.0; S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0;
-    S.status = -1; S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.done = false;
+    S.status = -1; S.nstall = 0; S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.done = false;
     S.obj = 0.0; S.viol = 0.0;
 }
 
@@ -1327,7 +1327,9 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
         bool stationary = gn <= 1e-10 * dmax(1.0, A.vmax) || S.lm_lambda > 1e12;
         if (stationary) {
             if (A.vmax > P.constr_viol_tol) { S.status = 2; S.done = true; return true; }
-            if (S.resto_entry <= 1e-9) { S.status = -2; S.done = true; return true; }
+            // stationary, violation within constr_viol_tol: give the main phase one more chance; a second stall at such a
+            // point (marginally infeasible problem, filter blocks every step) ends as Restoration_Failed instead of cycling
+            if (S.resto_entry <= 1e-9 || S.nstall++ >= 1) { S.status = -2; S.done = true; return true; }
             S.phase = PH_MAIN; S.reinit = true;
             return false;
         }

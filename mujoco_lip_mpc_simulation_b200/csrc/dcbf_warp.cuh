@@ -196,7 +196,7 @@ __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<
 
 struct WState {   // replicated scalars of one problem
     double mu, sf, alpha, alpha_z, delta_last, lm_lambda, resto_target, resto_entry, theta_max, theta_min, obj, viol;
-    int nf, iters, acc_cnt, status, phase;
+    int nf, iters, acc_cnt, status, phase, nstall;
     bool pending, reinit, first;
 };
 
@@ -345,7 +345,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
     const int nz = wsumi(nz_l), nrows = m;
     // ---- solver state ------------------------------------------------------------------------------------------------
     S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4; S.resto_target = 0.0;
-    S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1;
+    S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0;
     S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.obj = 0.0; S.viol = 0.0;
     const double tol = P.tol;
 
@@ -548,7 +548,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             const bool stationary = gn <= 1e-10 * fmax(1.0, st_vmax) || S.lm_lambda > 1e12;
             if (stationary) {
                 if (st_vmax > P.constr_viol_tol) { S.status = 2; break; }
-                if (S.resto_entry <= 1e-9) { S.status = -2; break; }
+                if (S.resto_entry <= 1e-9 || S.nstall++ >= 1) { S.status = -2; break; }   // see ipm_iterate()
                 S.phase = PH_MAIN; S.reinit = true; continue;
             }
             if (S.iters >= P.max_iter) { S.status = -1; break; }

@@ -633,7 +633,7 @@ static void ipm_solve(const orc_problem *pb, const double *u0, orc_result *R) {
     const double tol = P->tol > 0 ? P->tol : 1e-8;
     int iters = 0, status = -1;
     double delta_last = 0.0;
-    int acceptable_cnt = 0;
+    int acceptable_cnt = 0, nstall = 0;
 
     for (;;) {
         /* --- optimality error ----------------------------------------------------------------- */
@@ -751,7 +751,8 @@ static void ipm_solve(const orc_problem *pb, const double *u0, orc_result *R) {
             prob_eval(pb, S->x, &f, g, c, jac);
             double vnow = row_violation(S, c, cl, cu);
             if (!ok && vnow > 1e-4) { status = 2; break; }
-            if (!ok && c_now <= 1e-9) { status = -2; break; }   /* feasible but the line search is stuck */
+            /* feasible but the line search is stuck, or a second stall at a marginally infeasible stationary point */
+            if (!ok && (c_now <= 1e-9 || nstall++ >= 1)) { status = -2; break; }
             init_slacks(S, c);
             for (int r = 0; r < m; r++) { S->zl[r] = S->hasl[r] ? 1.0 : 0.0; S->zu[r] = S->hasu[r] ? 1.0 : 0.0; }
             (void)entry;
