@@ -47,6 +47,7 @@ def f_iter(n: int, m: int, m_nl: int, m_b: int, kc: int, ke: int, form: str) -> 
 
 
 F_ITER_SIG_K6 = f_iter(9, 30, 27, 0, 6, 0, "sig_step")   # = 8455
+NCU_DRAM_BYTES_PER_LAUNCH = 1.93e6   # measured once per change with ncu (profiles/r01_summary.md); not re-measured at run time
 
 
 def io_bytes_per_solve(kc: int) -> int:
@@ -279,7 +280,9 @@ def main():
             "gpu_launches": int(launches),
             "p50_solve_us": float(np.median(lat)), "p95_solve_us": float(np.percentile(lat, 95)),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                         "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of solve_lip_warp_kernel<1>, B = 4096)",
+                         "kernel": "solve_lip_warp_kernel<1> (one problem per warp)", "algorithmic_bytes": B * io_bytes_per_solve(6),
                          "peak_source": "measured on this GPU by dcbf_fp64_peak_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
                          "flop_per_iter": F_ITER_SIG_K6, "iters_per_step": int(iters.sum()),
                          "hbm": {"achieved": io_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": io_gbs / hbm_peak,

@@ -140,7 +140,7 @@ struct IpmState {
     double filt_th[DCBF_FILT], filt_ph[DCBF_FILT];
     double obj, viol;
     int nf, iters, acc_cnt, status;
-    int phase, nstall;
+    int phase, nstall, tiny;
     bool pending, reinit, first, done;
 };
 
@@ -1248,7 +1248,7 @@ template <int N>
 DCBF_HD void ipm_init(const dcbf_params &P, IpmState<N> &S) {
     S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4;
     S.resto_target = 0.0; S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0;
-    S.status = -1; S.nstall = 0; S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.done = false;
+    S.status = -1; S.nstall = 0; S.tiny = 0; S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.done = false;
     S.obj = 0.0; S.viol = 0.0;
 }
 
@@ -1311,6 +1311,15 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             S.acc_cnt = 0;
         }
         if (S.iters >= P.max_iter) { S.status = -1; S.done = true; return true; }
+        if (S.tiny >= 3) {
+            // three consecutive accepted steps shorter than 1e-2 while the rows are still violated: the fraction-to-boundary
+            // rule is pinning the iterate (typical for infeasible problems) -> go to restoration now instead of crawling
+            S.tiny = 0;
+            filter_add(S, (1.0 - 1e-5) * A.theta, (S.sf * A.f - S.mu * log_total(LA)) - 1e-5 * A.theta);
+            S.phase = PH_RESTO; S.resto_entry = A.vmax; S.resto_target = dmax(0.1 * A.vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0;
+            S.iters++;
+            return false;
+        }
         DCBF_UNROLL
         for (int i = 0; i < N; i++) rhs[i] = -S.sf * A.grad[i] - A.q1[i] + S.mu * A.q2[i];
     } else {
@@ -1425,6 +1434,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
     DCBF_UNROLL
     for (int i = 0; i < N; i++) S.z[i] = fma(alpha, S.dz[i], S.z[i]);
     S.alpha = alpha; S.alpha_z = D.az; S.pending = true;
+    if (alpha < 1e-2 && A.vmax > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
     S.iters++;
     return false;
 }

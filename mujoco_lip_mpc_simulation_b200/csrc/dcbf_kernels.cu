@@ -311,7 +311,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     const char *km = getenv("DCBF_KERNEL");
     ctx->kernel_mode = km ? (km[0] == 't' ? 1 : (km[0] == 'w' ? 2 : 0)) : 0;
     const char *wb = getenv("DCBF_WARP_MAX_BATCH");
-    ctx->warp_max_batch = wb ? atoi(wb) : 262144;   // measured crossover on B200 (profiles/r01_summary.md): warp 3.4 M/s vs thread 2.4 M/s at 65 536; thread wins at 1 M
+    ctx->warp_max_batch = wb ? atoi(wb) : 32768;   // measured crossover on B200 (profiles/r01_summary.md)
     *out = ctx;
     return DCBF_OK;
 }

@@ -196,7 +196,7 @@ __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<
 
 struct WState {   // replicated scalars of one problem
     double mu, sf, alpha, alpha_z, delta_last, lm_lambda, resto_target, resto_entry, theta_max, theta_min, obj, viol;
-    int nf, iters, acc_cnt, status, phase, nstall;
+    int nf, iters, acc_cnt, status, phase, nstall, tiny;
     bool pending, reinit, first;
 };
 
@@ -345,7 +345,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
     const int nz = wsumi(nz_l), nrows = m;
     // ---- solver state ------------------------------------------------------------------------------------------------
     S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4; S.resto_target = 0.0;
-    S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0;
+    S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0; S.tiny = 0;
     S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.obj = 0.0; S.viol = 0.0;
     const double tol = P.tol;
 
@@ -541,6 +541,16 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             if (E0 <= tol) { S.status = 0; break; }
             if (E0 <= 1e-6 && st_vmax <= P.constr_viol_tol) { if (++S.acc_cnt >= 15) { S.status = 1; break; } } else S.acc_cnt = 0;
             if (S.iters >= P.max_iter) { S.status = -1; break; }
+            if (S.tiny >= 3) {   // pinned by the fraction-to-boundary rule while still infeasible: restoration now (see ipm_iterate())
+                S.tiny = 0;
+                const int slot = S.nf < DCBF_FILT ? S.nf : (S.iters % DCBF_FILT);
+                if (lane == 0) { sm.filt_th[slot] = (1.0 - 1e-5) * st_theta; sm.filt_ph[slot] = (S.sf * fobj - S.mu * st_logsum) - 1e-5 * st_theta; }
+                if (S.nf < DCBF_FILT) S.nf++;
+                __syncwarp();
+                S.phase = PH_RESTO; S.resto_entry = st_vmax; S.resto_target = fmax(0.1 * st_vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0;
+                S.iters++;
+                continue;
+            }
             if (lane < 9) rhs_a = -S.sf * grad_a - sm.q[lane] + S.mu * sm.q[9 + lane];
         } else {
             if (st_vmax <= S.resto_target) { S.phase = PH_MAIN; S.reinit = true; continue; }
@@ -742,6 +752,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
         if (lane < 9) sm.zc[lane] = sm.zt[lane];
         __syncwarp();
         S.alpha = alpha; S.alpha_z = az; S.pending = true;
+        if (alpha < 1e-2 && st_vmax > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
         S.iters++;
     }
     // make sm.nodes the rollout of the final iterate

@@ -633,7 +633,7 @@ static void ipm_solve(const orc_problem *pb, const double *u0, orc_result *R) {
     const double tol = P->tol > 0 ? P->tol : 1e-8;
     int iters = 0, status = -1;
     double delta_last = 0.0;
-    int acceptable_cnt = 0, nstall = 0;
+    int acceptable_cnt = 0, nstall = 0, tiny = 0;
 
     for (;;) {
         /* --- optimality error ----------------------------------------------------------------- */
@@ -741,7 +741,9 @@ static void ipm_solve(const orc_problem *pb, const double *u0, orc_result *R) {
             }
             if (accepted) break;
         }
+        if (accepted && tiny >= 3) { accepted = 0; }   /* pinned by the fraction-to-boundary rule while infeasible: restoration now */
         if (!accepted) {
+            tiny = 0;
             /* restoration: reduce the violation of the original rows from the current x */
             double c_now = row_violation(S, c, cl, cu);
             double entry = 0; for (int r = 0; r < m; r++) entry += fabs(c[r] - S->s[r]);
@@ -765,6 +767,7 @@ static void ipm_solve(const orc_problem *pb, const double *u0, orc_result *R) {
             if (S->hasl[r]) { double z = S->zl[r] + az * dzl[r], gap = S->s[r] - S->dl[r]; z = fmax(fmin(z, 1e10 * S->mu / gap), S->mu / (1e10 * gap)); S->zl[r] = z; }
             if (S->hasu[r]) { double z = S->zu[r] + az * dzu[r], gap = S->du[r] - S->s[r]; z = fmax(fmin(z, 1e10 * S->mu / gap), S->mu / (1e10 * gap)); S->zu[r] = z; }
         }
+        if (alpha < 1e-2 && viol > 1e-4) tiny++; else tiny = 0;
         prob_eval(pb, S->x, &f, g, c, jac);
         iters++;
     }
