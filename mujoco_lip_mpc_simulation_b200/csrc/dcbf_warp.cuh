@@ -349,9 +349,13 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
     S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.obj = 0.0; S.viol = 0.0;
     const double tol = P.tol;
 
+    bool nodes_valid = false;      // sm.nodes / trig / nobj (with Hessian terms) already describe zc (staged by the accepted trial)
+    double carry_log = 0.0;        // sum of log(gaps) at the accepted trial point = barrier term of the next full pass
+    bool carry_ok = false;
     for (;;) {
         const bool resto = S.phase == PH_RESTO;
-        w_nodes<NS>(cs_, sm, sm.zc, lane, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
+        if (!nodes_valid) w_nodes<NS>(cs_, sm, sm.zc, lane, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
+        nodes_valid = false;
         // objective value and gradient (lane a < 9 owns grad[a])
         const double fobj = sm.nobj[1][0] + sm.nobj[2][0] + sm.nobj[3][0];
         double grad_a = 0.0;
@@ -425,7 +429,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                         t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzu[s];
                         lp *= gap; reu[s] = inv;
                     }
-                    t_log = dlog(lp);
+                    if (!carry_ok) t_log = dlog(lp);
                     rds[s] = rc;
                     t_rc = fabs(rc);
                     w1 = sig * rc;
@@ -453,8 +457,9 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
         }
         reduce8(st8);
         __syncwarp();
-        const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = st8.s2, st_v2 = st8.s3, st_pinf = st8.m0, st_cmin = -st8.m1,
-                     st_cmax = st8.m2, st_vmax = st8.m3;
+        const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? carry_log : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
+                     st_cmin = -st8.m1, st_cmax = st8.m2, st_vmax = st8.m3;
+        carry_ok = false;
         // ---- node Hessians ---------------------------------------------------------------------------------------------
         {
             const double gm1 = P.gamma - 1.0;
@@ -705,7 +710,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
         for (int ls = 0; ls < DCBF_LS_MAX; ls++, alpha *= 0.5) {
             if (lane < 9) sm.zt[lane] = fma(alpha, sm.dz[lane], sm.zc[lane]);
             __syncwarp();
-            w_nodes<NS>(cs_, sm, sm.zt, lane, 0.0, false);
+            w_nodes<NS>(cs_, sm, sm.zt, lane, S.sf, true);
             const double ft = sm.nobj[1][0] + sm.nobj[2][0] + sm.nobj[3][0];
             double th_t = 0.0, lg_t = 0.0;
             bool okv = true;
@@ -736,7 +741,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             const bool sw = dphi < 0.0 && theta <= S.theta_min && switch_cond(alpha, -dphi, theta);
             if (sw) { if (ph_t <= phi + 1e-8 * alpha * dphi + eps_phi) accepted = 1; }
             else if (th_t <= (1.0 - 1e-5) * theta || ph_t <= phi - 1e-5 * theta + eps_phi) accepted = 2;
-            if (accepted) break;
+            if (accepted) { carry_log = lg_t; break; }
         }
         if (accepted != 1) {   // filter augmentation (also before entering restoration)
             const int slot = S.nf < DCBF_FILT ? S.nf : (S.iters % DCBF_FILT);
@@ -752,11 +757,11 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
         if (lane < 9) sm.zc[lane] = sm.zt[lane];
         __syncwarp();
         S.alpha = alpha; S.alpha_z = az; S.pending = true;
+        nodes_valid = true; carry_ok = true;   // the accepted trial staged the nodes (with Hessian terms) and the barrier sum of the new point
         if (alpha < 1e-2 && st_vmax > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
         S.iters++;
     }
-    // make sm.nodes the rollout of the final iterate
-    w_nodes<NS>(cs_, sm, sm.zc, lane, 0.0, false);
+    // every exit leaves the loop right after a full pass (or before any trial), so sm.nodes is the rollout of the final iterate
 }
 
 template <int NS>
