@@ -241,6 +241,23 @@ def main():
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))
             extra[f"{form}_{Bs}"] = {"solves_per_s": Bs / (best * 1e-3), "ms": best, "mean_iters": float(r.iters.float().mean())}
+        # config 5 shape, one GPU's share at 8 GPUs: closed-loop rollout, 131072 scenarios x 50 steps, no host round trips
+        s5 = scenarios.make_batch("sig_step", 131072, seed=SEED + 3)
+        sv = DcbfSolver("sig_step", device=local)
+        sv.set_fields(s5.cir)
+        a5 = [t(s5.x0, torch.float64), t(s5.goal, torch.float64), t(s5.leg, torch.int32), t(s5.field, torch.int32)]
+        best = 1e9
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ro = sv.rollout(50, a5[0], a5[1], a5[2], field=a5[3], want_traj=False)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        n_solves = int(ro["steps_done"].sum())
+        extra["rollout_131072x50"] = {"solves_per_s": n_solves / (best * 1e-3), "ms": best, "solves": n_solves,
+                                      "mean_iters": float(ro["total_iters"].sum()) / n_solves,
+                                      "infeasible_frac": float(ro["n_infeasible"].sum()) / n_solves}
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on all host threads over the same 4096 scenarios ------------------
     cpu = None

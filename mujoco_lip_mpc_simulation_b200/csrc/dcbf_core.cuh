@@ -106,6 +106,7 @@ DCBF_HD double drsqrt(double x) {
 #endif
 }
 DCBF_MATH double drcp(double x) { return 1.0 / x; }
+DCBF_MATH double ddiv(double a, double b) { return a / b; }   // ~35 SASS instructions inline; one shared copy instead
 // alpha * a^2.3 > t^1.1 for a > 0, t >= 0 (switching condition of the filter line search) without pow()
 DCBF_HD bool switch_cond(double alpha, double a, double t) {
     if (!(t > 0.0)) return alpha > 0.0;

@@ -53,17 +53,17 @@ struct CtaShared {
     int ea[72], eb[72];
 };
 
-__device__ __forceinline__ double wsum(double v) {
+__device__ __noinline__ double wsum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
-__device__ __forceinline__ double wmax(double v) {
+__device__ __noinline__ double wmax(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
-__device__ __forceinline__ double wmin(double v) {
+__device__ __noinline__ double wmin(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
     return v;
@@ -228,7 +228,7 @@ __device__ __noinline__ void w_nodes(const CtaShared &cs_, WarpShared<NS> &sm, c
         const double w = P.w_q + (kn == 1 ? P.w_p : 0.0);
         const double ex = sm.nodes[kn][0] - sm.goal[0], ey = sm.nodes[kn][1] - sm.goal[1];
         const double dx = -ex, dy = -ey;
-        const double r2 = dx * dx + dy * dy, ir2 = 1.0 / r2;
+        const double r2 = dx * dx + dy * dy, ir2 = drcp(r2);
         const double tar = datan2(dy, dx);
         const double phi = th - tar;
         sm.trig[kn][0] = sn; sm.trig[kn][1] = cs; sm.trig[kn][2] = tar;
@@ -252,7 +252,7 @@ __device__ __noinline__ void w_nodes(const CtaShared &cs_, WarpShared<NS> &sm, c
 
 // eight statistics reduced together (interleaved butterflies): four sums and four maxima
 struct Stat8 { double s0, s1, s2, s3, m0, m1, m2, m3; };
-__device__ __forceinline__ void reduce8(Stat8 &t) {
+__device__ __forceinline__ void reduce8_inline(Stat8 &t) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         t.s0 += __shfl_xor_sync(FULL, t.s0, o); t.s1 += __shfl_xor_sync(FULL, t.s1, o);
@@ -366,7 +366,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
         }
         if (S.first) {
             const double gmax = wmax(fabs(grad_a));
-            S.sf = gmax > 100.0 ? 100.0 / gmax : 1.0;
+            S.sf = gmax > 100.0 ? ddiv(100.0, gmax) : 1.0;
             if (lane < 3) {   // the objective Hessian staged above used sf = 1: rescale
 #pragma unroll
                 for (int c = 4; c < 10; c++) sm.nobj[lane + 1][c] *= S.sf;
@@ -406,24 +406,26 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                         rs[s] += S.alpha * rds[s];
                         if (bb.has_lo) {
                             const double gap = rs[s] - lr;
-                            rzl[s] = fmax(fmin(rzl[s] + S.alpha_z * rel[s], DCBF_KAPPA_SIGMA * S.mu / gap), S.mu / (DCBF_KAPPA_SIGMA * gap));
+                            const double mg = ddiv(S.mu, gap);
+                            rzl[s] = fmax(fmin(rzl[s] + S.alpha_z * rel[s], DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
                         }
                         if (bb.has_hi) {
                             const double gap = hr - rs[s];
-                            rzu[s] = fmax(fmin(rzu[s] + S.alpha_z * reu[s], DCBF_KAPPA_SIGMA * S.mu / gap), S.mu / (DCBF_KAPPA_SIGMA * gap));
+                            const double mg = ddiv(S.mu, gap);
+                            rzu[s] = fmax(fmin(rzu[s] + S.alpha_z * reu[s], DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
                         }
                     }
                     const double rc = e.c - rs[s];
                     double lp = 1.0;
                     if (bb.has_lo) {
-                        const double gap = rs[s] - lr, inv = 1.0 / gap;
+                        const double gap = rs[s] - lr, inv = drcp(gap);
                         sig += rzl[s] * inv; binv += inv; y -= rzl[s];
                         const double cz = gap * rzl[s];
                         t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzl[s];
                         lp *= gap; rel[s] = inv;
                     }
                     if (bb.has_hi) {
-                        const double gap = hr - rs[s], inv = 1.0 / gap;
+                        const double gap = hr - rs[s], inv = drcp(gap);
                         sig += rzu[s] * inv; binv -= inv; y += rzu[s];
                         const double cz = gap * rzu[s];
                         t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzu[s];
@@ -455,7 +457,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             st8.s0 += t_rc; st8.s1 += t_z; st8.s2 += t_log; st8.s3 += t_v2;
             st8.m0 = fmax(st8.m0, t_rc); st8.m1 = fmax(st8.m1, -t_cmin); st8.m2 = fmax(st8.m2, t_cmax); st8.m3 = fmax(st8.m3, t_v);
         }
-        reduce8(st8);
+        reduce8_inline(st8);
         __syncwarp();
         const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? carry_log : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
                      st_cmin = -st8.m1, st_cmax = st8.m2, st_vmax = st8.m3;
@@ -495,7 +497,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                 if (r < m) acc = fma(pa[9 * r], pb[9 * r], acc);
                 acc += acc1;
                 // Lagrangian Hessian through the feature map
-#pragma unroll
+#pragma unroll 1
                 for (int kn = 1; kn <= 3; kn++) {
                     const double Xa = T[FN(kn, 0)][a], Ya = T[FN(kn, 1)][a], VXa = T[FN(kn, 2)][a], VYa = T[FN(kn, 3)][a], Ta = T[FN(kn, 4)][a];
                     const double Xb = T[FN(kn, 0)][bcol], Yb = T[FN(kn, 1)][bcol], VXb = T[FN(kn, 2)][bcol], VYb = T[FN(kn, 3)][bcol], Tb = T[FN(kn, 4)][bcol];
@@ -505,7 +507,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                     const double ut = H[3] * Xb + H[4] * Yb + H[5] * Tb + H[6] * VXb + H[7] * VYb;
                     acc += Xa * ux + Ya * uy + Ta * ut + (VXa * H[6] + VYa * H[7]) * Tb;
                 }
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < 3; i++)
                     acc += sm.legy[i] * (T[FLX(i)][a] * T[FLX(i)][bcol] + T[FLY(i)][a] * T[FLY(i)][bcol]);
                 sm.Kf[e] = acc;
@@ -528,13 +530,14 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
         if (!resto) {
             if (S.first) { S.theta_max = 1e4 * fmax(1.0, st_theta); S.theta_min = 1e-4 * fmax(1.0, st_theta); S.first = false; }
             const double dinf = wmax(lane < 9 ? fabs(fma(S.sf, grad_a, sm.q[18 + lane])) : 0.0);
-            const double sd = fmax(100.0, 2.0 * st_zsum / (double)(nrows + nz)) * 0.01;
-            const double sc = fmax(100.0, st_zsum / (double)(nz > 0 ? nz : 1)) * 0.01;
+            const double sd = fmax(100.0, ddiv(2.0 * st_zsum, (double)(nrows + nz))) * 0.01;
+            const double sc = fmax(100.0, ddiv(st_zsum, (double)(nz > 0 ? nz : 1))) * 0.01;
+            const double isd = drcp(sd), isc = drcp(sc);
             double E0;
             for (;;) {
                 const double compm = fmax(fabs(st_cmax - S.mu), fabs(st_cmin - S.mu));
-                E0 = fmax(fmax(dinf / sd, st_pinf), st_cmax / sc);
-                const double Emu = fmax(fmax(dinf / sd, st_pinf), compm / sc);
+                E0 = fmax(fmax(dinf * isd, st_pinf), st_cmax * isc);
+                const double Emu = fmax(fmax(dinf * isd, st_pinf), compm * isc);
                 if (E0 <= tol) break;
                 if (Emu <= 10.0 * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
                     S.mu = fmax(tol * 0.1, fmin(0.2 * S.mu, S.mu * sqrt(S.mu)));
@@ -682,16 +685,16 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                     const double dzl = S.mu * inv - rzl[s] - rzl[s] * inv * d;
                     rel[s] = dzl;
                     dphi -= S.mu * d * inv;
-                    if (d < 0.0) amax = fmin(amax, -tau * gap / d);
-                    if (dzl < 0.0) az = fmin(az, -tau * rzl[s] / dzl);
+                    if (d < 0.0) amax = fmin(amax, ddiv(-tau * gap, d));
+                    if (dzl < 0.0) az = fmin(az, ddiv(-tau * rzl[s], dzl));
                 }
                 if (e.has_hi) {
                     const double inv = reu[s], gap = relax_hi(e.hi) - rs[s];
                     const double dzu = S.mu * inv - rzu[s] + rzu[s] * inv * d;
                     reu[s] = dzu;
                     dphi += S.mu * d * inv;
-                    if (d > 0.0) amax = fmin(amax, tau * gap / d);
-                    if (dzu < 0.0) az = fmin(az, -tau * rzu[s] / dzu);
+                    if (d > 0.0) amax = fmin(amax, ddiv(tau * gap, d));
+                    if (dzu < 0.0) az = fmin(az, ddiv(-tau * rzu[s], dzu));
                 }
             }
 #pragma unroll

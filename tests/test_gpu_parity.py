@@ -150,6 +150,26 @@ def test_both_kernel_families_match_oracle(gpu, monkeypatch, mode, form, B, seed
     np.testing.assert_allclose(ro["traj"][:, 0, :5].cpu().numpy(), one.x_plan[:, 0].cpu().numpy(), atol=1e-12)
 
 
+def test_warm_started_resolves_match_oracle(gpu):
+    """config 2: "half of the batch additionally re-solved warm from the shifted solution of a first solve"
+    (warm start u0 = [x_2, x_3, x_3] at the advanced state x_1, flipped leg: MPC_LIP_sig_step.py:188-189,565-575)."""
+    B = 2048
+    sc = scenarios.make_batch("sig_step", B, seed=0)
+    s = _solver(gpu, "sig_step", sc, max_iter=300)
+    first = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
+    xp = first.x_plan.cpu().numpy()
+    keep = first.status.cpu().numpy() == 0
+    x1, warm = xp[:, 0], np.concatenate([xp[:, 1], xp[:, 2], xp[:, 2]], axis=1)
+    res = s.solve(x1, sc.goal, -sc.leg, warm, field=sc.field)
+    P = c_oracle.params("sig_step", max_iter=300)
+    ref = c_oracle.solve_batch(P, x1, sc.goal, -sc.leg, sc.cir, None, warm, field=sc.field, threads=os.cpu_count() or 4)
+    same_class, both, dp, rel = _agreement("sig_step", res, ref, B)
+    both &= keep
+    assert same_class[keep].mean() >= 0.995 and np.mean(dp[both] <= POS_TOL) >= 0.995 and np.mean(rel[both] <= OBJ_TOL) >= 0.995
+    it_cold, it_warm = first.iters.cpu().numpy()[both].mean(), res.iters.cpu().numpy()[both].mean()
+    print(f"mean iterations cold {it_cold:.1f} -> warm {it_warm:.1f}")
+
+
 def test_warm_started_resolve_is_idempotent(gpu):
     """size-independent property at config 3's full size: re-solving from the returned plan returns the same plan."""
     B = 65536
