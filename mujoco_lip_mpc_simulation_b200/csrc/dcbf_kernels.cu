@@ -39,6 +39,9 @@ struct dcbf_ctx {
     int sm_count;
     int kernel_mode;   // 0 auto, 1 per-thread, 2 warp-cooperative (env DCBF_KERNEL=thread|warp)
     int warp_max_batch;
+    int *d_counter;          // work counter of the persistent (refill) kernels
+    int refill_ctas_lip, refill_ctas_dd;   // resident CTAs of the refill kernels on this device
+    int refill_min_batch;
 };
 
 #define CK(call)                                                                                        \
@@ -63,6 +66,34 @@ __global__ void __launch_bounds__(DCBF_BLOCK) solve_lip_kernel(dcbf_params P, Co
 }
 __global__ void __launch_bounds__(DCBF_BLOCK) solve_dd_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out) {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) solve_dd_lane(P, K, in, out, b);
+}
+// persistent variants: every lane pulls its next problem from an atomic counter the moment its current one is done, so the
+// lanes of a warp stay busy although iteration counts differ (feasible ~14, infeasible ~21, max ~40)
+__global__ void __launch_bounds__(DCBF_BLOCK) solve_lip_refill_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out, int *counter) {
+    LipModel<DCBF_KT> M;
+    IpmState<9> S;
+    int b = -1;
+    for (;;) {
+        if (b < 0) {
+            b = atomicAdd(counter, 1);
+            if (b >= B) break;
+            lip_lane_begin(P, K, in, b, M, S);
+        }
+        if (ipm_iterate(K, P, M, S)) { lip_lane_finish(P, M, S, b, out); b = -1; }
+    }
+}
+__global__ void __launch_bounds__(DCBF_BLOCK) solve_dd_refill_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out, int *counter) {
+    DdModel<DCBF_KT> M;
+    IpmState<6> S;
+    int b = -1;
+    for (;;) {
+        if (b < 0) {
+            b = atomicAdd(counter, 1);
+            if (b >= B) break;
+            dd_lane_begin(P, in, b, M, S);
+        }
+        if (ipm_iterate(K, P, M, S)) { dd_lane_finish(P, K, M, S, b, out); b = -1; }
+    }
 }
 __global__ void __launch_bounds__(DCBF_BLOCK) eval_lip_kernel(dcbf_params P, Consts K, int B, BatchIn in, EvalPtrs ev) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,6 +342,18 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     const char *km = getenv("DCBF_KERNEL");
     ctx->kernel_mode = km ? (km[0] == 't' ? 1 : (km[0] == 'w' ? 2 : 0)) : 0;
     const char *wb = getenv("DCBF_WARP_MAX_BATCH");
+    if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
+    {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_lip_refill_kernel, DCBF_BLOCK, 0);
+        ctx->refill_ctas_lip = (nb > 0 ? nb : 1) * ctx->sm_count;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_dd_refill_kernel, DCBF_BLOCK, 0);
+        ctx->refill_ctas_dd = (nb > 0 ? nb : 1) * ctx->sm_count;
+    }
+    const char *rb = getenv("DCBF_REFILL_MIN_BATCH");
+    // measured on B200 (profiles/r01_summary.md): refill desynchronises the lanes of a warp (different iteration index, phase and
+    // line-search depth per lane) and loses 25-30 % against the static assignment -> off unless requested (0: auto, N: batches > N)
+    ctx->refill_min_batch = rb ? atoi(rb) : -1;
     ctx->warp_max_batch = wb ? atoi(wb) : 32768;   // measured crossover on B200 (profiles/r01_summary.md)
     *out = ctx;
     return DCBF_OK;
@@ -319,7 +362,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
 void dcbf_destroy(dcbf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
+    cudaFree(ctx->d_counter); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -390,7 +433,16 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
     BatchIn in = {x0, goal, warm, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
     SolveOut out = {u, x_plan, p_plan, obj, viol, status, iters, close2goal};
     cudaStream_t st = (cudaStream_t)stream;
-    if (ctx->P.formulation == DCBF_DD) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
+    const bool dd = ctx->P.formulation == DCBF_DD;
+    const int resident = (dd ? ctx->refill_ctas_dd : ctx->refill_ctas_lip) * DCBF_BLOCK;
+    const bool refill = ctx->refill_min_batch >= 0 && B > (ctx->refill_min_batch > 0 ? ctx->refill_min_batch : resident) &&
+                        (dd || !use_warp_kernel(ctx, B));
+    if (refill) {
+        CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
+        if (dd) solve_dd_refill_kernel<<<ctx->refill_ctas_dd, DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out, ctx->d_counter);
+        else solve_lip_refill_kernel<<<ctx->refill_ctas_lip, DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out, ctx->d_counter);
+    }
+    else if (dd) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
     else if (use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);
         const int rc = ns == 1 ? launch_solve_warp<1>(ctx, B, in, out, st) : (ns == 2 ? launch_solve_warp<2>(ctx, B, in, out, st) : launch_solve_warp<4>(ctx, B, in, out, st));

@@ -79,19 +79,18 @@ DCBF_HD void write_lip_plan(const dcbf_params &P, const Problem &pb, const LipNo
     if (o.close) o.close[b] = lip_close(P, pb, nd) ? 1 : 0;
 }
 
-// ---- K1+K2: one solve ---------------------------------------------------------------------------------------------
-DCBF_HD void solve_lip_lane(const dcbf_params &P, const Consts &K, const BatchIn &in, const SolveOut &out, int b) {
-    LipModel<DCBF_KT> M;
-    IpmState<9> S;
+// ---- K1+K2: one solve, split into begin / iterate / finish so that a lane can pick up a new problem as soon as its
+// current one has converged (persistent "refill" kernels) ----------------------------------------------------------------
+DCBF_HD void lip_lane_begin(const dcbf_params &P, const Consts &K, const BatchIn &in, int b, LipModel<DCBF_KT> &M, IpmState<9> &S) {
     load_problem<false>(P, in, b, M.pb);
     ipm_init(P, S);
-    {
-        double u0[15];
-        DCBF_UNROLL
-        for (int i = 0; i < 15; i++) u0[i] = in.warm[15 * (size_t)b + i];
-        lip_z_from_u(K, M.pb.x0, u0, S.z);
-    }
-    while (!ipm_iterate(K, P, M, S)) {}
+    double u0[15];
+    DCBF_UNROLL
+    for (int i = 0; i < 15; i++) u0[i] = in.warm[15 * (size_t)b + i];
+    lip_z_from_u(K, M.pb.x0, u0, S.z);
+}
+
+DCBF_HD void lip_lane_finish(const dcbf_params &P, const LipModel<DCBF_KT> &M, const IpmState<9> &S, int b, const SolveOut &out) {
     if (out.status) out.status[b] = S.status;
     if (out.iters) out.iters[b] = S.iters;
     if (out.obj) out.obj[b] = S.obj;
@@ -99,14 +98,22 @@ DCBF_HD void solve_lip_lane(const dcbf_params &P, const Consts &K, const BatchIn
     write_lip_plan(P, M.pb, M.nd, S.z, b, out);
 }
 
-DCBF_HD void solve_dd_lane(const dcbf_params &P, const Consts &K, const BatchIn &in, const SolveOut &out, int b) {
-    DdModel<DCBF_KT> M;
-    IpmState<6> S;
+DCBF_HD void solve_lip_lane(const dcbf_params &P, const Consts &K, const BatchIn &in, const SolveOut &out, int b) {
+    LipModel<DCBF_KT> M;
+    IpmState<9> S;
+    lip_lane_begin(P, K, in, b, M, S);
+    while (!ipm_iterate(K, P, M, S)) {}
+    lip_lane_finish(P, M, S, b, out);
+}
+
+DCBF_HD void dd_lane_begin(const dcbf_params &P, const BatchIn &in, int b, DdModel<DCBF_KT> &M, IpmState<6> &S) {
     load_problem<true>(P, in, b, M.pb);
     ipm_init(P, S);
     DCBF_UNROLL
     for (int i = 0; i < 6; i++) S.z[i] = in.warm[6 * (size_t)b + i];
-    while (!ipm_iterate(K, P, M, S)) {}
+}
+
+DCBF_HD void dd_lane_finish(const dcbf_params &P, const Consts &K, DdModel<DCBF_KT> &M, const IpmState<6> &S, int b, const SolveOut &out) {
     if (out.status) out.status[b] = S.status;
     if (out.iters) out.iters[b] = S.iters;
     if (out.obj) out.obj[b] = S.obj;
@@ -126,6 +133,14 @@ DCBF_HD void solve_dd_lane(const dcbf_params &P, const Consts &K, const BatchIn 
         const double dxg = M.nd.x[1] - M.pb.goal_raw[0], dyg = M.nd.y[1] - M.pb.goal_raw[1];
         out.close[b] = sqrt(dxg * dxg + dyg * dyg) <= P.close_radius ? 1 : 0;
     }
+}
+
+DCBF_HD void solve_dd_lane(const dcbf_params &P, const Consts &K, const BatchIn &in, const SolveOut &out, int b) {
+    DdModel<DCBF_KT> M;
+    IpmState<6> S;
+    dd_lane_begin(P, in, b, M, S);
+    while (!ipm_iterate(K, P, M, S)) {}
+    dd_lane_finish(P, K, M, S, b, out);
 }
 
 // ---- K1: evaluation at given points ------------------------------------------------------------------------------------
