@@ -78,6 +78,15 @@ DCBF_CE int FYI(int l) { return 2 * l + 1; }
 DCBF_CE int THI(int l) { return 6 + l; }
 
 #define DCBF_KAPPA_SIGMA 1e10
+#ifndef DCBF_KAPPA_MU
+#define DCBF_KAPPA_MU 0.2            /* Ipopt mu_linear_decrease_factor */
+#endif
+#ifndef DCBF_MU_POW
+#define DCBF_MU_POW(mu) ((mu) * sqrt(mu))   /* Ipopt mu_superlinear_decrease_power = 1.5 */
+#endif
+#ifndef DCBF_KAPPA_EPS
+#define DCBF_KAPPA_EPS 10.0          /* Ipopt barrier_tol_factor */
+#endif
 #define DCBF_FILT 8
 #define DCBF_LS_MAX 22
 
@@ -1298,8 +1307,8 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             E0 = dmax(dmax(dinf / sd, A.pinf), A.cmax / sc);
             const double Emu = dmax(dmax(dinf / sd, A.pinf), compm / sc);
             if (E0 <= tol) break;
-            if (Emu <= 10.0 * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
-                S.mu = dmax(tol * 0.1, dmin(0.2 * S.mu, S.mu * sqrt(S.mu)));
+            if (Emu <= DCBF_KAPPA_EPS * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
+                S.mu = dmax(tol * 0.1, dmin(DCBF_KAPPA_MU * S.mu, DCBF_MU_POW(S.mu)));
                 S.nf = 0;
                 continue;
             }
