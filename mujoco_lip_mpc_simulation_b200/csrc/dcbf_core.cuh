@@ -87,6 +87,12 @@ DCBF_CE int THI(int l) { return 6 + l; }
 #ifndef DCBF_KAPPA_EPS
 #define DCBF_KAPPA_EPS 10.0          /* Ipopt barrier_tol_factor */
 #endif
+#ifndef DCBF_RESTO_WINDOW
+#define DCBF_RESTO_WINDOW 1e-2       /* restoration: relative decrease of the squared violation over three steps */
+#endif
+#ifdef DCBF_COUNT
+static long g_trials = 0;
+#endif
 #define DCBF_FILT 8
 #define DCBF_LS_MAX 22
 
@@ -147,10 +153,11 @@ struct IpmState {
     double alpha, alpha_z;
     double delta_last, lm_lambda, resto_target, resto_entry;
     double theta_max, theta_min;
+    double v2_h1, v2_h2;   // squared violation one and two accepted restoration steps ago (windowed stagnation test)
     double filt_th[DCBF_FILT], filt_ph[DCBF_FILT];
     double obj, viol;
     int nf, iters, acc_cnt, status;
-    int phase, nstall, tiny;
+    int phase, nstall, tiny, nresto;
     bool pending, reinit, first, done;
 };
 
@@ -1258,7 +1265,7 @@ template <int N>
 DCBF_HD void ipm_init(const dcbf_params &P, IpmState<N> &S) {
     S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4;
     S.resto_target = 0.0; S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0;
-    S.status = -1; S.nstall = 0; S.tiny = 0; S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.done = false;
+    S.status = -1; S.nstall = 0; S.tiny = 0; S.nresto = 0; S.v2_h1 = 0.0; S.v2_h2 = 0.0; S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.done = false;
     S.obj = 0.0; S.viol = 0.0;
 }
 
@@ -1326,7 +1333,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             // rule is pinning the iterate (typical for infeasible problems) -> go to restoration now instead of crawling
             S.tiny = 0;
             filter_add(S, (1.0 - 1e-5) * A.theta, (S.sf * A.f - S.mu * log_total(LA)) - 1e-5 * A.theta);
-            S.phase = PH_RESTO; S.resto_entry = A.vmax; S.resto_target = dmax(0.1 * A.vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0;
+            S.phase = PH_RESTO; S.resto_entry = A.vmax; S.resto_target = dmax(0.1 * A.vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0; S.nresto = 0;
             S.iters++;
             return false;
         }
@@ -1363,6 +1370,9 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             ValStat V;
             V.f = 0.0; V.theta = 0.0; V.v2 = 0.0; V.vmax = 0.0; V.ok = true; V.la.sum = 0.0; V.la.prod = 1.0; V.la.cnt = 0;
             M.pass_value(k, P, S, 1.0, V);
+#ifdef DCBF_COUNT
+            g_trials++;
+#endif
             if (V.v2 < A.v2 * (1.0 - 1e-12)) {
                 double dn = 0.0;
                 DCBF_UNROLL
@@ -1372,7 +1382,11 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
                 // stagnation: the squared violation has stopped decreasing (two consecutive accepted steps with a relative
                 // decrease below 1e-4) -> the iterate is (numerically) a stationary point of the violation
                 if (A.v2 - V.v2 <= 1e-4 * A.v2) S.acc_cnt++; else S.acc_cnt = 0;
-                if ((dn < 1e-12 || S.acc_cnt >= 2) && V.vmax > S.resto_target) S.lm_lambda = 1e13;
+                // ... or three consecutive accepted steps that together gained less than DCBF_RESTO_WINDOW (the iterate
+                // crawls along a kink of the violation: rows entering and leaving the violated set)
+                const bool crawl = S.nresto >= 2 && S.v2_h2 - V.v2 <= DCBF_RESTO_WINDOW * S.v2_h2;
+                S.v2_h2 = S.v2_h1; S.v2_h1 = A.v2; S.nresto++;
+                if ((dn < 1e-12 || S.acc_cnt >= 2 || crawl) && V.vmax > S.resto_target) S.lm_lambda = 1e13;
                 return false;
             }
             S.lm_lambda *= 10.0;
@@ -1437,6 +1451,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
         S.resto_target = dmax(0.1 * A.vmax, 1e-9);
         S.lm_lambda = 1e-4;
         S.acc_cnt = 0;
+        S.nresto = 0;
         S.iters++;
         return false;
     }

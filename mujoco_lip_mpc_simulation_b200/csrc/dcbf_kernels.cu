@@ -39,6 +39,7 @@ struct dcbf_ctx {
     int sm_count;
     int kernel_mode;   // 0 auto, 1 per-thread, 2 warp-cooperative (env DCBF_KERNEL=thread|warp)
     int warp_max_batch;
+    wp::WarpTables *d_tab;   // constant tables of the warp kernels (dcbf_warp.cuh)
     int *d_counter;          // work counter of the persistent (refill) kernels
     int refill_ctas_lip, refill_ctas_dd;   // resident CTAs of the refill kernels on this device
     int refill_min_batch;
@@ -111,12 +112,17 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
 // ---------------------------------------------------------------------------------------------------------------
 // warp-cooperative kernels (one problem per warp): small / medium batches and low latency
 // ---------------------------------------------------------------------------------------------------------------
-#define DCBF_WARPS_PER_CTA 4
+// One warp per CTA: the block scheduler hands a freed warp slot to the next problem (iteration counts differ by 3x), and the
+// scratch lives in static shared memory.
 #ifndef DCBF_WARP_MIN_CTAS
-#define DCBF_WARP_MIN_CTAS 4
+#define DCBF_WARP_MIN_CTAS(NS) ((NS) == 1 ? 12 : 8)   /* register budget 168 / 255: spills to local memory cost more than the lost warps */
+#endif
+#ifndef DCBF_WARP_GRID_CAP
+#define DCBF_WARP_GRID_CAP 64   /* CTAs per SM in the grid (grid-stride loop beyond); 0 = one CTA per problem */
 #endif
 
-// lane 0 stages the scenario state and the start point z0 (from the reference's u0) in shared memory
+// lane 0 stages the scenario state, the start point z0 (from the reference's u0) and the free response of the LIP
+// (positions / velocities at nodes 1..3 for zero foot placements) in shared memory
 template <int NS>
 __device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<NS> &sm, const double *x0, const double *graw, const double *u0, int lane) {
     if (lane == 0) {
@@ -127,20 +133,25 @@ __device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<NS
 #pragma unroll
         for (int i = 0; i < 5; i++) sm.x0[i] = x0[i];
         sm.graw[0] = graw[0]; sm.graw[1] = graw[1];
+        double x = x0[0], y = x0[1], vx = x0[2], vy = x0[3];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            sm.fr[k][0] = x; sm.fr[k][1] = y; sm.fr[k][2] = vx; sm.fr[k][3] = vy;
+            const double xn = K.C * x + K.Sb * vx, yn = K.C * y + K.Sb * vy;
+            vx = K.bS * x + K.C * vx; vy = K.bS * y + K.C * vy;
+            x = xn; y = yn;
+        }
     }
     __syncwarp();
 }
 
 template <int NS>
-__global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) solve_lip_warp_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    wp::CtaShared &cs_ = *reinterpret_cast<wp::CtaShared *>(smem_raw);
-    wp::WarpShared<NS> *wsm = reinterpret_cast<wp::WarpShared<NS> *>(smem_raw + ((sizeof(wp::CtaShared) + 15) & ~(size_t)15));
-    wp::stage_cta(P, K, cs_);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    wp::WarpShared<NS> &sm = wsm[wid];
-    const int nw = gridDim.x * DCBF_WARPS_PER_CTA;
-    for (int b = blockIdx.x * DCBF_WARPS_PER_CTA + wid; b < B; b += nw) {
+__global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out) {
+    wp::WarpShared<NS> &sm = wp::g_sm<NS>;
+    const wp::CtaShared &cs_ = wp::g_cs;
+    const int lane = wp::lane_id();
+    wp::stage_cta<NS>(P, K, tab, lane);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
         if (lane == 0) {
             double x0[5], u0[15], g[2];
 #pragma unroll
@@ -154,7 +165,7 @@ __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) s
         }
         const int leg = in.leg ? in.leg[b] : 1;
         wp::WState S;
-        wp::solve_lip_warp<NS>(cs_, sm, in, b, lane, leg, S);
+        wp::solve_lip_warp<NS>(in, b, lane, leg, S);
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
         if (lane < 15) {
             const double v = sm.nodes[lane / 5 + 1][lane % 5];
@@ -168,8 +179,13 @@ __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) s
         if (lane == 0) {
             if (out.status) out.status[b] = S.status;
             if (out.iters) out.iters[b] = S.iters;
-            if (out.obj) out.obj[b] = S.obj;
-            if (out.viol) out.viol[b] = S.viol;
+#ifdef DCBF_DBG
+            if (out.obj) out.obj[b] = S.n_fact + 1e-3 * S.n_fail;
+            if (out.viol) out.viol[b] = S.n_trial + 1e-3 * S.n_pass;
+#else
+            if (out.obj) out.obj[b] = sm.cold[wp::C_OBJ];
+            if (out.viol) out.viol[b] = sm.cold[wp::C_VIOL];
+#endif
             if (out.close) out.close[b] = wp::w_close<NS>(cs_.P, sm) ? 1 : 0;
         }
         __syncwarp();
@@ -177,15 +193,12 @@ __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) s
 }
 
 template <int NS>
-__global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) rollout_lip_warp_kernel(dcbf_params P, Consts K, int B, int steps, BatchIn in, RolloutOut out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    wp::CtaShared &cs_ = *reinterpret_cast<wp::CtaShared *>(smem_raw);
-    wp::WarpShared<NS> *wsm = reinterpret_cast<wp::WarpShared<NS> *>(smem_raw + ((sizeof(wp::CtaShared) + 15) & ~(size_t)15));
-    wp::stage_cta(P, K, cs_);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    wp::WarpShared<NS> &sm = wsm[wid];
-    const int nw = gridDim.x * DCBF_WARPS_PER_CTA;
-    for (int b = blockIdx.x * DCBF_WARPS_PER_CTA + wid; b < B; b += nw) {
+__global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, int steps, BatchIn in, RolloutOut out) {
+    wp::WarpShared<NS> &sm = wp::g_sm<NS>;
+    const wp::CtaShared &cs_ = wp::g_cs;
+    const int lane = wp::lane_id();
+    wp::stage_cta<NS>(P, K, tab, lane);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
         int leg = in.leg ? in.leg[b] : 1;
         if (lane == 0) {
             double x0[5], u0[15], g[2];
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) r
         int done = 0, ninf = 0, tot = 0;
         for (int st = 0; st < steps; st++) {
             wp::WState S;
-            wp::solve_lip_warp<NS>(cs_, sm, in, b, lane, leg, S);
+            wp::solve_lip_warp<NS>(in, b, lane, leg, S);
             tot += S.iters;
             if (S.status == 2) ninf++;
             const bool close = wp::w_close<NS>(cs_.P, sm);
@@ -241,9 +254,6 @@ __global__ void __launch_bounds__(32 * DCBF_WARPS_PER_CTA, DCBF_WARP_MIN_CTAS) r
     }
 }
 
-template <int NS>
-static size_t warp_smem_bytes() { return ((sizeof(wp::CtaShared) + 15) & ~(size_t)15) + sizeof(wp::WarpShared<NS>) * DCBF_WARPS_PER_CTA; }
-
 // ---------------------------------------------------------------------------------------------------------------
 // FP64 peak microbenchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------------------------------------
@@ -269,23 +279,19 @@ static int warp_slots(const dcbf_ctx *ctx) {
 }
 template <int NS>
 static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
-    const size_t smem = warp_smem_bytes<NS>();
-    CK(cudaFuncSetAttribute(solve_lip_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (B + DCBF_WARPS_PER_CTA - 1) / DCBF_WARPS_PER_CTA;
-    const int cap = ctx->sm_count * 16;
-    if (grid > cap) grid = cap;
-    solve_lip_warp_kernel<NS><<<grid, 32 * DCBF_WARPS_PER_CTA, smem, st>>>(ctx->P, ctx->K, B, in, out);
+    int grid = B;
+    const int cap = ctx->sm_count * DCBF_WARP_GRID_CAP;
+    if (cap > 0 && grid > cap) grid = cap;
+    solve_lip_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
 template <int NS>
 static int launch_rollout_warp(dcbf_ctx *ctx, int B, int steps, const BatchIn &in, const RolloutOut &out, cudaStream_t st) {
-    const size_t smem = warp_smem_bytes<NS>();
-    CK(cudaFuncSetAttribute(rollout_lip_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (B + DCBF_WARPS_PER_CTA - 1) / DCBF_WARPS_PER_CTA;
-    const int cap = ctx->sm_count * 16;
-    if (grid > cap) grid = cap;
-    rollout_lip_warp_kernel<NS><<<grid, 32 * DCBF_WARPS_PER_CTA, smem, st>>>(ctx->P, ctx->K, B, steps, in, out);
+    int grid = B;
+    const int cap = ctx->sm_count * DCBF_WARP_GRID_CAP;
+    if (cap > 0 && grid > cap) grid = cap;
+    rollout_lip_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, steps, in, out);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -344,6 +350,13 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     const char *wb = getenv("DCBF_WARP_MAX_BATCH");
     if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     {
+        wp::WarpTables *W = new (std::nothrow) wp::WarpTables();
+        const bool ok = W && wp::build_warp_tables(ctx->K, *W) && cudaMalloc(&ctx->d_tab, sizeof(wp::WarpTables)) == cudaSuccess &&
+                        cudaMemcpy(ctx->d_tab, W, sizeof(wp::WarpTables), cudaMemcpyHostToDevice) == cudaSuccess;
+        delete W;
+        if (!ok) { cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); delete ctx; return DCBF_ERR_CUDA; }
+    }
+    {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_lip_refill_kernel, DCBF_BLOCK, 0);
         ctx->refill_ctas_lip = (nb > 0 ? nb : 1) * ctx->sm_count;
@@ -362,7 +375,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
 void dcbf_destroy(dcbf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_counter); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
+    cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

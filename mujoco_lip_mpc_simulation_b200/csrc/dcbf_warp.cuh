@@ -1,17 +1,23 @@
 // dcbf_warp.cuh -- warp-cooperative variant of the LIP solver: ONE PROBLEM PER WARP (device only).
 //
 // The per-thread kernels of dcbf_lanes.cuh have the lowest instruction count per problem but a long serial chain per
-// interior-point iteration (~7 k dependent instructions) and, at 255 registers, only two warps per scheduler: a
-// 4096-scenario batch is bound by single-warp latency times the slowest problem's iteration count (profiles/
-// r01_summary.md).  Here the 32 lanes of a warp share one problem:
-//   * rows are distributed over lanes (row r -> lane r % 32, slot r / 32); every lane evaluates its rows, applies
-//     the slack/multiplier updates and publishes the row gradient (9 doubles) and weights to shared memory;
-//   * the condensed matrix  W + J^T Sigma J  and the three J^T-vectors are accumulated entry-parallel (72 entries over
-//     32 lanes) from the staged rows; the Lagrangian Hessian is assembled from per-node Hessians (5x5 with 8 distinct
-//     entries) through the constant feature map T (24 features x 9 variables);
-//   * norms, merit values and step sizes are warp-shuffle reductions; the 9x9 Cholesky is row-owned (lane i owns row i)
-//     with the factor staged in shared memory; all scalar control flow is replicated and therefore uniform.
-// ~2.5 k warp instructions per iteration at ~100 registers (4-5 warps per scheduler), ~3x shorter dependent chain.
+// interior-point iteration and, at 255 registers, only two warps per scheduler: a 4096-scenario batch is bound by
+// single-warp latency times the slowest problem's iteration count (profiles/r01_summary.md).  Here the 32 lanes of a
+// warp share one problem:
+//   * rows are ordered step-major (all rows of step 0, then step 1, then step 2) and distributed over lanes (row r ->
+//     lane r % 32, slot r / 32); every lane evaluates its rows, applies the slack/multiplier updates in registers and
+//     stages the row gradient, sigma * gradient and the weights TRANSPOSED in shared memory (ST[a][r]: consecutive lanes
+//     write consecutive words, and an entry-parallel reader fetches two rows per 128-bit load);
+//   * row gradients come from six scalars per row and two constant coefficient vectors per (row class, step): in
+//     z = (foot, turn) space the rollout is affine, so d row / d foot_l = cA[l] * (d row / d node_{i+1}) + cB[l] * (d row /
+//     d node_i);
+//   * the condensed matrix  W + J^T Sigma J  and the three J^T-vectors are 72 dot products over the staged rows,
+//     distributed over the lanes in three rounds sorted by the first step whose rows can contribute (an entry that
+//     involves a variable of step s only sees rows of steps >= s); the Lagrangian Hessian is added from 27 node
+//     quantities through a host-built sparse table (at most 6 terms per entry);
+//   * norms, merit values and step sizes are warp-shuffle reductions; the 9x9 Cholesky is row-owned (lane i owns row
+//     i, lane 9 carries the right-hand side as a tenth row, which is the forward substitution) with the factor staged
+//     in shared memory; all scalar control flow is replicated and therefore uniform.
 // The algorithm (barrier rule, filter, restoration, status codes) is the one of ipm_iterate() in dcbf_core.cuh.
 #pragma once
 #include "dcbf_lanes.cuh"
@@ -19,68 +25,35 @@
 namespace dcbf {
 namespace wp {
 
-constexpr int NFEAT = 24;   // 3 nodes x (x, y, vx, vy, th) | 3 x (lx, ly) | 3 x dth
 enum { RT_NONE = 0, RT_CBF, RT_VBX, RT_VBY, RT_LEG, RT_DTH, RT_FENP, RT_FENM };
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int NSRC = 27;     // node quantities feeding the Lagrangian Hessian: 3 nodes x 8 entries, 3 leg multipliers
+constexpr int NHT = 6;       // terms per matrix entry in the Hessian table
+// flat layout of the assembled system: q1 q2 q3 (27) | pad | K (45, packed rows 0..8) | right-hand side (= packed row 9) | tail.
+// The tail lets all 32 lanes store "their" right-hand-side component without a lane test (only 0..8 are meaningful).
+constexpr int KQ_Q = 0;
+constexpr int KQ_K = 28;
+constexpr int KQ_RHS = KQ_K + 45;
+constexpr int KQ_LEN = KQ_RHS + 32;
+constexpr int LF_LEN = 56 + 32;   // factor rows 0..9, then one dump slot per lane for the branch-free stores
 
-__device__ __forceinline__ int FN(int k, int c) { return 5 * (k - 1) + c; }   // node k in 1..3, c: 0 x,1 y,2 vx,3 vy,4 th
-__device__ __forceinline__ int FLX(int i) { return 15 + 2 * i; }
-__device__ __forceinline__ int FLY(int i) { return 16 + 2 * i; }
-__device__ __forceinline__ int FDT(int i) { return 21 + i; }
-
-template <int NS>
-struct WarpShared {
-    double G[32 * NS][9];    // row gradients (internal variable order)
-    double SG[32 * NS][9];   // sigma * row gradient
-    double RW[32 * NS][4];   // sigma, w1, binv, y
-    double HQ[32 * NS][3];   // y * (2a', b', 2c') of the D-CBF rows
-    double obs[DCBF_KT][6];  // selected obstacles: cx, cy, a', b', c', rhs
-    double Kf[45], Lf[45], q[27], dz[9], zc[9], zt[9], red[8];
-    double x0[5], goal[2], graw[2];
-    double nodes[4][5];      // x, y, vx, vy, th of nodes 0..3
-    double trig[4][3];       // sin, cos, atan2 target of nodes 1..3
-    double nobj[4][10];      // f_k, nx, ny, nt, hxx, hxy, hyy, hxt, hyt, htt of the objective at node k
-    double NH[4][8];         // node Hessians xx, xy, yy, xt, yt, tt, vxt, vyt
-    double legy[3];
-    double filt_th[DCBF_FILT], filt_ph[DCBF_FILT];
+// Host-built constant tables, one copy per context in device memory (build_warp_tables()).
+struct WarpTables {
+    int desc[96];             // 3 rounds x 32 lanes: rowP | rowQ << 8 | class << 16 | out << 20   (-1: idle)
+    double hc[NHT][48];       // K[e] += hc[t][e] * src[hs[t][e]]
+    unsigned char hs[NHT][48];
+    double cab[10][6];        // (cA[3], cB[3]) per row class: CBF step 0..2, velocity rows step 0..2, leg step 0..2, turn
 };
 
-// per-CTA constants staged in shared memory: parameters, model constants, feature map, (row, col) of the 72 entries
-struct CtaShared {
-    dcbf_params P;
-    Consts K;
-    double T[NFEAT][9];
-    int ea[72], eb[72];
-};
+// variable order (fx0, fy0, fx1, fy1, fx2, fy2, t0, t1, t2): step of a variable
+inline int var_step(int a) { return a < 6 ? a >> 1 : a - 6; }
 
-__device__ __noinline__ double wsum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __noinline__ double wmax(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-__device__ __noinline__ double wmin(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-__device__ __forceinline__ int wsumi(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-
-// constant feature map T[f][a] = d feature_f / d z_a  (built once per CTA)
-__device__ __forceinline__ void build_T(const Consts &k, double (*T)[9]) {
-    for (int t = threadIdx.x; t < NFEAT * 9; t += blockDim.x) {
-        const int f = t / 9, a = t % 9;
+// d feature / d z for the 24 node features (3 nodes x (x, y, vx, vy, th) | 3 x (lx, ly) | 3 x dth); host only
+inline void build_feature_map(const Consts &k, double (*T)[9]) {
+    for (int f = 0; f < 24; f++) for (int a = 0; a < 9; a++) {
         double v = 0.0;
         const bool ax = a < 6 && (a & 1) == 0, ay = a < 6 && (a & 1) == 1;
-        const int l = a < 6 ? a >> 1 : a - 6;
+        const int l = var_step(a);
         if (f < 15) {
             const int kn = f / 5 + 1, c = f % 5;
             if (l < kn) {
@@ -96,34 +69,133 @@ __device__ __forceinline__ void build_T(const Consts &k, double (*T)[9]) {
                 if (l < i) v = k.gx[i - 1 - l];
                 else if (l == i) v = -1.0;
             }
-        } else {
-            if (a >= 6 && l == f - 21) v = 1.0;
-        }
+        } else if (a >= 6 && l == f - 21) v = 1.0;
         T[f][a] = v;
     }
 }
 
-struct RowDesc { int type, step, obs; };
-
-__device__ __forceinline__ RowDesc row_desc(int r, int Ks, bool has_fen) {
-    RowDesc d;
-    d.type = RT_NONE; d.step = 0; d.obs = 0;
-    if (r < 3 * Ks) { d.type = RT_CBF; d.step = r / Ks; d.obs = r - d.step * Ks; return d; }
-    const int q = r - 3 * Ks, t = q / 3;
-    if (t < (has_fen ? 6 : 4)) { d.type = RT_VBX + t; d.step = q - 3 * t; }
-    return d;
+inline bool build_warp_tables(const Consts &k, WarpTables &W) {
+    // ---- the 72 dot products, sorted by class = first step whose rows can contribute ---------------------------------
+    struct Ent { int rowP, rowQ, cls, out; };
+    Ent ent[72];
+    int n = 0;
+    for (int cls = 0; cls < 3; cls++) {
+        for (int a = 0; a < 9; a++) for (int b = 0; b <= a; b++) {
+            const int c = var_step(a) > var_step(b) ? var_step(a) : var_step(b);
+            if (c == cls) ent[n++] = {9 + a, b, cls, KQ_K + tri(a, b)};            // sum_r ST[9 + a][r] * ST[b][r]
+        }
+        for (int v = 0; v < 3; v++) for (int a = 0; a < 9; a++)
+            if (var_step(a) == cls) ent[n++] = {18 + 1 + v, a, cls, KQ_Q + 9 * v + a};   // sum_r ST[19 + v][r] * ST[a][r]
+    }
+    if (n != 72) return false;
+    for (int t = 0; t < 96; t++) W.desc[t] = t < 72 ? (ent[t].rowP | ent[t].rowQ << 8 | ent[t].cls << 16 | ent[t].out << 20) : -1;
+    // ---- Lagrangian Hessian map: sources = NH[kn][0..7] (xx, xy, yy, xt, yt, tt, vxt, vyt) for kn = 1..3, then legy[0..2] --
+    double T[24][9];
+    build_feature_map(k, T);
+    for (int t = 0; t < NHT; t++) for (int e = 0; e < 48; e++) { W.hc[t][e] = 0.0; W.hs[t][e] = (unsigned char)NSRC; }
+    static const int HP[8] = {0, 0, 1, 0, 1, 4, 2, 3}, HQ[8] = {0, 1, 1, 4, 4, 4, 4, 4};   // (p, q) of the 5x5 node Hessian
+    for (int a = 0; a < 9; a++) for (int b = 0; b <= a; b++) {
+        const int e = tri(a, b);
+        int cnt = 0;
+        for (int s = 0; s < NSRC; s++) {
+            double c = 0.0;
+            if (s < 24) {
+                const int kn = s / 8 + 1, h = s % 8, p = HP[h], q = HQ[h], fp = 5 * (kn - 1) + p, fq = 5 * (kn - 1) + q;
+                c = T[fp][a] * T[fq][b];
+                if (p != q) c += T[fq][a] * T[fp][b];
+            } else {
+                const int i = s - 24;
+                c = T[15 + 2 * i][a] * T[15 + 2 * i][b] + T[16 + 2 * i][a] * T[16 + 2 * i][b];
+            }
+            if (c != 0.0) {
+                if (cnt >= NHT) return false;
+                W.hc[cnt][e] = c; W.hs[cnt][e] = (unsigned char)s; cnt++;
+            }
+        }
+    }
+    // ---- gradient coefficient vectors ------------------------------------------------------------------------------------
+    for (int c = 0; c < 10; c++) for (int j = 0; j < 6; j++) W.cab[c][j] = 0.0;
+    for (int i = 0; i < 3; i++) for (int l = 0; l < 3; l++) {
+        if (l <= i) { W.cab[i][l] = k.gx[i - l]; W.cab[3 + i][l] = k.gv[i - l]; }       // cA of D-CBF / velocity rows
+        if (l < i) { W.cab[i][3 + l] = k.gx[i - 1 - l]; W.cab[6 + i][3 + l] = k.gx[i - 1 - l]; }   // cB of D-CBF / leg rows
+        if (l == i) W.cab[6 + i][3 + l] = -1.0;
+    }
+    return true;
 }
 
-// z is replicated in registers; dynamic element access goes through a switch-free select
-__device__ __forceinline__ double zsel(const double *z, int a) {
-    double v = z[0];
+#if defined(__CUDACC__)
+
+template <int NS> struct KsMax { static constexpr int v = NS == 1 ? 6 : (NS == 2 ? 17 : 2 * DCBF_MAX_OBS); };
+
+template <int NS>
+struct alignas(16) WarpShared {
+    static constexpr int RP = 32 * NS + 2;   // padded row length: class starts / ends are rounded to even rows
+    double ST[22][RP];       // staged rows, transposed: 0..8 gradient, 9..17 sigma * gradient, 18..21 sigma, w1, binv, y
+    double HQ[32 * NS][3];   // y * (2a', b', 2c') of the D-CBF rows
+    double obs[KsMax<NS>::v][6];   // selected obstacles: cx, cy, a', b', c', rhs
+    double KQ[KQ_LEN];       // assembled system (see KQ_*)
+    double Lf[LF_LEN];       // Cholesky factor (packed rows 0..8), the forward-substituted right-hand side (row 9), dump slots
+    double dz[32], zc[32], zt[32];   // 9 meaningful entries each; all lanes store
+    double x0[5], goal[2], graw[2];
+    double fr[4][4];         // free response (zero foot placements) x, y, vx, vy at nodes 0..3
+    double nodes[4][5];      // x, y, vx, vy, th of nodes 0..3
+    double trig[4][3];       // sin, cos, atan2 target of nodes 1..3
+    double nobj[4][10];      // f_k, nx, ny, nt, hxx, hxy, hyy, hxt, hyt, htt of the objective at node k
+    double NHf[NSRC + 1];    // Hessian sources (+ one zero for the padding terms of the table)
+    double cold[12];         // replicated scalars that are written once per event and read much later (see C_*): kept out of registers
+    double filt_th[DCBF_FILT], filt_ph[DCBF_FILT];
+};
+
+// per-CTA constants staged in shared memory
+struct CtaShared {
+    dcbf_params P;
+    Consts K;
+    double cab[10][6];
+    double hc[NHT][48];          // copy of the Hessian table (global loads in the assembly loop cost a long-scoreboard stall each)
+    unsigned char hs[NHT][48];
+    const WarpTables *tab;
+};
+
+// one warp per CTA: the per-problem scratch and the constants are static shared-memory objects, so every function sees
+// them as shared-space symbols (LDS/STS with immediate offsets, no generic pointers through the out-of-line calls)
+template <int NS> __shared__ WarpShared<NS> g_sm;
+__shared__ CtaShared g_cs;
+
+// %laneid through a volatile asm: the value stays in a register (the compiler otherwise re-reads SR_TID.X at every use)
+__device__ __forceinline__ int lane_id() {
+    int l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+
+__device__ __noinline__ double wmax(double v) {
 #pragma unroll
-    for (int j = 1; j < 9; j++) v = (a == j) ? z[j] : v;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ int wsumi(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 
-// value, feature ids and feature derivatives of one row
-struct RowEval { double c, d[4]; int f[4]; int nf; double hq0, hq1, hq2; };
+struct RowDesc { int type, step, obs, cls; };
+
+// step-major row order: step i holds  [D-CBF x Ks, v_bx, v_by, leg, turn, (fen+, fen-)]
+__device__ __forceinline__ RowDesc row_desc(int r, int Ks, int ms, int m) {
+    RowDesc d;
+    d.type = RT_NONE; d.step = 0; d.obs = 0; d.cls = 9;
+    if (r >= m) return d;
+    d.step = r / ms;
+    const int w = r - d.step * ms;
+    if (w < Ks) { d.type = RT_CBF; d.obs = w; d.cls = d.step; }
+    else {
+        d.type = RT_VBX + (w - Ks);
+        d.cls = d.type == RT_LEG ? 6 + d.step : (d.type == RT_DTH ? 9 : 3 + d.step);
+    }
+    return d;
+}
+
 struct RowBnd { double lo, hi; bool has_lo, has_hi; };
 
 // static bounds of a row (MPC_LIP_sig_step.py:193-227, MPC_LIP_modi.py:203-245; split form of the coupling row)
@@ -142,13 +214,14 @@ __device__ __forceinline__ RowBnd row_bounds(const dcbf_params &P, const RowDesc
     return b;
 }
 
+// value of one row and, with GRAD, the six scalars its gradient is made of:
+//   d row / d foot_l = cA[l] * (p0, p1) + cB[l] * (q0, q1),   d row / d turn_l = (l <= step) * t_all + (l == step) * t_own
+struct RowEval { double c, p0, p1, q0, q1, t_all, t_own, hq0, hq1, hq2; };
+
 template <int NS, bool GRAD>
 __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
-    e.nf = 0; e.c = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0;
-    if (GRAD) {
-#pragma unroll
-        for (int p = 0; p < 4; p++) { e.d[p] = 0.0; e.f[p] = 0; }
-    }
+    e.c = 0.0;
+    if (GRAD) { e.p0 = e.p1 = e.q0 = e.q1 = e.t_all = e.t_own = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0; }
     const int i = rd.step, kn = i + 1;
     if (rd.type == RT_CBF) {
         const double *o = sm.obs[rd.obs];
@@ -157,76 +230,74 @@ __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<
         const double ea = o[2], eb = o[3], ec = o[4];
         e.c = (ea * ax * ax + eb * ax * ay + ec * ay * ay - o[5]) + gm1 * (ea * bx * bx + eb * bx * by + ec * by * by - o[5]);
         if (GRAD) {
-            e.f[0] = FN(kn, 0); e.f[1] = FN(kn, 1);
-            e.d[0] = 2.0 * ea * ax + eb * ay; e.d[1] = 2.0 * ec * ay + eb * ax;
-            e.nf = 2;
-            if (i > 0) {
-                e.f[2] = FN(i, 0); e.f[3] = FN(i, 1);
-                e.d[2] = gm1 * (2.0 * ea * bx + eb * by); e.d[3] = gm1 * (2.0 * ec * by + eb * bx);
-                e.nf = 4;
-            }
+            e.p0 = 2.0 * ea * ax + eb * ay; e.p1 = 2.0 * ec * ay + eb * ax;
+            e.q0 = gm1 * (2.0 * ea * bx + eb * by); e.q1 = gm1 * (2.0 * ec * by + eb * bx);
             e.hq0 = 2.0 * ea; e.hq1 = eb; e.hq2 = 2.0 * ec;
-        }
-    } else if (rd.type == RT_VBX || rd.type == RT_VBY || rd.type == RT_FENP || rd.type == RT_FENM) {
-        const double sn = sm.trig[kn][0], cs = sm.trig[kn][1];
-        const double vx = sm.nodes[kn][2], vy = sm.nodes[kn][3];
-        const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
-        if (GRAD) { e.f[0] = FN(kn, 2); e.f[1] = FN(kn, 3); e.f[2] = FN(kn, 4); e.nf = 3; }
-        if (rd.type == RT_VBY) {
-            e.c = vby;
-            if (GRAD) { e.d[0] = -sn; e.d[1] = cs; e.d[2] = -vbx; }
-        } else {
-            if (GRAD) { e.d[0] = cs; e.d[1] = sn; e.d[2] = vby; }
-            if (rd.type == RT_VBX) e.c = vbx;
-            else {
-                const double sg = rd.type == RT_FENP ? P.s_turn : -P.s_turn;
-                e.c = vbx + sg * z[6 + i];
-                if (GRAD) { e.f[3] = FDT(i); e.d[3] = sg; e.nf = 4; }
-            }
         }
     } else if (rd.type == RT_LEG) {
         const double lx = sm.nodes[i][0] - z[2 * i], ly = sm.nodes[i][1] - z[2 * i + 1];
         e.c = lx * lx + ly * ly;
-        if (GRAD) { e.f[0] = FLX(i); e.f[1] = FLY(i); e.d[0] = 2.0 * lx; e.d[1] = 2.0 * ly; e.nf = 2; }
+        if (GRAD) { e.q0 = 2.0 * lx; e.q1 = 2.0 * ly; }
     } else if (rd.type == RT_DTH) {
         e.c = z[6 + i];
-        if (GRAD) { e.f[0] = FDT(i); e.d[0] = 1.0; e.nf = 1; }
+        if (GRAD) e.t_own = 1.0;
+    } else if (rd.type != RT_NONE) {   // v_bx, v_by, fen+, fen-
+        const double sn = sm.trig[kn][0], cs = sm.trig[kn][1];
+        const double vx = sm.nodes[kn][2], vy = sm.nodes[kn][3];
+        const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
+        if (rd.type == RT_VBY) {
+            e.c = vby;
+            if (GRAD) { e.p0 = -sn; e.p1 = cs; e.t_all = -vbx; }
+        } else {
+            if (GRAD) { e.p0 = cs; e.p1 = sn; e.t_all = vby; }
+            if (rd.type == RT_VBX) e.c = vbx;
+            else {
+                const double sg = rd.type == RT_FENP ? P.s_turn : -P.s_turn;
+                e.c = vbx + sg * z[6 + i];
+                if (GRAD) e.t_own = sg;
+            }
+        }
     }
 }
 
-struct WState {   // replicated scalars of one problem
-    double mu, sf, alpha, alpha_z, delta_last, lm_lambda, resto_target, resto_entry, theta_max, theta_min, obj, viol;
-    int nf, iters, acc_cnt, status, phase, nstall, tiny;
+// slots of WarpShared::cold.  Every lane stores the same value and nobody reads before the next __syncwarp(); none of these is
+// updated by read-modify-write (that would not be safe if the lanes of a warp drifted apart).
+enum { C_RESTO_TARGET = 0, C_RESTO_ENTRY, C_THETA_MAX, C_THETA_MIN, C_OBJ, C_VIOL, C_ST_THETA, C_ST_LOGSUM, C_ST_V2, C_ST_VMAX };
+
+struct WState {   // replicated scalars of one problem (registers)
+    double mu, sf, alpha, alpha_z, delta_last, lm_lambda;
+    double v2_h1, v2_h2;   // windowed stagnation test of the restoration (see ipm_iterate())
+    int nf, iters, acc_cnt, status, phase, nstall, tiny, nresto;
     bool pending, reinit, first;
+#ifdef DCBF_DBG
+    int n_fact, n_fail, n_trial, n_pass;
+#endif
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// rollout + per-node trigonometry and objective terms at the point z (shared memory); collective, out of line
+// nodes 1..3 at the point z (lanes 0..2, directly from the free response and the constant influence coefficients),
+// per-node trigonometry and objective terms; collective, out of line
 // ---------------------------------------------------------------------------------------------------------------
 template <int NS>
-__device__ __noinline__ void w_nodes(const CtaShared &cs_, WarpShared<NS> &sm, const double *z, int lane, double sf, bool want_hess) {
-    const Consts &k = cs_.K;
+__device__ __noinline__ void w_nodes(const double *z, int lane, double sf, bool want_hess) {
+    WarpShared<NS> &sm = g_sm<NS>;
+    const CtaShared &cs_ = g_cs;
     const dcbf_params &P = cs_.P;
-    if (lane == 0) {
-        double x = sm.x0[0], y = sm.x0[1], vx = sm.x0[2], vy = sm.x0[3], th = sm.x0[4];
-        sm.nodes[0][0] = x; sm.nodes[0][1] = y; sm.nodes[0][2] = vx; sm.nodes[0][3] = vy; sm.nodes[0][4] = th;
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const double fx = z[2 * i], fy = z[2 * i + 1];
-            const double xn = k.C * x + k.Sb * vx + k.gx[0] * fx, yn = k.C * y + k.Sb * vy + k.gx[0] * fy;
-            vx = k.bS * x + k.C * vx + k.gv[0] * fx; vy = k.bS * y + k.C * vy + k.gv[0] * fy;
-            x = xn; y = yn; th += z[6 + i];
-            sm.nodes[i + 1][0] = x; sm.nodes[i + 1][1] = y; sm.nodes[i + 1][2] = vx; sm.nodes[i + 1][3] = vy; sm.nodes[i + 1][4] = th;
-        }
-    }
-    __syncwarp();
     if (lane < 3) {
         const int kn = lane + 1;
-        const double th = sm.nodes[kn][4];
+        double x = sm.fr[kn][0], y = sm.fr[kn][1], vx = sm.fr[kn][2], vy = sm.fr[kn][3], th = sm.x0[4];
+        const double *cx = cs_.cab[lane], *cv = cs_.cab[3 + lane];   // gx[kn-1-l], gv[kn-1-l] for l < kn, else 0
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+            const double fx = z[2 * l], fy = z[2 * l + 1];
+            x = fma(cx[l], fx, x); y = fma(cx[l], fy, y); vx = fma(cv[l], fx, vx); vy = fma(cv[l], fy, vy);
+            th += l < kn ? z[6 + l] : 0.0;
+        }
+        sm.nodes[kn][0] = x; sm.nodes[kn][1] = y; sm.nodes[kn][2] = vx; sm.nodes[kn][3] = vy; sm.nodes[kn][4] = th;
         double sn, cs;
         dsincos(th, &sn, &cs);
         const double w = P.w_q + (kn == 1 ? P.w_p : 0.0);
-        const double ex = sm.nodes[kn][0] - sm.goal[0], ey = sm.nodes[kn][1] - sm.goal[1];
+        const double ex = x - sm.goal[0], ey = y - sm.goal[1];
         const double dx = -ex, dy = -ey;
         const double r2 = dx * dx + dy * dy, ir2 = drcp(r2);
         const double tar = datan2(dy, dx);
@@ -263,12 +334,14 @@ __device__ __forceinline__ void reduce8_inline(Stat8 &t) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// the solver for one problem (all 32 lanes call it with identical arguments).  Inputs in sm: x0, graw, zc.
+// the solver for one problem (all 32 lanes call it with identical arguments).  Inputs in sm: x0, graw, zc, fr.
 // ---------------------------------------------------------------------------------------------------------------
 template <int NS>
-__device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const BatchIn &in, int b, int lane, int leg, WState &S) {
+__device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WState &S) {
+    constexpr int RP = WarpShared<NS>::RP;
+    WarpShared<NS> &sm = g_sm<NS>;
+    const CtaShared &cs_ = g_cs;
     const dcbf_params &P = cs_.P;
-    const double (*T)[9] = cs_.T;
     // ---- problem setup -------------------------------------------------------------------------------------------
     const int fld = in.field ? in.field[b] : 0;
     const double *cir = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC;
@@ -295,8 +368,10 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
         Ks = __popc(mask);
         if (sel) {
             const int pos = __popc(mask & ((1u << lane) - 1u));
+            if (pos < KsMax<NS>::v) {
 #pragma unroll
-            for (int c = 0; c < 6; c++) sm.obs[pos][c] = rec[c];
+                for (int c = 0; c < 6; c++) sm.obs[pos][c] = rec[c];
+            }
         }
         bool hit = false;
         double ngx = 0.0, ngy = 0.0;
@@ -326,43 +401,65 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             g0 = __shfl_sync(FULL, ngx, src); g1 = __shfl_sync(FULL, ngy, src);
         }
         if (lane == 0) { sm.goal[0] = g0; sm.goal[1] = g1; }
+        if (lane < 5) sm.nodes[0][lane] = sm.x0[lane];
         __syncwarp();
     }
     const bool has_fen = P.has_fen != 0;
-    const int m = 3 * (Ks + (has_fen ? 6 : 4));
+    const int ms = Ks + (has_fen ? 6 : 4);   // rows per step
+    const int m = 3 * ms;
+    const int mp = (m + 1) & ~1;             // dot products run over row pairs
     RowDesc rd[NS];
     RowBnd rb[NS];
     double rs[NS], rzl[NS], rzu[NS], rds[NS], rel[NS], reu[NS];
     int nz_l = 0;
 #pragma unroll
     for (int s = 0; s < NS; s++) {
-        rd[s] = row_desc(s * 32 + lane, Ks, has_fen);
-        if (s * 32 + lane >= m) rd[s].type = RT_NONE;
+        rd[s] = row_desc(s * 32 + lane, Ks, ms, m);
         rb[s] = row_bounds(P, rd[s], leg);
         nz_l += (rb[s].has_lo ? 1 : 0) + (rb[s].has_hi ? 1 : 0);
         rs[s] = rzl[s] = rzu[s] = rds[s] = rel[s] = reu[s] = 0.0;
     }
     const int nz = wsumi(nz_l), nrows = m;
+    // the lane's dot products of the three assembly rounds (packed: operand rows, first contributing step, output slot)
+    int dsc[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++) dsc[t] = __ldg(&cs_.tab->desc[32 * t + lane]);
+    const int l8 = lane < 9 ? lane : 8;
+    const int rowbase = lane < 10 ? lane * (lane + 1) / 2 : 0;
     // ---- solver state ------------------------------------------------------------------------------------------------
-    S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4; S.resto_target = 0.0;
-    S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0; S.tiny = 0;
-    S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.obj = 0.0; S.viol = 0.0;
+    S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4; 
+    sm.cold[C_RESTO_TARGET] = 0.0; sm.cold[C_RESTO_ENTRY] = 0.0; sm.cold[C_THETA_MAX] = 1e300; sm.cold[C_THETA_MIN] = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0; S.tiny = 0;
+    S.nresto = 0; S.v2_h1 = 0.0; S.v2_h2 = 0.0;
+    S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; sm.cold[C_OBJ] = 0.0; sm.cold[C_VIOL] = 0.0;
     const double tol = P.tol;
+    const double *stf = &sm.ST[0][0];
+#ifdef DCBF_DBG
+    S.n_fact = S.n_fail = S.n_trial = S.n_pass = 0;
+#endif
 
     bool nodes_valid = false;      // sm.nodes / trig / nobj (with Hessian terms) already describe zc (staged by the accepted trial)
     double carry_log = 0.0;        // sum of log(gaps) at the accepted trial point = barrier term of the next full pass
     bool carry_ok = false;
     for (;;) {
         const bool resto = S.phase == PH_RESTO;
-        if (!nodes_valid) w_nodes<NS>(cs_, sm, sm.zc, lane, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
+#ifdef DCBF_DBG
+        S.n_pass++;
+#endif
+        if (!nodes_valid) w_nodes<NS>(sm.zc, lane, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
         nodes_valid = false;
-        // objective value and gradient (lane a < 9 owns grad[a])
+        // objective value and gradient (lane a < 9 owns grad[a]):  d node_kn / d foot_l = gx[kn-1-l],  d th_kn / d turn_l = 1
         const double fobj = sm.nobj[1][0] + sm.nobj[2][0] + sm.nobj[3][0];
         double grad_a = 0.0;
-        if (lane < 9) {
+        {   // branch-free (see the note at the factorisation): lanes >= 9 compute on clamped indices and select 0
+            const int l = l8 < 6 ? l8 >> 1 : l8 - 6;
+            const int c = l8 < 6 ? 1 + (l8 & 1) : 3;
 #pragma unroll
-            for (int kn = 1; kn <= 3; kn++)
-                grad_a += sm.nobj[kn][1] * T[FN(kn, 0)][lane] + sm.nobj[kn][2] * T[FN(kn, 1)][lane] + sm.nobj[kn][3] * T[FN(kn, 4)][lane];
+            for (int kn = 1; kn <= 3; kn++) {
+                const double wf = cs_.cab[kn - 1][l];
+                const double w = l8 < 6 ? wf : (l < kn ? 1.0 : 0.0);
+                grad_a = fma(sm.nobj[kn][c], w, grad_a);
+            }
+            grad_a = lane < 9 ? grad_a : 0.0;
         }
         if (S.first) {
             const double gmax = wmax(fabs(grad_a));
@@ -437,99 +534,88 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                     w1 = sig * rc;
                 }
             }
-            // stage (rows beyond m stage neutral values so that the entry-parallel loops need no guards)
-            double g[9];
+            // stage the transposed row (rows beyond m stage zeros so that the dot products need no guards)
+            {
+                const double *ab = cs_.cab[rd[s].cls];
+                const int i = rd[s].step;
+                double *col = &sm.ST[0][r];
 #pragma unroll
-            for (int a = 0; a < 9; a++) g[a] = 0.0;
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                if (p < e.nf) {
-                    const double dp = e.d[p];
-                    const double *Tf = T[e.f[p]];
-#pragma unroll
-                    for (int a = 0; a < 9; a++) g[a] = fma(dp, Tf[a], g[a]);
+                for (int l = 0; l < 3; l++) {
+                    const double ca = ab[l], cb = ab[3 + l];
+                    const double gxv = fma(ca, e.p0, cb * e.q0), gyv = fma(ca, e.p1, cb * e.q1);
+                    const double gtv = (l <= i ? e.t_all : 0.0) + (l == i ? e.t_own : 0.0);
+                    col[(2 * l) * RP] = gxv; col[(2 * l + 1) * RP] = gyv; col[(6 + l) * RP] = gtv;
+                    col[(9 + 2 * l) * RP] = sig * gxv; col[(9 + 2 * l + 1) * RP] = sig * gyv; col[(9 + 6 + l) * RP] = sig * gtv;
                 }
+                col[18 * RP] = sig; col[19 * RP] = w1; col[20 * RP] = binv; col[21 * RP] = y;
             }
-#pragma unroll
-            for (int a = 0; a < 9; a++) { sm.G[r][a] = g[a]; sm.SG[r][a] = sig * g[a]; }
-            sm.RW[r][0] = sig; sm.RW[r][1] = w1; sm.RW[r][2] = binv; sm.RW[r][3] = y;
             sm.HQ[r][0] = y * e.hq0; sm.HQ[r][1] = y * e.hq1; sm.HQ[r][2] = y * e.hq2;
             st8.s0 += t_rc; st8.s1 += t_z; st8.s2 += t_log; st8.s3 += t_v2;
             st8.m0 = fmax(st8.m0, t_rc); st8.m1 = fmax(st8.m1, -t_cmin); st8.m2 = fmax(st8.m2, t_cmax); st8.m3 = fmax(st8.m3, t_v);
         }
+        __syncwarp();   // the row branches reconverge here, before the shuffles
         reduce8_inline(st8);
-        __syncwarp();
         const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? carry_log : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
                      st_cmin = -st8.m1, st_cmax = st8.m2, st_vmax = st8.m3;
         carry_ok = false;
-        // ---- node Hessians ---------------------------------------------------------------------------------------------
+        sm.cold[C_ST_THETA] = st_theta; sm.cold[C_ST_LOGSUM] = st_logsum; sm.cold[C_ST_V2] = st_v2; sm.cold[C_ST_VMAX] = st_vmax;
+        // ---- node Hessians -> the 27 sources of the Hessian table ---------------------------------------------------------------
         {
             const double gm1 = P.gamma - 1.0;
-            if (lane < 9) {            // position block: node kn = lane/3 + 1, component lane % 3
-                const int kn = lane / 3 + 1, c = lane % 3;
+            const double *yv = sm.ST[21];
+            const int lp = lane - 16;
+            if ((unsigned)lp < 9u) {   // position block on lanes 16..24: node kn = lp/3 + 1, component lp % 3
+                const int kn = lp / 3 + 1, c = lp % 3;
                 double acc = sm.nobj[kn][4 + c];
-                for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * Ks + j][c];
-                if (kn < 3) for (int j = 0; j < Ks; j++) acc = fma(gm1, sm.HQ[kn * Ks + j][c], acc);
-                sm.NH[kn][c] = acc;
-            } else if (lane < 12) {    // heading / velocity entries of node kn = lane - 8 (rows of step kn - 1)
-                const int kn = lane - 8, i = kn - 1, base = 3 * Ks;
-                double Yx = sm.RW[base + i][3], Yy = sm.RW[base + 3 + i][3];
-                if (has_fen) Yx += sm.RW[base + 12 + i][3] + sm.RW[base + 15 + i][3];
+                for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * ms + j][c];
+                if (kn < 3) for (int j = 0; j < Ks; j++) acc = fma(gm1, sm.HQ[kn * ms + j][c], acc);
+                sm.NHf[8 * (kn - 1) + c] = acc;
+            } else if (lane < 3) {     // heading / velocity entries of node kn = lane + 1 (rows of step kn - 1)
+                const int kn = lane + 1, i = kn - 1, base = i * ms + Ks;
+                double Yx = yv[base], Yy = yv[base + 1];
+                if (has_fen) Yx += yv[base + 4] + yv[base + 5];
                 const double sn = sm.trig[kn][0], cs = sm.trig[kn][1];
                 const double vx = sm.nodes[kn][2], vy = sm.nodes[kn][3];
                 const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
-                sm.NH[kn][3] = sm.nobj[kn][7]; sm.NH[kn][4] = sm.nobj[kn][8];
-                sm.NH[kn][5] = sm.nobj[kn][9] - (Yx * vbx + Yy * vby);
-                sm.NH[kn][6] = -sn * Yx - cs * Yy; sm.NH[kn][7] = cs * Yx - sn * Yy;
-                sm.legy[i] = 2.0 * sm.RW[base + 6 + i][3];
+                double *H = &sm.NHf[8 * i];
+                H[3] = sm.nobj[kn][7]; H[4] = sm.nobj[kn][8];
+                H[5] = sm.nobj[kn][9] - (Yx * vbx + Yy * vby);
+                H[6] = -sn * Yx - cs * Yy; H[7] = cs * Yx - sn * Yy;
+                sm.NHf[24 + i] = 2.0 * yv[base + 2];
             }
         }
         __syncwarp();
-        // ---- condensed matrix and J^T vectors, entry-parallel (72 entries over 32 lanes) ---------------------------------------
-        for (int e = lane; e < 72; e += 32) {
-            const int a = cs_.ea[e], bcol = cs_.eb[e];
-            double acc = 0.0;
-            if (e < 45) {
-                const double *pa = &sm.SG[0][a], *pb = &sm.G[0][bcol];
-                double acc1 = 0.0;
-                int r = 0;
-                for (; r + 1 < m; r += 2) { acc = fma(pa[9 * r], pb[9 * r], acc); acc1 = fma(pa[9 * r + 9], pb[9 * r + 9], acc1); }
-                if (r < m) acc = fma(pa[9 * r], pb[9 * r], acc);
-                acc += acc1;
-                // Lagrangian Hessian through the feature map
-#pragma unroll 1
-                for (int kn = 1; kn <= 3; kn++) {
-                    const double Xa = T[FN(kn, 0)][a], Ya = T[FN(kn, 1)][a], VXa = T[FN(kn, 2)][a], VYa = T[FN(kn, 3)][a], Ta = T[FN(kn, 4)][a];
-                    const double Xb = T[FN(kn, 0)][bcol], Yb = T[FN(kn, 1)][bcol], VXb = T[FN(kn, 2)][bcol], VYb = T[FN(kn, 3)][bcol], Tb = T[FN(kn, 4)][bcol];
-                    const double *H = sm.NH[kn];
-                    const double ux = H[0] * Xb + H[1] * Yb + H[3] * Tb;
-                    const double uy = H[1] * Xb + H[2] * Yb + H[4] * Tb;
-                    const double ut = H[3] * Xb + H[4] * Yb + H[5] * Tb + H[6] * VXb + H[7] * VYb;
-                    acc += Xa * ux + Ya * uy + Ta * ut + (VXa * H[6] + VYa * H[7]) * Tb;
+        // ---- condensed matrix and J^T vectors: three rounds of dot products over row pairs ---------------------------------------
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int d = dsc[t];
+            if (d >= 0) {
+                const double *pp = stf + (d & 0xff) * RP, *pq = stf + ((d >> 8) & 0xff) * RP;
+                const int lo = (((d >> 16) & 0xf) * ms) & ~1, eo = d >> 20;
+                double acc0 = 0.0, acc1 = 0.0;
+                for (int r = mp - 2; r >= lo; r -= 2) {
+                    const double2 u = *reinterpret_cast<const double2 *>(pp + r), v = *reinterpret_cast<const double2 *>(pq + r);
+                    acc0 = fma(u.x, v.x, acc0); acc1 = fma(u.y, v.y, acc1);
                 }
-#pragma unroll 1
-                for (int i = 0; i < 3; i++)
-                    acc += sm.legy[i] * (T[FLX(i)][a] * T[FLX(i)][bcol] + T[FLY(i)][a] * T[FLY(i)][bcol]);
-                sm.Kf[e] = acc;
-            } else {
-                const double *pw = &sm.RW[0][bcol], *pg = &sm.G[0][a];   // bcol = 1 + vector index
-                double acc1 = 0.0;
-                int r = 0;
-                for (; r + 1 < m; r += 2) { acc = fma(pw[4 * r], pg[9 * r], acc); acc1 = fma(pw[4 * r + 4], pg[9 * r + 9], acc1); }
-                if (r < m) acc = fma(pw[4 * r], pg[9 * r], acc);
-                acc += acc1;
-                sm.q[e - 45] = acc;
+                double acc = acc0 + acc1;
+                if (eo >= KQ_K) {   // Lagrangian Hessian through the table
+                    const int e = eo - KQ_K;
+#pragma unroll
+                    for (int h = 0; h < NHT; h++) acc = fma(cs_.hc[h][e], sm.NHf[cs_.hs[h][e]], acc);
+                }
+                sm.KQ[eo] = acc;
             }
         }
         __syncwarp();
         S.pending = false; S.reinit = false;
-        S.obj = fobj; S.viol = st_vmax;
+        sm.cold[C_OBJ] = fobj; sm.cold[C_VIOL] = st_vmax;
         if (!(fobj == fobj) || !(st_theta == st_theta)) { S.status = -13; break; }
         // ---- convergence / barrier update / right-hand side ---------------------------------------------------------------
+        const double *q = &sm.KQ[KQ_Q];
         double rhs_a = 0.0;
         if (!resto) {
-            if (S.first) { S.theta_max = 1e4 * fmax(1.0, st_theta); S.theta_min = 1e-4 * fmax(1.0, st_theta); S.first = false; }
-            const double dinf = wmax(lane < 9 ? fabs(fma(S.sf, grad_a, sm.q[18 + lane])) : 0.0);
+            if (S.first) { sm.cold[C_THETA_MAX] = 1e4 * fmax(1.0, st_theta); sm.cold[C_THETA_MIN] = 1e-4 * fmax(1.0, st_theta); S.first = false; }
+            const double dinf = wmax(lane < 9 ? fabs(fma(S.sf, grad_a, q[18 + l8])) : 0.0);
             const double sd = fmax(100.0, ddiv(2.0 * st_zsum, (double)(nrows + nz))) * 0.01;
             const double sc = fmax(100.0, ddiv(st_zsum, (double)(nz > 0 ? nz : 1))) * 0.01;
             const double isd = drcp(sd), isc = drcp(sc);
@@ -539,8 +625,8 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                 E0 = fmax(fmax(dinf * isd, st_pinf), st_cmax * isc);
                 const double Emu = fmax(fmax(dinf * isd, st_pinf), compm * isc);
                 if (E0 <= tol) break;
-                if (Emu <= 10.0 * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
-                    S.mu = fmax(tol * 0.1, fmin(0.2 * S.mu, S.mu * sqrt(S.mu)));
+                if (Emu <= DCBF_KAPPA_EPS * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
+                    S.mu = fmax(tol * 0.1, fmin(DCBF_KAPPA_MU * S.mu, DCBF_MU_POW(S.mu)));
                     S.nf = 0;
                     continue;
                 }
@@ -555,23 +641,25 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                 if (lane == 0) { sm.filt_th[slot] = (1.0 - 1e-5) * st_theta; sm.filt_ph[slot] = (S.sf * fobj - S.mu * st_logsum) - 1e-5 * st_theta; }
                 if (S.nf < DCBF_FILT) S.nf++;
                 __syncwarp();
-                S.phase = PH_RESTO; S.resto_entry = st_vmax; S.resto_target = fmax(0.1 * st_vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0;
+                S.phase = PH_RESTO; sm.cold[C_RESTO_ENTRY] = st_vmax; sm.cold[C_RESTO_TARGET] = fmax(0.1 * st_vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0; S.nresto = 0;
                 S.iters++;
                 continue;
             }
-            if (lane < 9) rhs_a = -S.sf * grad_a - sm.q[lane] + S.mu * sm.q[9 + lane];
+            rhs_a = -S.sf * grad_a - q[l8] + S.mu * q[9 + l8];
         } else {
-            if (st_vmax <= S.resto_target) { S.phase = PH_MAIN; S.reinit = true; continue; }
-            const double gn = wmax(lane < 9 ? fabs(sm.q[lane]) : 0.0);
+            if (st_vmax <= sm.cold[C_RESTO_TARGET]) { S.phase = PH_MAIN; S.reinit = true; continue; }
+            const double gn = wmax(lane < 9 ? fabs(q[l8]) : 0.0);
             const bool stationary = gn <= 1e-10 * fmax(1.0, st_vmax) || S.lm_lambda > 1e12;
             if (stationary) {
                 if (st_vmax > P.constr_viol_tol) { S.status = 2; break; }
-                if (S.resto_entry <= 1e-9 || S.nstall++ >= 1) { S.status = -2; break; }   // see ipm_iterate()
+                if (sm.cold[C_RESTO_ENTRY] <= 1e-9 || S.nstall++ >= 1) { S.status = -2; break; }   // see ipm_iterate()
                 S.phase = PH_MAIN; S.reinit = true; continue;
             }
             if (S.iters >= P.max_iter) { S.status = -1; break; }
-            if (lane < 9) rhs_a = -sm.q[lane];
+            rhs_a = -q[l8];
         }
+        sm.KQ[KQ_RHS + lane] = rhs_a;   // = packed row 9 of the system: tri(9, j) = 45 + j (lanes >= 9 write the tail)
+        __syncwarp();
         // ---- restoration: Levenberg-Marquardt trials reuse the assembled K while lambda is escalated ---------------------------
         // ---- main phase: one factorisation with inertia correction by delta ----------------------------------------------------
         bool lm_accept = false;
@@ -580,21 +668,31 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             double shift = resto ? S.lm_lambda : 0.0;
             bool ok = false;
             for (int tr = 0; tr < 48; tr++) {
+                // lanes 0..8 own the rows of K, lane 9 the right-hand side (its "row" of the factor is L^-1 rhs).  Branch-free:
+                // every lane runs the column arithmetic (idle lanes on harmless operands), only the stores are predicated,
+                // so the warp reaches each shuffle converged.
                 double Lrow[9];
                 ok = true;
+#ifdef DCBF_DBG
+                S.n_fact++;
+#endif
 #pragma unroll
                 for (int j = 0; j < 9; j++) {
-                    double s_ = 0.0;
-                    if (lane >= j && lane < 9) {
-                        s_ = sm.Kf[tri(lane, j)] + (lane == j ? shift : 0.0);
+                    const bool act = lane >= j && lane < 10;
+                    double s_ = sm.KQ[KQ_K + rowbase + j] + (lane == j ? shift : 0.0);
 #pragma unroll
-                        for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[tri(j, c)], s_);
-                    }
+                    for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[tri(j, c)], s_);
                     const double d = __shfl_sync(FULL, s_, j);
-                    if (!(d > 1e-14)) { ok = false; break; }
+                    if (!(d > 1e-14)) {
+                        ok = false;
+#ifdef DCBF_DBG
+                        S.n_fail++;
+#endif
+                        break;
+                    }
                     const double rinv = drsqrt(d);
                     Lrow[j] = lane == j ? rinv : s_ * rinv;   // diagonal stored as its reciprocal
-                    if (lane >= j && lane < 9) sm.Lf[tri(lane, j)] = Lrow[j];
+                    sm.Lf[act ? rowbase + j : 56 + lane] = Lrow[j];
                     __syncwarp();
                 }
                 if (ok || resto) break;
@@ -608,29 +706,24 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                 continue;
             }
             if (!resto && shift > 0.0) S.delta_last = shift;
-            // triangular solves: lane i holds component i
+            // backward substitution: lane i holds component i, starting from y = L^-1 rhs (row 9 of the factor); branch-free
             {
-                double bi = rhs_a;
-#pragma unroll
-                for (int c = 0; c < 9; c++) {
-                    const double yc = __shfl_sync(FULL, bi * sm.Lf[tri(c, c)], c);   // y_c = b_c / L_cc
-                    if (lane == c) bi = yc;
-                    else if (lane > c && lane < 9) bi = fma(-sm.Lf[tri(lane, c)], yc, bi);
-                }
+                const int li = l8;
+                double bi = sm.Lf[45 + li];
 #pragma unroll
                 for (int c = 8; c >= 0; c--) {
                     const double xc = __shfl_sync(FULL, bi * sm.Lf[tri(c, c)], c);
-                    if (lane == c) bi = xc;
-                    else if (lane < c) bi = fma(-sm.Lf[tri(c, lane)], xc, bi);
+                    const double lc = sm.Lf[tri(c, 0) + (li < c ? li : 0)];
+                    bi = lane == c ? xc : (lane < c ? fma(-lc, xc, bi) : bi);
                 }
-                if (lane < 9) sm.dz[lane] = bi;
+                sm.dz[lane] = bi;
             }
             __syncwarp();
             if (!resto) break;
             // Levenberg-Marquardt trial at full step (violation only)
-            if (lane < 9) sm.zt[lane] = sm.zc[lane] + sm.dz[lane];
+            sm.zt[lane] = sm.zc[l8] + sm.dz[l8];
             __syncwarp();
-            w_nodes<NS>(cs_, sm, sm.zt, lane, 0.0, false);
+            w_nodes<NS>(sm.zt, lane, 0.0, false);
             v2t = 0.0; vmt = 0.0;
 #pragma unroll
             for (int s = 0; s < NS; s++) {
@@ -642,25 +735,28 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                 if (rb[s].has_hi && e.c > rb[s].hi) v = e.c - rb[s].hi;
                 v2t += v * v; vmt = fmax(vmt, fabs(v));
             }
+            __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 v2t += __shfl_xor_sync(FULL, v2t, o);
                 vmt = fmax(vmt, __shfl_xor_sync(FULL, vmt, o));
             }
-            if (v2t < st_v2 * (1.0 - 1e-12)) { lm_accept = true; break; }
+            if (v2t < sm.cold[C_ST_V2] * (1.0 - 1e-12)) { lm_accept = true; break; }
             S.lm_lambda *= 10.0;
             if (S.lm_lambda > 1e12) break;
         }
         if (S.status == -3) break;
         if (resto) {
             if (lm_accept) {
-                double dn = lane < 9 ? fabs(sm.dz[lane]) : 0.0;
-                dn = wmax(dn);
-                if (lane < 9) sm.zc[lane] = sm.zt[lane];
+                const double dn = wmax(fabs(sm.dz[l8]));
+                sm.zc[lane] = sm.zt[lane];
                 S.iters++;
                 S.lm_lambda = fmax(S.lm_lambda * 0.2, 1e-12);
-                if (st_v2 - v2t <= 1e-4 * st_v2) S.acc_cnt++; else S.acc_cnt = 0;
-                if ((dn < 1e-12 || S.acc_cnt >= 2) && vmt > S.resto_target) S.lm_lambda = 1e13;
+                const double v2c = sm.cold[C_ST_V2];
+                if (v2c - v2t <= 1e-4 * v2c) S.acc_cnt++; else S.acc_cnt = 0;
+                const bool crawl = S.nresto >= 2 && S.v2_h2 - v2t <= DCBF_RESTO_WINDOW * S.v2_h2;
+                S.v2_h2 = S.v2_h1; S.v2_h1 = v2c; S.nresto++;
+                if ((dn < 1e-12 || S.acc_cnt >= 2 || crawl) && vmt > sm.cold[C_RESTO_TARGET]) S.lm_lambda = 1e13;
             }
             __syncwarp();
             continue;
@@ -669,14 +765,14 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
         double amax = 1.0, az = 1.0, dphi = 0.0;
         {
             const double tau = fmax(0.99, 1.0 - S.mu);
-            if (lane < 9) dphi = S.sf * grad_a * sm.dz[lane];
+            dphi = S.sf * grad_a * sm.dz[l8];
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 if (rd[s].type == RT_NONE) continue;
                 const int r = s * 32 + lane;
                 double jd = 0.0;
 #pragma unroll
-                for (int a = 0; a < 9; a++) jd = fma(sm.G[r][a], sm.dz[a], jd);
+                for (int a = 0; a < 9; a++) jd = fma(sm.ST[a][r], sm.dz[a], jd);
                 const RowBnd &e = rb[s];
                 const double d = jd + rds[s];
                 rds[s] = d;
@@ -697,6 +793,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                     if (dzu < 0.0) az = fmin(az, ddiv(-tau * rzu[s], dzu));
                 }
             }
+            __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {   // three reductions interleaved
                 amax = fmin(amax, __shfl_xor_sync(FULL, amax, o));
@@ -705,15 +802,18 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             }
         }
         // ---- filter line search -------------------------------------------------------------------------------------------------
-        const double theta = st_theta;
-        const double phi = S.sf * fobj - S.mu * st_logsum;
+        const double theta = sm.cold[C_ST_THETA];
+        const double phi = S.sf * sm.cold[C_OBJ] - S.mu * sm.cold[C_ST_LOGSUM];
         const double eps_phi = 10.0 * 2.2e-16 * fabs(phi);
         double alpha = amax;
         int accepted = 0;
         for (int ls = 0; ls < DCBF_LS_MAX; ls++, alpha *= 0.5) {
-            if (lane < 9) sm.zt[lane] = fma(alpha, sm.dz[lane], sm.zc[lane]);
+            sm.zt[lane] = fma(alpha, sm.dz[l8], sm.zc[l8]);
             __syncwarp();
-            w_nodes<NS>(cs_, sm, sm.zt, lane, S.sf, true);
+#ifdef DCBF_DBG
+            S.n_trial++;
+#endif
+            w_nodes<NS>(sm.zt, lane, S.sf, true);
             const double ft = sm.nobj[1][0] + sm.nobj[2][0] + sm.nobj[3][0];
             double th_t = 0.0, lg_t = 0.0;
             bool okv = true;
@@ -729,6 +829,7 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
                 if (rb[s].has_hi) { const double gap = relax_hi(rb[s].hi) - stv; if (!(gap > 0.0)) okv = false; lp *= gap; }
                 lg_t += dlog(lp);
             }
+            __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 th_t += __shfl_xor_sync(FULL, th_t, o);
@@ -736,12 +837,12 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             }
             okv = __all_sync(FULL, okv);
             const double ph_t = S.sf * ft - S.mu * lg_t;
-            if (!okv || !(ph_t == ph_t) || !(th_t <= S.theta_max)) continue;
+            if (!okv || !(ph_t == ph_t) || !(th_t <= sm.cold[C_THETA_MAX])) continue;
             bool in_filter = false;
-            for (int q = 0; q < S.nf; q++)
-                if (th_t >= sm.filt_th[q] && ph_t >= sm.filt_ph[q]) in_filter = true;
+            for (int qf = 0; qf < S.nf; qf++)
+                if (th_t >= sm.filt_th[qf] && ph_t >= sm.filt_ph[qf]) in_filter = true;
             if (in_filter) continue;
-            const bool sw = dphi < 0.0 && theta <= S.theta_min && switch_cond(alpha, -dphi, theta);
+            const bool sw = dphi < 0.0 && theta <= sm.cold[C_THETA_MIN] && switch_cond(alpha, -dphi, theta);
             if (sw) { if (ph_t <= phi + 1e-8 * alpha * dphi + eps_phi) accepted = 1; }
             else if (th_t <= (1.0 - 1e-5) * theta || ph_t <= phi - 1e-5 * theta + eps_phi) accepted = 2;
             if (accepted) { carry_log = lg_t; break; }
@@ -753,15 +854,16 @@ __device__ void solve_lip_warp(const CtaShared &cs_, WarpShared<NS> &sm, const B
             __syncwarp();
         }
         if (!accepted) {
-            S.phase = PH_RESTO; S.resto_entry = st_vmax; S.resto_target = fmax(0.1 * st_vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0;
+            const double vm = sm.cold[C_ST_VMAX];
+            S.phase = PH_RESTO; sm.cold[C_RESTO_ENTRY] = vm; sm.cold[C_RESTO_TARGET] = fmax(0.1 * vm, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0; S.nresto = 0;
             S.iters++;
             continue;
         }
-        if (lane < 9) sm.zc[lane] = sm.zt[lane];
+        sm.zc[lane] = sm.zt[lane];
         __syncwarp();
         S.alpha = alpha; S.alpha_z = az; S.pending = true;
         nodes_valid = true; carry_ok = true;   // the accepted trial staged the nodes (with Hessian terms) and the barrier sum of the new point
-        if (alpha < 1e-2 && st_vmax > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
+        if (alpha < 1e-2 && sm.cold[C_ST_VMAX] > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
         S.iters++;
     }
     // every exit leaves the loop right after a full pass (or before any trial), so sm.nodes is the rollout of the final iterate
@@ -778,22 +880,20 @@ __device__ __forceinline__ bool w_close(const dcbf_params &P, const WarpShared<N
     return close;
 }
 
-// per-CTA staging of the constants
-__device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K, CtaShared &cs_) {
-    if (threadIdx.x == 0) { cs_.P = P; cs_.K = K; }
-    for (int e = threadIdx.x; e < 72; e += blockDim.x) {
-        if (e < 45) {
-            int a = 0;
-            while ((a + 1) * (a + 2) / 2 <= e) a++;
-            cs_.ea[e] = a; cs_.eb[e] = e - a * (a + 1) / 2;
-        } else {
-            const int t = e - 45;
-            cs_.ea[e] = t % 9; cs_.eb[e] = 1 + t / 9;
-        }
-    }
-    build_T(K, cs_.T);
-    __syncthreads();
+// per-CTA staging of the constants; zeroes the pad columns of the staged rows
+template <int NS>
+__device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K, const WarpTables *tab, int lane) {
+    WarpShared<NS> &sm = g_sm<NS>;
+    if (lane == 0) { g_cs.P = P; g_cs.K = K; g_cs.tab = tab; sm.NHf[NSRC] = 0.0; }
+    for (int t = lane; t < 60; t += 32) (&g_cs.cab[0][0])[t] = __ldg(&tab->cab[0][0] + t);
+    for (int t = lane; t < NHT * 48; t += 32) (&g_cs.hc[0][0])[t] = __ldg(&tab->hc[0][0] + t);
+    for (int t = lane; t < NHT * 48 / 4; t += 32)
+        reinterpret_cast<unsigned *>(&g_cs.hs[0][0])[t] = __ldg(reinterpret_cast<const unsigned *>(&tab->hs[0][0]) + t);
+    for (int t = lane; t < 44; t += 32) sm.ST[t >> 1][32 * NS + (t & 1)] = 0.0;
+    __syncwarp();
 }
+
+#endif  // __CUDACC__
 
 }  // namespace wp
 }  // namespace dcbf

@@ -63,4 +63,8 @@ int hostsim_rollout(const dcbf_params *P, int B, int steps, const double *x0, co
     return 0;
 }
 
+#ifdef DCBF_COUNT
+long hostsim_trials() { return dcbf::g_trials; }
+#endif
+
 }  // extern "C"
