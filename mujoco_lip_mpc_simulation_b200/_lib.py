@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libdcbf_mpc.so")
-SOURCES = ["dcbf_kernels.cu", "dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_warp.cuh"]
+SOURCES = ["dcbf_kernels.cu", "dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_warp.cuh", "dcbf_math.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

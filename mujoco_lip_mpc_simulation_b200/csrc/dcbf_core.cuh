@@ -26,6 +26,7 @@
 #endif
 
 #include "../../include/dcbf_mpc.h"
+#include "dcbf_math.cuh"
 
 #if defined(__CUDACC__)
 #define DCBF_HD __host__ __device__ __forceinline__
@@ -101,17 +102,20 @@ enum { PH_MAIN = 0, PH_RESTO = 1 };
 
 DCBF_HD double dmax(double a, double b) { return a > b ? a : b; }
 DCBF_HD double dmin(double a, double b) { return a < b ? a : b; }
-// Software FP64 routines (sincos, atan2, log, 1/sqrt) are each several hundred SASS instructions; one out-of-line copy
-// keeps the solver body inside the instruction cache (profiles/r01_summary.md: "no_instruction" was the top stall).
-DCBF_MATH void dsincos(double a, double *s, double *c) {
-#if defined(__CUDA_ARCH__)
-    sincos(a, s, c);
+// Elementary functions.  The warp kernels (dcbf_warp.cuh) inline the lean versions of dcbf_math.cuh.  The per-thread kernels keep
+// one out-of-line copy of each routine (they call them from dozens of sites and their register allocation is fragile: the lean
+// versions measured 5-10 % slower there, profiles/r01_summary.md), built on the library functions unless DCBF_LEAN_MATH is set.
+#if defined(DCBF_LEAN_MATH) || !defined(__CUDA_ARCH__)
+DCBF_MATH void dsincos(double a, double *s, double *c) { fsincos(a, s, c); }
+DCBF_MATH double datan2(double y, double x) { return fatan2(y, x); }
+DCBF_MATH double drcp(double x) { return frcp(x); }
+DCBF_MATH double ddiv(double a, double b) { return fdiv(a, b); }
 #else
-    *s = sin(a);
-    *c = cos(a);
-#endif
-}
+DCBF_MATH void dsincos(double a, double *s, double *c) { sincos(a, s, c); }
 DCBF_MATH double datan2(double y, double x) { return atan2(y, x); }
+DCBF_MATH double drcp(double x) { return 1.0 / x; }
+DCBF_MATH double ddiv(double a, double b) { return a / b; }
+#endif
 DCBF_MATH double dlog(double x) { return log(x); }
 DCBF_HD double drsqrt(double x) {
 #if defined(__CUDA_ARCH__)
@@ -120,8 +124,6 @@ DCBF_HD double drsqrt(double x) {
     return 1.0 / sqrt(x);
 #endif
 }
-DCBF_MATH double drcp(double x) { return 1.0 / x; }
-DCBF_MATH double ddiv(double a, double b) { return a / b; }   // ~35 SASS instructions inline; one shared copy instead
 // alpha * a^2.3 > t^1.1 for a > 0, t >= 0 (switching condition of the filter line search) without pow()
 DCBF_HD bool switch_cond(double alpha, double a, double t) {
     if (!(t > 0.0)) return alpha > 0.0;

@@ -367,7 +367,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     // measured on B200 (profiles/r01_summary.md): refill desynchronises the lanes of a warp (different iteration index, phase and
     // line-search depth per lane) and loses 25-30 % against the static assignment -> off unless requested (0: auto, N: batches > N)
     ctx->refill_min_batch = rb ? atoi(rb) : -1;
-    ctx->warp_max_batch = wb ? atoi(wb) : 32768;   // measured crossover on B200 (profiles/r01_summary.md)
+    ctx->warp_max_batch = wb ? atoi(wb) : 0x7fffffff;   // round 2: the warp kernels win at every batch size (profiles/r02_summary.md)
     *out = ctx;
     return DCBF_OK;
 }

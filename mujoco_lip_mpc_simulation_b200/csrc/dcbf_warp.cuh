@@ -295,12 +295,12 @@ __device__ __noinline__ void w_nodes(const double *z, int lane, double sf, bool 
         }
         sm.nodes[kn][0] = x; sm.nodes[kn][1] = y; sm.nodes[kn][2] = vx; sm.nodes[kn][3] = vy; sm.nodes[kn][4] = th;
         double sn, cs;
-        dsincos(th, &sn, &cs);
+        fsincos(th, &sn, &cs);   // inline: interleaves with the atan2 chain below
         const double w = P.w_q + (kn == 1 ? P.w_p : 0.0);
         const double ex = x - sm.goal[0], ey = y - sm.goal[1];
         const double dx = -ex, dy = -ey;
-        const double r2 = dx * dx + dy * dy, ir2 = drcp(r2);
-        const double tar = datan2(dy, dx);
+        const double r2 = dx * dx + dy * dy, ir2 = frcp(r2);
+        const double tar = fatan2(dy, dx);
         const double phi = th - tar;
         sm.trig[kn][0] = sn; sm.trig[kn][1] = cs; sm.trig[kn][2] = tar;
         const double px = -dy * ir2, py = dx * ir2;
@@ -381,7 +381,7 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
             const double dg = (px - gx) * (px - gx) + (py - gy) * (py - gy);
             const double dc = (px - rec[0]) * (px - rec[0]) + (py - rec[1]) * (py - rec[1]);
             if (dc < dg && dc < 9.0 * rec[5]) {
-                const double th = datan2(gy - py, gx - px), al = datan2(rec[1] - py, rec[0] - px);
+                const double th = fatan2(gy - py, gx - px), al = fatan2(rec[1] - py, rec[0] - px);
                 double d = th - al;
                 if (d < 0.0 && fabs(d) > PI) d += 2.0 * PI;
                 else if (d > 0.0 && fabs(d) > PI) d -= 2.0 * PI;
@@ -389,7 +389,7 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                     const double na = d < 0.0 ? th - PI / 12.0 : th + PI / 12.0;
                     const double rad = sqrt(dg);
                     double sn, cs;
-                    dsincos(na, &sn, &cs);
+                    fsincos(na, &sn, &cs);
                     ngx = px + rad * cs; ngy = py + rad * sn; hit = true;
                 }
             }
@@ -463,7 +463,7 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
         }
         if (S.first) {
             const double gmax = wmax(fabs(grad_a));
-            S.sf = gmax > 100.0 ? ddiv(100.0, gmax) : 1.0;
+            S.sf = gmax > 100.0 ? fdiv(100.0, gmax) : 1.0;
             if (lane < 3) {   // the objective Hessian staged above used sf = 1: rescale
 #pragma unroll
                 for (int c = 4; c < 10; c++) sm.nobj[lane + 1][c] *= S.sf;
@@ -503,26 +503,26 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                         rs[s] += S.alpha * rds[s];
                         if (bb.has_lo) {
                             const double gap = rs[s] - lr;
-                            const double mg = ddiv(S.mu, gap);
+                            const double mg = fdiv(S.mu, gap);
                             rzl[s] = fmax(fmin(rzl[s] + S.alpha_z * rel[s], DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
                         }
                         if (bb.has_hi) {
                             const double gap = hr - rs[s];
-                            const double mg = ddiv(S.mu, gap);
+                            const double mg = fdiv(S.mu, gap);
                             rzu[s] = fmax(fmin(rzu[s] + S.alpha_z * reu[s], DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
                         }
                     }
                     const double rc = e.c - rs[s];
                     double lp = 1.0;
                     if (bb.has_lo) {
-                        const double gap = rs[s] - lr, inv = drcp(gap);
+                        const double gap = rs[s] - lr, inv = frcp(gap);
                         sig += rzl[s] * inv; binv += inv; y -= rzl[s];
                         const double cz = gap * rzl[s];
                         t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzl[s];
                         lp *= gap; rel[s] = inv;
                     }
                     if (bb.has_hi) {
-                        const double gap = hr - rs[s], inv = drcp(gap);
+                        const double gap = hr - rs[s], inv = frcp(gap);
                         sig += rzu[s] * inv; binv -= inv; y += rzu[s];
                         const double cz = gap * rzu[s];
                         t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzu[s];
@@ -616,9 +616,9 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
         if (!resto) {
             if (S.first) { sm.cold[C_THETA_MAX] = 1e4 * fmax(1.0, st_theta); sm.cold[C_THETA_MIN] = 1e-4 * fmax(1.0, st_theta); S.first = false; }
             const double dinf = wmax(lane < 9 ? fabs(fma(S.sf, grad_a, q[18 + l8])) : 0.0);
-            const double sd = fmax(100.0, ddiv(2.0 * st_zsum, (double)(nrows + nz))) * 0.01;
-            const double sc = fmax(100.0, ddiv(st_zsum, (double)(nz > 0 ? nz : 1))) * 0.01;
-            const double isd = drcp(sd), isc = drcp(sc);
+            const double sd = fmax(100.0, fdiv(2.0 * st_zsum, (double)(nrows + nz))) * 0.01;
+            const double sc = fmax(100.0, fdiv(st_zsum, (double)(nz > 0 ? nz : 1))) * 0.01;
+            const double isd = frcp(sd), isc = frcp(sc);
             double E0;
             for (;;) {
                 const double compm = fmax(fabs(st_cmax - S.mu), fabs(st_cmin - S.mu));
@@ -781,16 +781,16 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                     const double dzl = S.mu * inv - rzl[s] - rzl[s] * inv * d;
                     rel[s] = dzl;
                     dphi -= S.mu * d * inv;
-                    if (d < 0.0) amax = fmin(amax, ddiv(-tau * gap, d));
-                    if (dzl < 0.0) az = fmin(az, ddiv(-tau * rzl[s], dzl));
+                    if (d < 0.0) amax = fmin(amax, fdiv(-tau * gap, d));
+                    if (dzl < 0.0) az = fmin(az, fdiv(-tau * rzl[s], dzl));
                 }
                 if (e.has_hi) {
                     const double inv = reu[s], gap = relax_hi(e.hi) - rs[s];
                     const double dzu = S.mu * inv - rzu[s] + rzu[s] * inv * d;
                     reu[s] = dzu;
                     dphi += S.mu * d * inv;
-                    if (d > 0.0) amax = fmin(amax, ddiv(tau * gap, d));
-                    if (dzu < 0.0) az = fmin(az, ddiv(-tau * rzu[s], dzu));
+                    if (d > 0.0) amax = fmin(amax, fdiv(tau * gap, d));
+                    if (dzu < 0.0) az = fmin(az, fdiv(-tau * rzu[s], dzu));
                 }
             }
             __syncwarp();

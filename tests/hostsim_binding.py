@@ -30,7 +30,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "hostsim", "libhostsim.so")
-        srcs = [os.path.join(_HERE, "hostsim", "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in ("dcbf_core.cuh", "dcbf_lanes.cuh")]
+        srcs = [os.path.join(_HERE, "hostsim", "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in ("dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_math.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["sh", os.path.join(_HERE, "hostsim", "build.sh")])
         _LIB = C.CDLL(so)
