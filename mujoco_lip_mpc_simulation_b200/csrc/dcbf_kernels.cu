@@ -41,8 +41,11 @@ struct dcbf_ctx {
     int warp_max_batch;
     wp::WarpTables *d_tab;   // constant tables of the warp kernels (dcbf_warp.cuh)
     int *d_counter;          // work counter of the persistent (refill) kernels
+    int *d_order; size_t order_cap;   // size-class split of obstacle-selecting formulations: [counts(2) | small list | large list]
+    cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
     int refill_ctas_lip, refill_ctas_dd;   // resident CTAs of the refill kernels on this device
     int refill_min_batch;
+    int split_classes;   // smallest batch that is split by size class (env DCBF_SPLIT; 0 = never)
 };
 
 #define CK(call)                                                                                        \
@@ -121,6 +124,39 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
 #define DCBF_WARP_GRID_CAP 64   /* CTAs per SM in the grid (grid-stride loop beyond); 0 = one CTA per problem */
 #endif
 
+// Size classes for formulations with obstacle selection (MPC_LIP_modi.py:325-338): the number of rows of a problem is known
+// once its obstacles are selected, and half of the config-3 scenarios fit the 32-row kernel.  One thread per scenario counts the
+// selected obstacles and appends the scenario to the list of its class.
+__global__ void classify_lip_kernel(dcbf_params P, int B, BatchIn in, int small_max_obs, int *__restrict__ counts,
+                                    int *__restrict__ small, int *__restrict__ large) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double px = in.x0[5 * (size_t)b], py = in.x0[5 * (size_t)b + 1];
+    const int fld = in.field ? in.field[b] : 0;
+    const double *cir = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC;
+    const double *elp = in.elp_rec + (size_t)fld * in.Ke * DCBF_ELP_REC;
+    int ks = 0;
+    for (int j = 0; j < in.Kc; j++) {
+        const double *o = cir + DCBF_CIR_REC * j;
+        if ((px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]) - o[2] <= P.detect_sq) ks++;
+    }
+    for (int j = 0; j < in.Ke; j++) {
+        const double *o = elp + DCBF_ELP_REC * j;
+        if ((px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]) - o[6] <= P.detect_sq) ks++;
+    }
+    const bool is_small = ks <= small_max_obs;
+    // warp-aggregated append
+    const unsigned act = __activemask();
+    const unsigned ms = __ballot_sync(act, is_small), ml = act & ~ms;
+    const int lane = threadIdx.x & 31;
+    const unsigned mine = is_small ? ms : ml;
+    const int leader = __ffs(mine) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counts[is_small ? 0 : 1], __popc(mine));
+    base = __shfl_sync(mine, base, leader);
+    (is_small ? small : large)[base + __popc(mine & ((1u << lane) - 1u))] = b;
+}
+
 // lane 0 stages the scenario state, the start point z0 (from the reference's u0) and the free response of the LIP
 // (positions / velocities at nodes 1..3 for zero foot placements) in shared memory
 template <int NS>
@@ -146,12 +182,18 @@ __device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<NS
 }
 
 template <int NS>
-__global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out) {
+__global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out,
+                                                                                       const int *__restrict__ order, const int *__restrict__ count) {
     wp::WarpShared<NS> &sm = wp::g_sm<NS>;
     const wp::CtaShared &cs_ = wp::g_cs;
     const int lane = wp::lane_id();
+    // with an index list (size-class split, see classify_lip_kernel) the grid covers the whole batch and the CTAs beyond the
+    // list's length leave at once
+    const int n = count ? *count : B;
+    if ((int)blockIdx.x >= n) return;
     wp::stage_cta<NS>(P, K, tab, lane);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int i_ = blockIdx.x; i_ < n; i_ += gridDim.x) {
+        const int b = order ? order[i_] : i_;
         if (lane == 0) {
             double x0[5], u0[15], g[2];
 #pragma unroll
@@ -278,14 +320,42 @@ static int warp_slots(const dcbf_ctx *ctx) {
     return m <= 32 ? 1 : (m <= 64 ? 2 : 4);
 }
 template <int NS>
-static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
+static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st, const int *order = nullptr,
+                             const int *count = nullptr) {
     int grid = B;
     const int cap = ctx->sm_count * DCBF_WARP_GRID_CAP;
-    if (cap > 0 && grid > cap) grid = cap;
-    solve_lip_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out);
+    if (!order && cap > 0 && grid > cap) grid = cap;
+    solve_lip_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, count);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
+
+// obstacle-selecting formulations: split the batch by row count and run the 32-row kernel and the NS-slot kernel side by side
+template <int NS>
+static int launch_solve_split(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
+    if (ctx->order_cap < (size_t)B) {
+        CK(cudaFree(ctx->d_order));
+        ctx->d_order = nullptr; ctx->order_cap = 0;
+        CK(cudaMalloc(&ctx->d_order, sizeof(int) * (2 * (size_t)B + 2)));
+        ctx->order_cap = (size_t)B;
+    }
+    int *counts = ctx->d_order, *small = ctx->d_order + 2, *large = small + ctx->order_cap;
+    const int small_max_obs = 32 / 3 - (ctx->P.has_fen ? 6 : 4);
+    CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
+    classify_lip_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->P, B, in, small_max_obs, counts, small, large);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    int rc = launch_solve_warp<NS>(ctx, B, in, out, st, large, counts + 1);          // the long problems first
+    if (rc != DCBF_OK) return rc;
+    rc = launch_solve_warp<1>(ctx, B, in, out, ctx->aux_stream, small, counts);
+    if (rc != DCBF_OK) return rc;
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    ctx->launches += 2;
+    return DCBF_OK;
+}
+
 template <int NS>
 static int launch_rollout_warp(dcbf_ctx *ctx, int B, int steps, const BatchIn &in, const RolloutOut &out, cudaStream_t st) {
     int grid = B;
@@ -367,6 +437,9 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     // measured on B200 (profiles/r01_summary.md): refill desynchronises the lanes of a warp (different iteration index, phase and
     // line-search depth per lane) and loses 25-30 % against the static assignment -> off unless requested (0: auto, N: batches > N)
     ctx->refill_min_batch = rb ? atoi(rb) : -1;
+    { const char *sp = getenv("DCBF_SPLIT"); ctx->split_classes = sp ? atoi(sp) : 16384; }
+    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     ctx->warp_max_batch = wb ? atoi(wb) : 0x7fffffff;   // round 2: the warp kernels win at every batch size (profiles/r02_summary.md)
     *out = ctx;
     return DCBF_OK;
@@ -375,9 +448,12 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
 void dcbf_destroy(dcbf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
+    cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); cudaFree(ctx->d_order); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 
@@ -458,7 +534,10 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
     else if (dd) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
     else if (use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);
-        const int rc = ns == 1 ? launch_solve_warp<1>(ctx, B, in, out, st) : (ns == 2 ? launch_solve_warp<2>(ctx, B, in, out, st) : launch_solve_warp<4>(ctx, B, in, out, st));
+        const bool split = ns > 1 && ctx->P.select_obs && ctx->split_classes > 0 && B >= ctx->split_classes;   // measured: pays from ~16 k scenarios
+        const int rc = ns == 1 ? launch_solve_warp<1>(ctx, B, in, out, st)
+                     : split ? (ns == 2 ? launch_solve_split<2>(ctx, B, in, out, st) : launch_solve_split<4>(ctx, B, in, out, st))
+                             : (ns == 2 ? launch_solve_warp<2>(ctx, B, in, out, st) : launch_solve_warp<4>(ctx, B, in, out, st));
         if (rc != DCBF_OK) return rc;
     }
     else solve_lip_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);

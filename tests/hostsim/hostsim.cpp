@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../mujoco_lip_mpc_simulation_b200/csrc/dcbf_lanes.cuh"
+#include "../../mujoco_lip_mpc_simulation_b200/csrc/dcbf_warp.cuh"   // host part only: the constant tables of the warp kernels
 
 using namespace dcbf;
 
@@ -60,6 +61,26 @@ int hostsim_rollout(const dcbf_params *P, int B, int steps, const double *x0, co
     BatchIn in = {x0, goal, nullptr, nullptr, leg, field, cr.data(), er.data(), Kc, Ke};
     RolloutOut out = {x_final, traj, steps_done, n_infeasible, total_iters};
     for (int b = 0; b < B; b++) rollout_lip_lane(*P, K, in, out, steps, b);
+    return 0;
+}
+
+// lean elementary functions of the kernels (dcbf_math.cuh), evaluated on the host for the accuracy test
+int hostsim_math(int n, const double *a, double *sn, double *cs, const double *y, const double *x, double *at) {
+    for (int i = 0; i < n; i++) { fsincos(a[i], sn + i, cs + i); at[i] = fatan2(y[i], x[i]); }
+    return 0;
+}
+
+// constant tables of the warp kernels + the dense feature map they are derived from
+int hostsim_warp_tables(int *desc, double *hc, int *hs, double *cab, double *T) {
+    const Consts K = make_consts();
+    wp::WarpTables W;
+    if (!wp::build_warp_tables(K, W)) return -1;
+    for (int t = 0; t < 96; t++) desc[t] = W.desc[t];
+    for (int t = 0; t < wp::NHT; t++) for (int e = 0; e < 48; e++) { hc[48 * t + e] = W.hc[t][e]; hs[48 * t + e] = W.hs[t][e]; }
+    for (int c = 0; c < 10; c++) for (int j = 0; j < 6; j++) cab[6 * c + j] = W.cab[c][j];
+    double Tm[24][9];
+    wp::build_feature_map(K, Tm);
+    for (int f = 0; f < 24; f++) for (int v = 0; v < 9; v++) T[9 * f + v] = Tm[f][v];
     return 0;
 }
 

@@ -30,7 +30,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "hostsim", "libhostsim.so")
-        srcs = [os.path.join(_HERE, "hostsim", "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in ("dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_math.cuh")]
+        srcs = [os.path.join(_HERE, "hostsim", "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in ("dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_math.cuh", "dcbf_warp.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["sh", os.path.join(_HERE, "hostsim", "build.sh")])
         _LIB = C.CDLL(so)
@@ -129,3 +129,21 @@ def rollout(P, steps, x0, goal, leg, cir, elp, field=None):
     lib().hostsim_rollout(C.byref(P), B, steps, _p(x0), _p(goal), _p(leg, C.c_int32), _p(field, C.c_int32), F, cir.shape[1],
                           _p(cir), elp.shape[1], _p(elp), _p(xf), _p(sd, C.c_int32), _p(ni, C.c_int32), _p(ti, C.c_int32), _p(traj))
     return dict(x_final=xf, steps_done=sd, n_infeasible=ni, total_iters=ti, traj=traj)
+
+
+def lean_math(a, y, x):
+    """fsincos / fatan2 of csrc/dcbf_math.cuh evaluated on the host."""
+    a, y, x = _d(a).ravel(), _d(y).ravel(), _d(x).ravel()
+    n = len(a)
+    sn, cs, at = np.zeros(n), np.zeros(n), np.zeros(n)
+    lib().hostsim_math(n, _p(a), _p(sn), _p(cs), _p(y), _p(x), _p(at))
+    return sn, cs, at
+
+
+def warp_tables():
+    """Constant tables of the warp kernels (csrc/dcbf_warp.cuh: build_warp_tables) and the dense feature map."""
+    desc, hs = np.zeros(96, np.int32), np.zeros((6, 48), np.int32)
+    hc, cab, T = np.zeros((6, 48)), np.zeros((10, 6)), np.zeros((24, 9))
+    rc = lib().hostsim_warp_tables(_p(desc, C.c_int32), _p(hc), _p(hs, C.c_int32), _p(cab), _p(T))
+    assert rc == 0
+    return dict(desc=desc, hc=hc, hs=hs, cab=cab, T=T)
