@@ -17,6 +17,10 @@
  *                            MPC_DD_sig_step.py:70-99,123-193) i.e. the cyipopt.Problem(...).solve(u0) call
  *   dcbf_rollout         <- the plan -> apply -> re-plan loop of MPC_LIP_sig_step.py:565-575
  *   dcbf_solve_host      <- same as dcbf_solve for callers that hold host (numpy) buffers
+ *   dcbf_tick            <- one control tick of Logger.gen_nex_foot_input (data_procs/logger_mpc.py:318-341):
+ *                           LIP prediction to the end of the running step (MPCCBF.get_next_states,
+ *                           MPC_LIP_modi.py:149-178), the warm-start rule, the re-plan, and the dense plan trajectory
+ *                           pos_det of gen_control_test (MPC_LIP_modi.py:117-122, xk_track_det :304-322)
  *
  * Conventions
  *   - all floating point data is FP64, row-major, densely packed; index data is int32
@@ -39,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DCBF_ABI_VERSION 1
+#define DCBF_ABI_VERSION 2
 #define DCBF_MAX_OBS 16 /* circles and ellipses each, per field */
 
 enum dcbf_formulation { DCBF_SIG_STEP = 0, DCBF_MODI = 1, DCBF_DD = 2 };
@@ -115,6 +119,22 @@ int dcbf_set_fields_host(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir
 int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg,
                     const int32_t *field, const double *warm, const double *last_u, double *u, double *x_plan,
                     double *p_plan, int32_t *status, int32_t *iters, double *obj, double *viol, uint8_t *close2goal);
+
+/* One control tick per scenario (LIP formulations), everything on the device:
+ *   x_next = A(t_rest) [pos, vel, hd] + B(t_rest) glo_p          LIP flow to the end of the running step; the heading row
+ *                                                               of B is t_rest / dt (MPC_LIP_modi.py:149-178)
+ *   warm   = prev_plan verbatim (mode 0), shifted [x_2, x_3, x_3] (mode 1: first tick of a step, logger_mpc.py:329-331)
+ *            or [x_next, x_next, x_next] (mode 2: no previous plan, logger_mpc.py:326-327); mode NULL => 2 everywhere
+ *   re-plan from x_next with the swing leg's sign leg[B] (the caller passes -leg_ind like logger_mpc.py:336)
+ *   pos_det[B][126][2]: per planned step the start position and the LIP flow at t = 0, 0.01, ..., 0.40 s
+ * Inputs: glo_pos[B][2], glo_vel[B][2], glo_hd[B], glo_p[B][3] = (stance foot x, y, heading input), t_rest[B],
+ * goal[B][2], leg[B], field[B]|NULL, prev_plan[B][15]|NULL, mode[B]|NULL.  Outputs (any may be NULL): x_next[B][5],
+ * warm[B][15] (the start vector that was used), then the outputs of dcbf_solve, then pos_det. */
+int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo_vel, const double *glo_hd,
+              const double *glo_p, const double *t_rest, const double *goal, const int32_t *leg, const int32_t *field,
+              const double *prev_plan, const uint8_t *mode, double *x_next, double *warm, double *u, double *x_plan,
+              double *p_plan, int32_t *status, int32_t *iters, double *obj, double *viol, uint8_t *close2goal,
+              double *pos_det, void *stream);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t dcbf_launch_count(const dcbf_ctx *ctx);

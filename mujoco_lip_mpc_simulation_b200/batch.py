@@ -200,6 +200,45 @@ class DcbfSolver:
         self._check(rc, "dcbf_rollout")
         return dict(x_final=xf, steps_done=sd, n_infeasible=ni, total_iters=ti, traj=traj)
 
+    def tick(self, glo_pos, glo_vel, glo_hd, glo_p, t_rest, goal, leg, prev_plan=None, mode=None, field=None, want_pos_det=True):
+        """One control tick per scenario on the device (dcbf_tick): LIP prediction to the end of the running step
+        (MPCCBF.get_next_states), warm start from the previous plan (mode 0 verbatim, 1 shifted, 2 / no previous plan:
+        [x_next] * 3 -- data_procs/logger_mpc.py:326-333), re-plan, dense plan trajectory pos_det [B,126,2]."""
+        assert not self.dd, "the tick path belongs to the LIP formulations"
+        pos = self._dev(glo_pos, torch.float64).reshape(-1, 2)
+        B = pos.shape[0]
+        vel = self._dev(glo_vel, torch.float64).reshape(B, 2)
+        hd = self._dev(glo_hd, torch.float64).reshape(B)
+        gp = self._dev(glo_p, torch.float64).reshape(B, 3)
+        tr = self._dev(t_rest, torch.float64).reshape(-1)
+        if tr.shape[0] != B:
+            tr = tr.expand(B).contiguous()
+        _, _, goal, leg, field, _ = self._inputs(torch.zeros((B, 5), dtype=torch.float64, device=self.tdev), goal, leg, field, None)
+        prev = None if prev_plan is None else self._dev(prev_plan, torch.float64).reshape(B, 15)
+        md = None if (mode is None or prev is None) else self._dev(mode, torch.uint8).reshape(-1)
+        if md is not None and md.shape[0] != B:
+            md = md.expand(B).contiguous()
+        if prev is not None and md is None:
+            md = torch.zeros(B, dtype=torch.uint8, device=self.tdev)
+        kw = dict(device=self.tdev)
+        xn = torch.empty((B, 5), dtype=torch.float64, **kw)
+        warm = torch.empty((B, 15), dtype=torch.float64, **kw)
+        u = torch.empty((B, 15), dtype=torch.float64, **kw)
+        xp = torch.empty((B, 3, 5), dtype=torch.float64, **kw)
+        pp = torch.empty((B, 3, 3), dtype=torch.float64, **kw)
+        st = torch.empty(B, dtype=torch.int32, **kw)
+        it = torch.empty(B, dtype=torch.int32, **kw)
+        obj = torch.empty(B, dtype=torch.float64, **kw)
+        viol = torch.empty(B, dtype=torch.float64, **kw)
+        cl = torch.empty(B, dtype=torch.uint8, **kw)
+        pd = torch.empty((B, 126, 2), dtype=torch.float64, **kw) if want_pos_det else None
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_tick(self._ctx, B, _ptr(pos), _ptr(vel), _ptr(hd), _ptr(gp), _ptr(tr), _ptr(goal), _ptr(leg), _ptr(field),
+                                    _ptr(prev), _ptr(md), _ptr(xn), _ptr(warm), _ptr(u), _ptr(xp), _ptr(pp), _ptr(st), _ptr(it),
+                                    _ptr(obj), _ptr(viol), _ptr(cl), _ptr(pd), self._stream())
+        self._check(rc, "dcbf_tick")
+        return dict(x_next=xn, warm=warm, plan=SolveResult(u, xp, pp, st, it, obj, viol, cl.bool()), pos_det=pd)
+
     # ------------------------------------------------------------------------------------------------------
     def set_fields_host(self, cir, elp=None):
         cir = np.ascontiguousarray(np.zeros((1, 0, 3)) if cir is None else cir, dtype=np.float64)

@@ -41,6 +41,8 @@ struct dcbf_ctx {
     int warp_max_batch;
     wp::WarpTables *d_tab;   // constant tables of the warp kernels (dcbf_warp.cuh)
     int *d_counter;          // work counter of the persistent (refill) kernels
+    double *d_tick; size_t tick_cap;   // scratch of dcbf_tick: [x_next | warm | x_plan | p_plan] when the caller passes NULL
+    double *d_flow;                    // cosh / sinh table of pos_det_kernel (2 x 41)
     int *d_order; size_t order_cap;   // size-class split of obstacle-selecting formulations: [counts(2) | small list | large list]
     cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
     int refill_ctas_lip, refill_ctas_dd;   // resident CTAs of the refill kernels on this device
@@ -297,6 +299,55 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_k
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// control tick: prediction + warm-start bookkeeping in front of the solve, dense plan trajectory behind it
+// ---------------------------------------------------------------------------------------------------------------
+// one thread per scenario: x_next (MPC_LIP_modi.py:149-178) and the start vector of the re-plan (logger_mpc.py:326-333)
+__global__ void tick_prepare_kernel(int B, double beta, double dt, const double *__restrict__ pos, const double *__restrict__ vel,
+                                    const double *__restrict__ hd, const double *__restrict__ gp, const double *__restrict__ t_rest,
+                                    const double *__restrict__ prev, const uint8_t *__restrict__ mode, double *__restrict__ x_next,
+                                    double *__restrict__ warm) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double t = t_rest[b];
+    const double c = cosh(beta * t), s = sinh(beta * t);
+    const double px = pos[2 * (size_t)b], py = pos[2 * (size_t)b + 1], vx = vel[2 * (size_t)b], vy = vel[2 * (size_t)b + 1];
+    const double fx = gp[3 * (size_t)b], fy = gp[3 * (size_t)b + 1], fh = gp[3 * (size_t)b + 2];
+    double xn[5];
+    xn[0] = c * px + (s / beta) * vx + (1.0 - c) * fx;
+    xn[1] = c * py + (s / beta) * vy + (1.0 - c) * fy;
+    xn[2] = (s * beta) * px + c * vx - (s * beta) * fx;
+    xn[3] = (s * beta) * py + c * vy - (s * beta) * fy;
+    xn[4] = hd[b] + (t * (1.0 / dt)) * fh;
+#pragma unroll
+    for (int i = 0; i < 5; i++) x_next[5 * (size_t)b + i] = xn[i];
+    const int md = (mode && prev) ? mode[b] : 2;
+    for (int k = 0; k < 3; k++) {
+        const int src = md == 1 ? (k < 2 ? k + 1 : 2) : k;
+#pragma unroll
+        for (int i = 0; i < 5; i++) warm[15 * (size_t)b + 5 * k + i] = md == 2 ? xn[i] : prev[15 * (size_t)b + 5 * src + i];
+    }
+}
+
+// one thread per (scenario, sample): pos_det[b][42 j + r] of gen_control_test (MPC_LIP_modi.py:117-122, 304-322); ch[i] =
+// cosh(beta t_i), sb[i] = sinh(beta t_i) / beta for t_i = 0.01 i, i = 0..40 (host-built table)
+__global__ void pos_det_kernel(int B, const double *__restrict__ ch, const double *__restrict__ sb, const double *__restrict__ x0,
+                               const double *__restrict__ x_plan, const double *__restrict__ p_plan, double *__restrict__ pos_det) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)B * 126) return;
+    const size_t b = t / 126;
+    const int q = (int)(t - b * 126), j = q / 42, r = q - 42 * j;
+    const double *st = j == 0 ? x0 + 5 * b : x_plan + 15 * b + 5 * (j - 1);
+    const double *p = p_plan + 9 * b + 3 * j;
+    double ox = st[0], oy = st[1];
+    if (r > 0) {
+        const double c = ch[r - 1], s = sb[r - 1];
+        ox = c * st[0] + s * st[2] + (1.0 - c) * p[0];
+        oy = c * st[1] + s * st[3] + (1.0 - c) * p[1];
+    }
+    reinterpret_cast<double2 *>(pos_det)[t] = make_double2(ox, oy);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // FP64 peak microbenchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
@@ -448,7 +499,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
 void dcbf_destroy(dcbf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); cudaFree(ctx->d_order); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
+    cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); cudaFree(ctx->d_order); cudaFree(ctx->d_tick); cudaFree(ctx->d_flow); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -543,6 +594,54 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
     else solve_lip_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
     CK(cudaGetLastError());
     ctx->launches++;
+    return DCBF_OK;
+}
+
+int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo_vel, const double *glo_hd, const double *glo_p,
+              const double *t_rest, const double *goal, const int32_t *leg, const int32_t *field, const double *prev_plan,
+              const uint8_t *mode, double *x_next, double *warm, double *u, double *x_plan, double *p_plan, int32_t *status,
+              int32_t *iters, double *obj, double *viol, uint8_t *close2goal, double *pos_det, void *stream) {
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
+    if (B == 0) return DCBF_OK;
+    if (ctx->P.formulation == DCBF_DD) return DCBF_ERR_ARG;
+    if (!glo_pos || !glo_vel || !glo_hd || !glo_p || !t_rest || !goal) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t b = (size_t)B;
+    if (ctx->tick_cap < b) {   // scratch for the intermediates the caller does not want back
+        CK(cudaFree(ctx->d_tick));
+        ctx->d_tick = nullptr; ctx->tick_cap = 0;
+        CK(cudaMalloc(&ctx->d_tick, sizeof(double) * (5 + 15 + 15 + 9) * b));
+        ctx->tick_cap = b;
+    }
+    if (!ctx->d_flow) {
+        double tab[82];
+        const double beta = sqrt(9.81 / 1.0);
+        for (int i = 0; i < 41; i++) {
+            const double t = (double)i * 0.01;   // numpy.arange(0, dt + 0.01, 0.01)[i]
+            tab[i] = cosh(beta * t); tab[41 + i] = sinh(beta * t) / beta;
+        }
+        CK(cudaMalloc(&ctx->d_flow, sizeof(tab)));
+        CK(cudaMemcpyAsync(ctx->d_flow, tab, sizeof(tab), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // tab lives on this stack frame
+    }
+    double *xn = x_next ? x_next : ctx->d_tick;
+    double *wm = warm ? warm : ctx->d_tick + 5 * ctx->tick_cap;
+    double *xp = x_plan ? x_plan : ctx->d_tick + 20 * ctx->tick_cap;
+    double *pp = p_plan ? p_plan : ctx->d_tick + 35 * ctx->tick_cap;
+    tick_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, sqrt(9.81 / 1.0), ctx->K.dt, glo_pos, glo_vel, glo_hd, glo_p, t_rest, prev_plan,
+                                                        mode, xn, wm);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    const int rc = dcbf_solve(ctx, B, xn, goal, leg, field, wm, nullptr, u, xp, pp, status, iters, obj, viol, close2goal, stream);
+    if (rc != DCBF_OK) return rc;
+    if (pos_det) {
+        const size_t n = b * 126;
+        pos_det_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(B, ctx->d_flow, ctx->d_flow + 41, xn, xp, pp, pos_det);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
     return DCBF_OK;
 }
 

@@ -1,0 +1,78 @@
+"""GPU tests of the control-tick path (dcbf_tick): the prediction, the warm-start rule and the dense plan trajectory are
+checked against the host restatements that tests/test_helpers_cpu.py pins to golden vectors of the reference classes
+(_lipmodel.flow_matrices / track_det <- MPCCBF.get_next_states / xk_track_det), and the re-plan inside the tick must be the
+very solve dcbf_solve performs on the same inputs."""
+import numpy as np
+import pytest
+import torch
+
+from mujoco_lip_mpc_simulation_b200 import _lipmodel, scenarios
+from mujoco_lip_mpc_simulation_b200.batch import DcbfSolver
+
+pytestmark = pytest.mark.gpu
+
+
+def _state_before_step_end(sc, t_rest, rng):
+    """current (pos, vel, hd, stance foot) such that the LIP flow over t_rest is well defined: take the scenario state as the
+    present and a stance foot near the body"""
+    B = len(sc.x0)
+    pos, vel, hd = sc.x0[:, 0:2].copy(), sc.x0[:, 2:4].copy(), sc.x0[:, 4].copy()
+    gp = np.concatenate([pos + rng.normal(scale=0.05, size=(B, 2)), rng.uniform(-0.1, 0.1, size=(B, 1))], axis=1)
+    return pos, vel, hd, gp
+
+
+@pytest.mark.parametrize("form", ["sig_step", "modi"])
+def test_tick_matches_host_restatement_and_plain_solve(form):
+    rng = np.random.default_rng(5)
+    B = 192
+    sc = scenarios.make_batch(form, B, seed=21)
+    s = DcbfSolver(form, device=0)
+    s.set_fields(sc.cir, sc.elp if sc.elp.shape[1] else None)
+    t_rest = rng.uniform(0.0, 0.4, size=B)
+    t_rest[:4] = [0.0, 0.4, 0.25, 0.01]
+    pos, vel, hd, gp = _state_before_step_end(sc, t_rest, rng)
+    prev = rng.normal(size=(B, 15)) * 0.1 + np.tile(sc.x0, (1, 3))
+    mode = rng.integers(0, 3, size=B).astype(np.uint8)
+    out = s.tick(pos, vel, hd, gp, t_rest, sc.goal, -sc.leg, prev_plan=prev, mode=mode, field=sc.field)
+    torch.cuda.synchronize()
+    xn = out["x_next"].cpu().numpy()
+    warm = out["warm"].cpu().numpy()
+    # prediction: A(t) x + B(t) p with the heading gain t / dt
+    for b in range(B):
+        A, Bm = _lipmodel.flow_matrices(float(t_rest[b]), float(t_rest[b]) * (1.0 / 0.4))
+        ref = A @ np.concatenate([pos[b], vel[b], [hd[b]]]) + Bm @ gp[b]
+        np.testing.assert_allclose(xn[b], ref, rtol=0, atol=2e-13)
+    # warm-start rule of data_procs/logger_mpc.py:326-333
+    for b in range(B):
+        p3 = prev[b].reshape(3, 5)
+        want = {0: p3, 1: np.stack([p3[1], p3[2], p3[2]]), 2: np.stack([xn[b]] * 3)}[int(mode[b])]
+        np.testing.assert_array_equal(warm[b].reshape(3, 5), want)
+    # the re-plan is the plain solve on (x_next, warm)
+    ref = s.solve(xn, sc.goal, -sc.leg, warm, field=sc.field)
+    torch.cuda.synchronize()
+    assert torch.equal(out["plan"].status, ref.status) and torch.equal(out["plan"].iters, ref.iters)
+    assert torch.equal(out["plan"].p_plan, ref.p_plan) and torch.equal(out["plan"].x_plan, ref.x_plan)
+    # dense plan trajectory: three segments of 1 + 41 samples (MPC_LIP_modi.py:117-122)
+    pd = out["pos_det"].cpu().numpy()
+    xp, pp = ref.x_plan.cpu().numpy(), ref.p_plan.cpu().numpy()
+    for b in range(0, B, 7):
+        starts = [xn[b], xp[b, 0], xp[b, 1]]
+        want = np.concatenate([_lipmodel.track_det(starts[j], pp[b, j], 0.4) for j in range(3)])
+        assert want.shape == (126, 2)
+        np.testing.assert_allclose(pd[b], want, rtol=0, atol=5e-13)
+
+
+def test_tick_without_previous_plan_is_a_cold_start():
+    sc = scenarios.make_batch("modi", 64, seed=22)
+    s = DcbfSolver("modi", device=0)
+    s.set_fields(sc.cir, sc.elp)
+    z2, z1 = np.zeros((64, 2)), np.zeros(64)
+    # t_rest = 0: the prediction is the state itself and the cold start is [x, x, x] -> same as the plain cold solve
+    out = s.tick(sc.x0[:, 0:2], sc.x0[:, 2:4], sc.x0[:, 4], np.zeros((64, 3)), z1, sc.goal, sc.leg, field=sc.field, want_pos_det=False)
+    ref = s.solve(sc.x0, sc.goal, sc.leg, np.tile(sc.x0, (1, 3)), field=sc.field)
+    torch.cuda.synchronize()
+    assert out["pos_det"] is None
+    np.testing.assert_allclose(out["x_next"].cpu().numpy(), sc.x0, rtol=0, atol=1e-15)
+    assert torch.equal(out["plan"].status, ref.status)
+    assert torch.allclose(out["plan"].p_plan, ref.p_plan, rtol=0, atol=1e-9)
+    del z2
