@@ -162,7 +162,7 @@ __global__ void classify_lip_kernel(dcbf_params P, int B, BatchIn in, int small_
 // lane 0 stages the scenario state, the start point z0 (from the reference's u0) and the free response of the LIP
 // (positions / velocities at nodes 1..3 for zero foot placements) in shared memory
 template <int NS>
-__device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<NS> &sm, const double *x0, const double *graw, const double *u0, int lane) {
+__device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<wp::LipW, NS> &sm, const double *x0, const double *graw, const double *u0, int lane) {
     if (lane == 0) {
         double z[9];
         lip_z_from_u(K, x0, u0, z);
@@ -174,7 +174,7 @@ __device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<NS
         double x = x0[0], y = x0[1], vx = x0[2], vy = x0[3];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            sm.fr[k][0] = x; sm.fr[k][1] = y; sm.fr[k][2] = vx; sm.fr[k][3] = vy;
+            sm.nd.fr[k][0] = x; sm.nd.fr[k][1] = y; sm.nd.fr[k][2] = vx; sm.nd.fr[k][3] = vy;
             const double xn = K.C * x + K.Sb * vx, yn = K.C * y + K.Sb * vy;
             vx = K.bS * x + K.C * vx; vy = K.bS * y + K.C * vy;
             x = xn; y = yn;
@@ -186,14 +186,14 @@ __device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<NS
 template <int NS>
 __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out,
                                                                                        const int *__restrict__ order, const int *__restrict__ count) {
-    wp::WarpShared<NS> &sm = wp::g_sm<NS>;
+    wp::WarpShared<wp::LipW, NS> &sm = wp::g_sm<wp::LipW, NS>;
     const wp::CtaShared &cs_ = wp::g_cs;
     const int lane = wp::lane_id();
     // with an index list (size-class split, see classify_lip_kernel) the grid covers the whole batch and the CTAs beyond the
     // list's length leave at once
     const int n = count ? *count : B;
     if ((int)blockIdx.x >= n) return;
-    wp::stage_cta<NS>(P, K, tab, lane);
+    wp::stage_cta<wp::LipW, NS>(P, K, tab, lane);
     for (int i_ = blockIdx.x; i_ < n; i_ += gridDim.x) {
         const int b = order ? order[i_] : i_;
         if (lane == 0) {
@@ -209,10 +209,10 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_ker
         }
         const int leg = in.leg ? in.leg[b] : 1;
         wp::WState S;
-        wp::solve_lip_warp<NS>(in, b, lane, leg, S);
+        wp::solve_warp<wp::LipW, NS>(in, b, lane, leg, S);
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
         if (lane < 15) {
-            const double v = sm.nodes[lane / 5 + 1][lane % 5];
+            const double v = sm.nd.nodes[lane / 5 + 1][lane % 5];
             if (out.u) out.u[15 * (size_t)b + lane] = v;
             if (out.x_plan) out.x_plan[15 * (size_t)b + lane] = v;
         }
@@ -236,12 +236,43 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_ker
     }
 }
 
+// differential-drive formulation, one problem per warp (wp::DdW): same driver, 6 variables, node Jacobians per iterate
 template <int NS>
-__global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, int steps, BatchIn in, RolloutOut out) {
-    wp::WarpShared<NS> &sm = wp::g_sm<NS>;
+__global__ void __launch_bounds__(32, 12) solve_dd_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out) {
+    wp::WarpShared<wp::DdW, NS> &sm = wp::g_sm<wp::DdW, NS>;
     const wp::CtaShared &cs_ = wp::g_cs;
     const int lane = wp::lane_id();
-    wp::stage_cta<NS>(P, K, tab, lane);
+    wp::stage_cta<wp::DdW, NS>(P, K, tab, lane);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        if (lane < 3) sm.x0[lane] = in.x0[3 * (size_t)b + lane];
+        if (lane >= 8 && lane < 10) { sm.graw[lane - 8] = in.goal[2 * (size_t)b + lane - 8]; sm.nd.last_u[lane - 8] = in.last_u ? in.last_u[2 * (size_t)b + lane - 8] : 0.0; }
+        if (lane >= 16 && lane < 22) sm.zc[lane - 16] = in.warm[6 * (size_t)b + lane - 16];
+        __syncwarp();
+        wp::WState S;
+        wp::solve_warp<wp::DdW, NS>(in, b, lane, 1, S);
+        // ---- outputs: plan re-roll of gen_dd_control (MPC_DD_sig_step.py:83-99) = the staged nodes of the final iterate ------
+        if (lane < 9 && out.x_plan) out.x_plan[9 * (size_t)b + lane] = sm.nd.nodes[lane / 3 + 1][lane % 3];
+        if (lane < 6 && out.u) out.u[6 * (size_t)b + lane] = sm.zc[lane];
+        if (lane == 0) {
+            if (out.status) out.status[b] = S.status;
+            if (out.iters) out.iters[b] = S.iters;
+            if (out.obj) out.obj[b] = sm.cold[wp::C_OBJ];
+            if (out.viol) out.viol[b] = sm.cold[wp::C_VIOL];
+            if (out.close) {
+                const double dxg = sm.nd.nodes[1][0] - sm.graw[0], dyg = sm.nd.nodes[1][1] - sm.graw[1];
+                out.close[b] = sqrt(dxg * dxg + dyg * dyg) <= cs_.P.close_radius ? 1 : 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, int steps, BatchIn in, RolloutOut out) {
+    wp::WarpShared<wp::LipW, NS> &sm = wp::g_sm<wp::LipW, NS>;
+    const wp::CtaShared &cs_ = wp::g_cs;
+    const int lane = wp::lane_id();
+    wp::stage_cta<wp::LipW, NS>(P, K, tab, lane);
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         int leg = in.leg ? in.leg[b] : 1;
         if (lane == 0) {
@@ -258,13 +289,13 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_k
         int done = 0, ninf = 0, tot = 0;
         for (int st = 0; st < steps; st++) {
             wp::WState S;
-            wp::solve_lip_warp<NS>(in, b, lane, leg, S);
+            wp::solve_warp<wp::LipW, NS>(in, b, lane, leg, S);
             tot += S.iters;
             if (S.status == 2) ninf++;
             const bool close = wp::w_close<NS>(cs_.P, sm);
             if (out.traj && lane < 8) {
                 double v;
-                if (lane < 5) v = sm.nodes[1][lane];
+                if (lane < 5) v = sm.nd.nodes[1][lane];
                 else if (lane == 5) v = sm.zc[0];
                 else if (lane == 6) v = sm.zc[1];
                 else v = (double)S.status;
@@ -275,7 +306,7 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_k
             if (lane == 0) {
                 double x0[5], u0[15], g[2] = {sm.graw[0], sm.graw[1]};
 #pragma unroll
-                for (int j = 0; j < 5; j++) { u0[j] = sm.nodes[2][j]; u0[5 + j] = sm.nodes[3][j]; u0[10 + j] = sm.nodes[3][j]; x0[j] = sm.nodes[1][j]; }
+                for (int j = 0; j < 5; j++) { u0[j] = sm.nd.nodes[2][j]; u0[5 + j] = sm.nd.nodes[3][j]; u0[10 + j] = sm.nd.nodes[3][j]; x0[j] = sm.nd.nodes[1][j]; }
                 stage_problem<NS>(cs_.K, sm, x0, g, u0, 0);
             } else {
                 __syncwarp();
@@ -361,13 +392,14 @@ __global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
 
 // one problem per warp for batches that cannot fill the GPU with one problem per thread (and for single solves)
 static bool use_warp_kernel(const dcbf_ctx *ctx, int B) {
-    if (ctx->P.formulation == DCBF_DD) return false;
+    // DD: the warp kernel wins up to ~32 k scenarios (3x at 4096), the per-thread kernel beyond (profiles/r02_summary.md)
+    if (ctx->P.formulation == DCBF_DD && ctx->kernel_mode == 0) return B <= 32768;
     if (ctx->kernel_mode == 1) return false;
     if (ctx->kernel_mode == 2) return true;
     return B <= ctx->warp_max_batch;
 }
 static int warp_slots(const dcbf_ctx *ctx) {
-    const int m = 3 * (ctx->Kc + ctx->Ke + (ctx->P.has_fen ? 6 : 4));
+    const int m = ctx->P.formulation == DCBF_DD ? 3 * (ctx->Kc + ctx->Ke + 4) : 3 * (ctx->Kc + ctx->Ke + (ctx->P.has_fen ? 6 : 4));
     return m <= 32 ? 1 : (m <= 64 ? 2 : 4);
 }
 template <int NS>
@@ -377,6 +409,16 @@ static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const Solv
     const int cap = ctx->sm_count * DCBF_WARP_GRID_CAP;
     if (!order && cap > 0 && grid > cap) grid = cap;
     solve_lip_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, count);
+    CK(cudaGetLastError());
+    return DCBF_OK;
+}
+
+template <int NS>
+static int launch_solve_dd_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
+    int grid = B;
+    const int cap = ctx->sm_count * DCBF_WARP_GRID_CAP;
+    if (cap > 0 && grid > cap) grid = cap;
+    solve_dd_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -576,11 +618,16 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
     const bool dd = ctx->P.formulation == DCBF_DD;
     const int resident = (dd ? ctx->refill_ctas_dd : ctx->refill_ctas_lip) * DCBF_BLOCK;
     const bool refill = ctx->refill_min_batch >= 0 && B > (ctx->refill_min_batch > 0 ? ctx->refill_min_batch : resident) &&
-                        (dd || !use_warp_kernel(ctx, B));
+                        !use_warp_kernel(ctx, B);
     if (refill) {
         CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
         if (dd) solve_dd_refill_kernel<<<ctx->refill_ctas_dd, DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out, ctx->d_counter);
         else solve_lip_refill_kernel<<<ctx->refill_ctas_lip, DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out, ctx->d_counter);
+    }
+    else if (dd && use_warp_kernel(ctx, B)) {
+        const int ns = warp_slots(ctx);
+        const int rc = ns == 1 ? launch_solve_dd_warp<1>(ctx, B, in, out, st) : (ns == 2 ? launch_solve_dd_warp<2>(ctx, B, in, out, st) : launch_solve_dd_warp<4>(ctx, B, in, out, st));
+        if (rc != DCBF_OK) return rc;
     }
     else if (dd) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
     else if (use_warp_kernel(ctx, B)) {

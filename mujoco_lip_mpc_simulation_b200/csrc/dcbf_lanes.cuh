@@ -5,7 +5,9 @@
 
 namespace dcbf {
 
+#ifndef DCBF_KT
 #define DCBF_KT (2 * DCBF_MAX_OBS)
+#endif
 
 // obstacle lists -> quadratic-form records (MPC_LIP_modi.py:598-609 hoisted out of the solve)
 DCBF_HD void prep_circle(const double *c, double *o) { o[0] = c[0]; o[1] = c[1]; o[2] = c[2] * c[2]; }

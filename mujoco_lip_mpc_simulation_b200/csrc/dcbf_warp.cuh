@@ -18,6 +18,9 @@
 //   * norms, merit values and step sizes are warp-shuffle reductions; the 9x9 Cholesky is row-owned (lane i owns row
 //     i, lane 9 carries the right-hand side as a tenth row, which is the forward substitution) with the factor staged
 //     in shared memory; all scalar control flow is replicated and therefore uniform.
+// The interior-point driver (solve_warp) is written once against a small model interface -- rows, nodes, gradient staging,
+// Hessian sources -- and instantiated for the LIP formulations (LipW, 9 variables) and the differential-drive formulation
+// (DdW, 6 variables; node Jacobians are recomputed per iterate because the unicycle rollout is not affine).
 // The algorithm (barrier rule, filter, restoration, status codes) is the one of ipm_iterate() in dcbf_core.cuh.
 #pragma once
 #include "dcbf_lanes.cuh"
@@ -43,6 +46,8 @@ struct WarpTables {
     double hc[NHT][48];       // K[e] += hc[t][e] * src[hs[t][e]]
     unsigned char hs[NHT][48];
     double cab[10][6];        // (cA[3], cB[3]) per row class: CBF step 0..2, velocity rows step 0..2, leg step 0..2, turn
+    int desc_dd[64];          // DD: 2 rounds x 32 lanes, same packing (21 matrix entries + 18 vector entries)
+    double sm_dd[24];         // DD: constant Hessian pattern of the control-smoothness cost (per unit 2 w_t)
 };
 
 // variable order (fx0, fy0, fx1, fy1, fx2, fy2, t0, t1, t2): step of a variable
@@ -120,6 +125,26 @@ inline bool build_warp_tables(const Consts &k, WarpTables &W) {
         if (l < i) { W.cab[i][3 + l] = k.gx[i - 1 - l]; W.cab[6 + i][3 + l] = k.gx[i - 1 - l]; }   // cB of D-CBF / leg rows
         if (l == i) W.cab[6 + i][3 + l] = -1.0;
     }
+    // ---- DD: variables (v0, w0, v1, w1, v2, w2), step of variable a = a / 2; staged rows 0..5 gradient, 6..11 sigma * gradient,
+    //      12..15 weights ------------------------------------------------------------------------------------------------------
+    {
+        struct Ent { int rowP, rowQ, cls, out; };
+        Ent ent[39];
+        int n = 0;
+        for (int cls = 0; cls < 3; cls++) {
+            for (int a = 0; a < 6; a++) for (int b = 0; b <= a; b++)
+                if ((a >> 1) == cls) ent[n++] = {6 + a, b, cls, KQ_K + tri(a, b)};      // max(step a, step b) = step a for b <= a
+            for (int v = 0; v < 3; v++) for (int a = 0; a < 6; a++)
+                if ((a >> 1) == cls) ent[n++] = {12 + 1 + v, a, cls, KQ_Q + 6 * v + a};
+        }
+        if (n != 39) return false;
+        for (int t = 0; t < 64; t++) W.desc_dd[t] = t < 39 ? (ent[t].rowP | ent[t].rowQ << 8 | ent[t].cls << 16 | ent[t].out << 20) : -1;
+        // t sum_i |u_i - u_{i-1}|^2  (MPC_DD_sig_step.py:351-369): Hessian 2 t * [[2,-1,0],[-1,2,-1],[0,-1,1]] on v and on w
+        for (int e = 0; e < 24; e++) W.sm_dd[e] = 0.0;
+        static const double D3[3][3] = {{2, -1, 0}, {-1, 2, -1}, {0, -1, 1}};
+        for (int a = 0; a < 6; a++) for (int b = 0; b <= a; b++)
+            if ((a & 1) == (b & 1)) W.sm_dd[tri(a, b)] = D3[a >> 1][b >> 1];
+    }
     return true;
 }
 
@@ -127,21 +152,46 @@ inline bool build_warp_tables(const Consts &k, WarpTables &W) {
 
 template <int NS> struct KsMax { static constexpr int v = NS == 1 ? 6 : (NS == 2 ? 17 : 2 * DCBF_MAX_OBS); };
 
-template <int NS>
-struct alignas(16) WarpShared {
-    static constexpr int RP = 32 * NS + 2;   // padded row length: class starts / ends are rounded to even rows
-    double ST[22][RP];       // staged rows, transposed: 0..8 gradient, 9..17 sigma * gradient, 18..21 sigma, w1, binv, y
-    double HQ[32 * NS][3];   // y * (2a', b', 2c') of the D-CBF rows
-    double obs[KsMax<NS>::v][6];   // selected obstacles: cx, cy, a', b', c', rhs
-    double KQ[KQ_LEN];       // assembled system (see KQ_*)
-    double Lf[LF_LEN];       // Cholesky factor (packed rows 0..8), the forward-substituted right-hand side (row 9), dump slots
-    double dz[32], zc[32], zt[32];   // 9 meaningful entries each; all lanes store
-    double x0[5], goal[2], graw[2];
+// slots of WarpShared::cold.  Every lane stores the same value and nobody reads before the next __syncwarp(); none of these is
+// updated by read-modify-write (that would not be safe if the lanes of a warp drifted apart).
+enum { C_RESTO_TARGET = 0, C_RESTO_ENTRY, C_THETA_MAX, C_THETA_MIN, C_OBJ, C_VIOL, C_ST_THETA, C_ST_LOGSUM, C_ST_V2, C_ST_VMAX };
+
+// model-specific node data -----------------------------------------------------------------------------------------------------
+struct LipNodeData {
     double fr[4][4];         // free response (zero foot placements) x, y, vx, vy at nodes 0..3
     double nodes[4][5];      // x, y, vx, vy, th of nodes 0..3
     double trig[4][3];       // sin, cos, atan2 target of nodes 1..3
     double nobj[4][10];      // f_k, nx, ny, nt, hxx, hxy, hyy, hxt, hyt, htt of the objective at node k
     double NHf[NSRC + 1];    // Hessian sources (+ one zero for the padding terms of the table)
+};
+struct DdNodeData {
+    double nodes[4][3];      // x, y, th of nodes 0..3
+    double trig[3][2];       // sin, cos of th_0..2
+    double Jx[4][6], Jy[4][6];   // d pos_k / dz (zero beyond the variables of steps < k)
+    double nobj[4][10];      // as above (node k = 1..3); slot 0: the smoothness part of the objective
+    double gsm[6];           // gradient of the smoothness cost
+    double Q[4][3], Cc[4][2];    // sum of y * Q_r and y * grad h over the rows that touch node k
+    double cvw[3], cww[3];   // curvature coefficients of the positions (see dd_add_second() in dcbf_core.cuh)
+    double last_u[2];
+};
+
+template <class M, int NS>
+struct alignas(16) WarpShared {
+    static constexpr int N = M::N;
+    static constexpr int RP = 32 * NS + 2;   // padded row length: class starts / ends are rounded to even rows
+    static constexpr int NST = 2 * N + 4;
+    double ST[NST][RP];      // staged rows, transposed: [0, N) gradient, [N, 2N) sigma * gradient, then sigma, w1, binv, y
+    double HQ[32 * NS][M::NHQ];   // y * (second-order / first-order row coefficients) of the D-CBF rows
+    double obs[KsMax<NS>::v][6];  // selected obstacles: cx, cy, a', b', c', rhs
+    double KQ[KQ_LEN];       // assembled system (see KQ_*)
+    double Lf[LF_LEN];       // Cholesky factor (packed rows 0..N-1), the forward-substituted right-hand side (row N), dump slots
+    double dz[32], zc[32], zt[32];   // N meaningful entries each; all lanes store
+    double x0[5], goal[2], graw[2];
+    // row state (slack, multipliers, step) of the kernels with more than one row per lane: the slot loop stays rolled there
+    // (half the code, a third fewer registers); the single-slot kernel keeps it in registers
+    static constexpr bool ROLLED = NS > 2 || (NS == 2 && M::ROLL2);
+    double RS[ROLLED ? 6 : 1][ROLLED ? 32 * NS : 1];
+    typename M::NodeData nd;
     double cold[12];         // replicated scalars that are written once per event and read much later (see C_*): kept out of registers
     double filt_th[DCBF_FILT], filt_ph[DCBF_FILT];
 };
@@ -153,12 +203,13 @@ struct CtaShared {
     double cab[10][6];
     double hc[NHT][48];          // copy of the Hessian table (global loads in the assembly loop cost a long-scoreboard stall each)
     unsigned char hs[NHT][48];
+    double sm_dd[24];
     const WarpTables *tab;
 };
 
 // one warp per CTA: the per-problem scratch and the constants are static shared-memory objects, so every function sees
 // them as shared-space symbols (LDS/STS with immediate offsets, no generic pointers through the out-of-line calls)
-template <int NS> __shared__ WarpShared<NS> g_sm;
+template <class M, int NS> __shared__ WarpShared<M, NS> g_sm;
 __shared__ CtaShared g_cs;
 
 // %laneid through a volatile asm: the value stays in a register (the compiler otherwise re-reads SR_TID.X at every use)
@@ -180,199 +231,90 @@ __device__ __forceinline__ int wsumi(int v) {
 }
 
 struct RowDesc { int type, step, obs, cls; };
-
-// step-major row order: step i holds  [D-CBF x Ks, v_bx, v_by, leg, turn, (fen+, fen-)]
-__device__ __forceinline__ RowDesc row_desc(int r, int Ks, int ms, int m) {
-    RowDesc d;
-    d.type = RT_NONE; d.step = 0; d.obs = 0; d.cls = 9;
-    if (r >= m) return d;
-    d.step = r / ms;
-    const int w = r - d.step * ms;
-    if (w < Ks) { d.type = RT_CBF; d.obs = w; d.cls = d.step; }
-    else {
-        d.type = RT_VBX + (w - Ks);
-        d.cls = d.type == RT_LEG ? 6 + d.step : (d.type == RT_DTH ? 9 : 3 + d.step);
-    }
-    return d;
-}
-
 struct RowBnd { double lo, hi; bool has_lo, has_hi; };
 
-// static bounds of a row (MPC_LIP_sig_step.py:193-227, MPC_LIP_modi.py:203-245; split form of the coupling row)
-__device__ __forceinline__ RowBnd row_bounds(const dcbf_params &P, const RowDesc &rd, int leg) {
-    RowBnd b;
-    b.lo = -1e300; b.hi = 1e300; b.has_lo = false; b.has_hi = false;
-    if (rd.type == RT_CBF) { b.lo = 0.0; b.has_lo = true; }
-    else if (rd.type == RT_VBX) { b.lo = P.bvx_min; b.hi = P.bvx_max; b.has_lo = b.has_hi = true; }
-    else if (rd.type == RT_VBY) {
-        const bool plus = (leg > 0) == ((rd.step & 1) == 0);
-        b.lo = plus ? P.bvy_min : -P.bvy_max; b.hi = plus ? P.bvy_max : -P.bvy_min; b.has_lo = b.has_hi = true;
-    }
-    else if (rd.type == RT_LEG) { b.hi = P.leg_sq; b.has_hi = true; }
-    else if (rd.type == RT_DTH) { b.lo = -P.ang_max; b.hi = P.ang_max; b.has_lo = b.has_hi = true; }
-    else if (rd.type == RT_FENP || rd.type == RT_FENM) { b.hi = P.bvx_max; b.has_hi = true; }
-    return b;
-}
-
-// value of one row and, with GRAD, the six scalars its gradient is made of:
-//   d row / d foot_l = cA[l] * (p0, p1) + cB[l] * (q0, q1),   d row / d turn_l = (l <= step) * t_all + (l == step) * t_own
+// value of one row and, with GRAD, the scalars its gradient is made of.
+//   LIP: d row / d foot_l = cA[l] * (p0, p1) + cB[l] * (q0, q1),   d row / d turn_l = (l <= step) * t_all + (l == step) * t_own
+//   DD : grad = p0 Jx[i+1] + p1 Jy[i+1] + q0 Jx[i] + q1 Jy[i] + t_all e_{v_i} + t_own e_{w_i}
 struct RowEval { double c, p0, p1, q0, q1, t_all, t_own, hq0, hq1, hq2; };
-
-template <int NS, bool GRAD>
-__device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
-    e.c = 0.0;
-    if (GRAD) { e.p0 = e.p1 = e.q0 = e.q1 = e.t_all = e.t_own = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0; }
-    const int i = rd.step, kn = i + 1;
-    if (rd.type == RT_CBF) {
-        const double *o = sm.obs[rd.obs];
-        const double gm1 = P.gamma - 1.0;
-        const double ax = sm.nodes[kn][0] - o[0], ay = sm.nodes[kn][1] - o[1], bx = sm.nodes[i][0] - o[0], by = sm.nodes[i][1] - o[1];
-        const double ea = o[2], eb = o[3], ec = o[4];
-        e.c = (ea * ax * ax + eb * ax * ay + ec * ay * ay - o[5]) + gm1 * (ea * bx * bx + eb * bx * by + ec * by * by - o[5]);
-        if (GRAD) {
-            e.p0 = 2.0 * ea * ax + eb * ay; e.p1 = 2.0 * ec * ay + eb * ax;
-            e.q0 = gm1 * (2.0 * ea * bx + eb * by); e.q1 = gm1 * (2.0 * ec * by + eb * bx);
-            e.hq0 = 2.0 * ea; e.hq1 = eb; e.hq2 = 2.0 * ec;
-        }
-    } else if (rd.type == RT_LEG) {
-        const double lx = sm.nodes[i][0] - z[2 * i], ly = sm.nodes[i][1] - z[2 * i + 1];
-        e.c = lx * lx + ly * ly;
-        if (GRAD) { e.q0 = 2.0 * lx; e.q1 = 2.0 * ly; }
-    } else if (rd.type == RT_DTH) {
-        e.c = z[6 + i];
-        if (GRAD) e.t_own = 1.0;
-    } else if (rd.type != RT_NONE) {   // v_bx, v_by, fen+, fen-
-        const double sn = sm.trig[kn][0], cs = sm.trig[kn][1];
-        const double vx = sm.nodes[kn][2], vy = sm.nodes[kn][3];
-        const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
-        if (rd.type == RT_VBY) {
-            e.c = vby;
-            if (GRAD) { e.p0 = -sn; e.p1 = cs; e.t_all = -vbx; }
-        } else {
-            if (GRAD) { e.p0 = cs; e.p1 = sn; e.t_all = vby; }
-            if (rd.type == RT_VBX) e.c = vbx;
-            else {
-                const double sg = rd.type == RT_FENP ? P.s_turn : -P.s_turn;
-                e.c = vbx + sg * z[6 + i];
-                if (GRAD) e.t_own = sg;
-            }
-        }
-    }
-}
-
-// slots of WarpShared::cold.  Every lane stores the same value and nobody reads before the next __syncwarp(); none of these is
-// updated by read-modify-write (that would not be safe if the lanes of a warp drifted apart).
-enum { C_RESTO_TARGET = 0, C_RESTO_ENTRY, C_THETA_MAX, C_THETA_MIN, C_OBJ, C_VIOL, C_ST_THETA, C_ST_LOGSUM, C_ST_V2, C_ST_VMAX };
 
 struct WState {   // replicated scalars of one problem (registers)
     double mu, sf, alpha, alpha_z, delta_last, lm_lambda;
     double v2_h1, v2_h2;   // windowed stagnation test of the restoration (see ipm_iterate())
     int nf, iters, acc_cnt, status, phase, nstall, tiny, nresto;
     bool pending, reinit, first;
-#ifdef DCBF_DBG
-    int n_fact, n_fail, n_trial, n_pass;
-#endif
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// nodes 1..3 at the point z (lanes 0..2, directly from the free response and the constant influence coefficients),
-// per-node trigonometry and objective terms; collective, out of line
-// ---------------------------------------------------------------------------------------------------------------
-template <int NS>
-__device__ __noinline__ void w_nodes(const double *z, int lane, double sf, bool want_hess) {
-    WarpShared<NS> &sm = g_sm<NS>;
-    const CtaShared &cs_ = g_cs;
-    const dcbf_params &P = cs_.P;
-    if (lane < 3) {
-        const int kn = lane + 1;
-        double x = sm.fr[kn][0], y = sm.fr[kn][1], vx = sm.fr[kn][2], vy = sm.fr[kn][3], th = sm.x0[4];
-        const double *cx = cs_.cab[lane], *cv = cs_.cab[3 + lane];   // gx[kn-1-l], gv[kn-1-l] for l < kn, else 0
-#pragma unroll
-        for (int l = 0; l < 3; l++) {
-            const double fx = z[2 * l], fy = z[2 * l + 1];
-            x = fma(cx[l], fx, x); y = fma(cx[l], fy, y); vx = fma(cv[l], fx, vx); vy = fma(cv[l], fy, vy);
-            th += l < kn ? z[6 + l] : 0.0;
-        }
-        sm.nodes[kn][0] = x; sm.nodes[kn][1] = y; sm.nodes[kn][2] = vx; sm.nodes[kn][3] = vy; sm.nodes[kn][4] = th;
-        double sn, cs;
-        fsincos(th, &sn, &cs);   // inline: interleaves with the atan2 chain below
-        const double w = P.w_q + (kn == 1 ? P.w_p : 0.0);
-        const double ex = x - sm.goal[0], ey = y - sm.goal[1];
-        const double dx = -ex, dy = -ey;
-        const double r2 = dx * dx + dy * dy, ir2 = frcp(r2);
-        const double tar = fatan2(dy, dx);
-        const double phi = th - tar;
-        sm.trig[kn][0] = sn; sm.trig[kn][1] = cs; sm.trig[kn][2] = tar;
-        const double px = -dy * ir2, py = dx * ir2;
-        sm.nobj[kn][0] = w * (ex * ex + ey * ey) + P.w_r * phi * phi;
-        sm.nobj[kn][1] = 2.0 * w * ex + 2.0 * P.w_r * phi * px;
-        sm.nobj[kn][2] = 2.0 * w * ey + 2.0 * P.w_r * phi * py;
-        sm.nobj[kn][3] = 2.0 * P.w_r * phi;
-        if (want_hess) {
-            const double ir4 = ir2 * ir2;
-            const double pxx = -2.0 * dx * dy * ir4, pyy = -pxx, pxy = (dx * dx - dy * dy) * ir4;
-            const double r2w = 2.0 * P.w_r * sf;
-            sm.nobj[kn][4] = sf * 2.0 * w + r2w * (px * px + phi * pxx);
-            sm.nobj[kn][5] = r2w * (px * py + phi * pxy);
-            sm.nobj[kn][6] = sf * 2.0 * w + r2w * (py * py + phi * pyy);
-            sm.nobj[kn][7] = r2w * px; sm.nobj[kn][8] = r2w * py; sm.nobj[kn][9] = r2w;
-        }
-    }
-    __syncwarp();
-}
-
-// eight statistics reduced together (interleaved butterflies): four sums and four maxima
-struct Stat8 { double s0, s1, s2, s3, m0, m1, m2, m3; };
-__device__ __forceinline__ void reduce8_inline(Stat8 &t) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        t.s0 += __shfl_xor_sync(FULL, t.s0, o); t.s1 += __shfl_xor_sync(FULL, t.s1, o);
-        t.s2 += __shfl_xor_sync(FULL, t.s2, o); t.s3 += __shfl_xor_sync(FULL, t.s3, o);
-        t.m0 = fmax(t.m0, __shfl_xor_sync(FULL, t.m0, o)); t.m1 = fmax(t.m1, __shfl_xor_sync(FULL, t.m1, o));
-        t.m2 = fmax(t.m2, __shfl_xor_sync(FULL, t.m2, o)); t.m3 = fmax(t.m3, __shfl_xor_sync(FULL, t.m3, o));
+// D-CBF row on the staged obstacle record (circle: a' = c' = 1, b' = 0); shared by both models
+template <bool GRAD>
+__device__ __forceinline__ void eval_cbf(const double *o, double gm1, double x1, double y1, double x0, double y0, RowEval &e) {
+    const double ax = x1 - o[0], ay = y1 - o[1], bx = x0 - o[0], by = y0 - o[1];
+    const double ea = o[2], eb = o[3], ec = o[4];
+    e.c = (ea * ax * ax + eb * ax * ay + ec * ay * ay - o[5]) + gm1 * (ea * bx * bx + eb * bx * by + ec * by * by - o[5]);
+    if (GRAD) {
+        e.p0 = 2.0 * ea * ax + eb * ay; e.p1 = 2.0 * ec * ay + eb * ax;
+        e.q0 = gm1 * (2.0 * ea * bx + eb * by); e.q1 = gm1 * (2.0 * ec * by + eb * bx);
+        e.hq0 = 2.0 * ea; e.hq1 = eb; e.hq2 = 2.0 * ec;
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// the solver for one problem (all 32 lanes call it with identical arguments).  Inputs in sm: x0, graw, zc, fr.
-// ---------------------------------------------------------------------------------------------------------------
-template <int NS>
-__device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WState &S) {
-    constexpr int RP = WarpShared<NS>::RP;
-    WarpShared<NS> &sm = g_sm<NS>;
-    const CtaShared &cs_ = g_cs;
-    const dcbf_params &P = cs_.P;
-    // ---- problem setup -------------------------------------------------------------------------------------------
+// one lane per obstacle: selection (MPC_LIP_modi.py:325-338), compaction into sm.obs; returns the number of selected obstacles.
+// `sel_out` / `rec` let the LIP model run the detour heuristic on the same lanes.
+template <class M, int NS>
+__device__ __forceinline__ int stage_obstacles(const dcbf_params &P, WarpShared<M, NS> &sm, const BatchIn &in, int b, int lane, double px, double py,
+                                               double *rec, bool &sel_out, bool &is_circle) {
     const int fld = in.field ? in.field[b] : 0;
     const double *cir = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC;
     const double *elp = in.elp_rec + (size_t)fld * in.Ke * DCBF_ELP_REC;
-    const double px = sm.x0[0], py = sm.x0[1];
-    int Ks;
-    {
-        // one lane per obstacle: selection (MPC_LIP_modi.py:325-338), compaction, detour heuristic (MPC_LIP_sig_step.py:229-253)
-        const int j = lane;
-        const bool is_c = j < in.Kc, is_e = !is_c && j < in.Kc + in.Ke;
-        double rec[6] = {0, 0, 1, 0, 1, 0};
-        double dsel = 1e300;
-        if (is_c) {
-            const double *o = cir + DCBF_CIR_REC * j;
-            rec[0] = o[0]; rec[1] = o[1]; rec[5] = o[2];
-            dsel = (px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]) - o[2];
-        } else if (is_e) {
-            const double *o = elp + DCBF_ELP_REC * (j - in.Kc);
-            rec[0] = o[0]; rec[1] = o[1]; rec[2] = o[2]; rec[3] = o[3]; rec[4] = o[4]; rec[5] = o[5];
-            dsel = (px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]) - o[6];
-        }
-        const bool sel = (is_c || is_e) && (!P.select_obs || dsel <= P.detect_sq);
-        const unsigned mask = __ballot_sync(FULL, sel);
-        Ks = __popc(mask);
-        if (sel) {
-            const int pos = __popc(mask & ((1u << lane) - 1u));
-            if (pos < KsMax<NS>::v) {
+    const int j = lane;
+    const bool is_c = j < in.Kc, is_e = !is_c && j < in.Kc + in.Ke;
+    rec[0] = 0; rec[1] = 0; rec[2] = 1; rec[3] = 0; rec[4] = 1; rec[5] = 0;
+    double dsel = 1e300;
+    if (is_c) {
+        const double *o = cir + DCBF_CIR_REC * j;
+        rec[0] = o[0]; rec[1] = o[1]; rec[5] = o[2];
+        dsel = (px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]) - o[2];
+    } else if (is_e) {
+        const double *o = elp + DCBF_ELP_REC * (j - in.Kc);
+        rec[0] = o[0]; rec[1] = o[1]; rec[2] = o[2]; rec[3] = o[3]; rec[4] = o[4]; rec[5] = o[5];
+        dsel = (px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]) - o[6];
+    }
+    const bool sel = (is_c || is_e) && (!P.select_obs || dsel <= P.detect_sq);
+    const unsigned mask = __ballot_sync(FULL, sel);
+    if (sel) {
+        const int pos = __popc(mask & ((1u << lane) - 1u));
+        if (pos < KsMax<NS>::v) {
 #pragma unroll
-                for (int c = 0; c < 6; c++) sm.obs[pos][c] = rec[c];
-            }
+            for (int c = 0; c < 6; c++) sm.obs[pos][c] = rec[c];
         }
+    }
+    sel_out = sel; is_circle = is_c;
+    return __popc(mask);
+}
+
+// ===============================================================================================================
+// LIP model (sig_step / modi): z = (fx0, fy0, fx1, fy1, fx2, fy2, t0, t1, t2)
+// ===============================================================================================================
+struct LipW {
+    static constexpr int N = 9;
+    static constexpr int NHQ = 3;
+    static constexpr int NROUND = 3;
+    static constexpr bool HAS_CURV = false;
+    static constexpr bool ROLL2 = false;   // two-slot kernel: unrolled slot loop, row state in registers (measured faster for modi)
+    using NodeData = LipNodeData;
+    enum { RT_NONE = 0, RT_CBF, RT_VBX, RT_VBY, RT_LEG, RT_DTH, RT_FENP, RT_FENM };
+
+    static __device__ __forceinline__ const int *desc(const WarpTables *tab) { return tab->desc; }
+    static __device__ __forceinline__ int rows_per_step(const dcbf_params &P, int Ks) { return Ks + (P.has_fen ? 6 : 4); }
+    static __device__ __forceinline__ int class_start(int cls, int, int ms) { return cls * ms; }   // first row that can touch a variable of step cls
+
+    // problem setup: obstacle selection + compaction, detour heuristic (MPC_LIP_sig_step.py:229-253), node 0
+    template <int NS>
+    static __device__ __forceinline__ int setup(WarpShared<LipW, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane) {
+        const double px = sm.x0[0], py = sm.x0[1];
+        double rec[6];
+        bool sel, is_c;
+        const int Ks = stage_obstacles<LipW, NS>(P, sm, in, b, lane, px, py, rec, sel, is_c);
         bool hit = false;
         double ngx = 0.0, ngy = 0.0;
         const double gx = sm.graw[0], gy = sm.graw[1];
@@ -394,6 +336,7 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                 }
             }
         }
+        __syncwarp();
         const unsigned hm = __ballot_sync(FULL, hit);
         double g0 = gx, g1 = gy;
         if (hm) {
@@ -401,87 +344,554 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
             g0 = __shfl_sync(FULL, ngx, src); g1 = __shfl_sync(FULL, ngy, src);
         }
         if (lane == 0) { sm.goal[0] = g0; sm.goal[1] = g1; }
-        if (lane < 5) sm.nodes[0][lane] = sm.x0[lane];
+        if (lane < 5) sm.nd.nodes[0][lane] = sm.x0[lane];
+        if (lane == 5) sm.nd.NHf[NSRC] = 0.0;   // the padding terms of the Hessian table read this slot
+        __syncwarp();
+        return Ks;
+    }
+
+    // step-major row order: step i holds  [D-CBF x Ks, v_bx, v_by, leg, turn, (fen+, fen-)]
+    static __device__ __forceinline__ RowDesc row_desc(int r, int Ks, int ms, int m) {
+        RowDesc d;
+        d.type = RT_NONE; d.step = 0; d.obs = 0; d.cls = 9;
+        if (r >= m) return d;
+        d.step = r / ms;
+        const int w = r - d.step * ms;
+        if (w < Ks) { d.type = RT_CBF; d.obs = w; d.cls = d.step; }
+        else {
+            d.type = RT_VBX + (w - Ks);
+            d.cls = d.type == RT_LEG ? 6 + d.step : (d.type == RT_DTH ? 9 : 3 + d.step);
+        }
+        return d;
+    }
+
+    // static bounds of a row (MPC_LIP_sig_step.py:193-227, MPC_LIP_modi.py:203-245; split form of the coupling row)
+    static __device__ __forceinline__ RowBnd row_bounds(const dcbf_params &P, const RowDesc &rd, int leg) {
+        RowBnd b;
+        b.lo = -1e300; b.hi = 1e300; b.has_lo = false; b.has_hi = false;
+        if (rd.type == RT_CBF) { b.lo = 0.0; b.has_lo = true; }
+        else if (rd.type == RT_VBX) { b.lo = P.bvx_min; b.hi = P.bvx_max; b.has_lo = b.has_hi = true; }
+        else if (rd.type == RT_VBY) {
+            const bool plus = (leg > 0) == ((rd.step & 1) == 0);
+            b.lo = plus ? P.bvy_min : -P.bvy_max; b.hi = plus ? P.bvy_max : -P.bvy_min; b.has_lo = b.has_hi = true;
+        }
+        else if (rd.type == RT_LEG) { b.hi = P.leg_sq; b.has_hi = true; }
+        else if (rd.type == RT_DTH) { b.lo = -P.ang_max; b.hi = P.ang_max; b.has_lo = b.has_hi = true; }
+        else if (rd.type == RT_FENP || rd.type == RT_FENM) { b.hi = P.bvx_max; b.has_hi = true; }
+        return b;
+    }
+
+    template <int NS, bool GRAD>
+    static __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<LipW, NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
+        e.c = 0.0;
+        if (GRAD) { e.p0 = e.p1 = e.q0 = e.q1 = e.t_all = e.t_own = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0; }
+        const int i = rd.step, kn = i + 1;
+        const double (*nodes)[5] = sm.nd.nodes;
+        if (rd.type == RT_CBF) {
+            eval_cbf<GRAD>(sm.obs[rd.obs], P.gamma - 1.0, nodes[kn][0], nodes[kn][1], nodes[i][0], nodes[i][1], e);
+        } else if (rd.type == RT_LEG) {
+            const double lx = nodes[i][0] - z[2 * i], ly = nodes[i][1] - z[2 * i + 1];
+            e.c = lx * lx + ly * ly;
+            if (GRAD) { e.q0 = 2.0 * lx; e.q1 = 2.0 * ly; }
+        } else if (rd.type == RT_DTH) {
+            e.c = z[6 + i];
+            if (GRAD) e.t_own = 1.0;
+        } else if (rd.type != RT_NONE) {   // v_bx, v_by, fen+, fen-
+            const double sn = sm.nd.trig[kn][0], cs = sm.nd.trig[kn][1];
+            const double vx = nodes[kn][2], vy = nodes[kn][3];
+            const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
+            if (rd.type == RT_VBY) {
+                e.c = vby;
+                if (GRAD) { e.p0 = -sn; e.p1 = cs; e.t_all = -vbx; }
+            } else {
+                if (GRAD) { e.p0 = cs; e.p1 = sn; e.t_all = vby; }
+                if (rd.type == RT_VBX) e.c = vbx;
+                else {
+                    const double sg = rd.type == RT_FENP ? P.s_turn : -P.s_turn;
+                    e.c = vbx + sg * z[6 + i];
+                    if (GRAD) e.t_own = sg;
+                }
+            }
+        }
+    }
+
+    // transposed staging of one row: gradient, sigma * gradient (rows beyond m stage zeros), D-CBF curvature weights
+    template <int NS>
+    static __device__ __forceinline__ void stage_row(WarpShared<LipW, NS> &sm, const CtaShared &cs_, const RowDesc &rd, const RowEval &e, double sig, double y, int r) {
+        constexpr int RP = WarpShared<LipW, NS>::RP;
+        const double *ab = cs_.cab[rd.cls];
+        const int i = rd.step;
+        double *col = &sm.ST[0][r];
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+            const double ca = ab[l], cb = ab[3 + l];
+            const double gxv = fma(ca, e.p0, cb * e.q0), gyv = fma(ca, e.p1, cb * e.q1);
+            const double gtv = (l <= i ? e.t_all : 0.0) + (l == i ? e.t_own : 0.0);
+            col[(2 * l) * RP] = gxv; col[(2 * l + 1) * RP] = gyv; col[(6 + l) * RP] = gtv;
+            col[(9 + 2 * l) * RP] = sig * gxv; col[(9 + 2 * l + 1) * RP] = sig * gyv; col[(9 + 6 + l) * RP] = sig * gtv;
+        }
+        sm.HQ[r][0] = y * e.hq0; sm.HQ[r][1] = y * e.hq1; sm.HQ[r][2] = y * e.hq2;
+    }
+
+    // nodes 1..3 at the point z (lanes 0..2, directly from the free response and the constant influence coefficients), per-node
+    // trigonometry and objective terms; collective, out of line
+    template <int NS>
+    static __device__ __noinline__ void nodes(const double *z, int lane, double sf, bool want_hess) {
+        WarpShared<LipW, NS> &sm = g_sm<LipW, NS>;
+        const CtaShared &cs_ = g_cs;
+        const dcbf_params &P = cs_.P;
+        if (lane < 3) {
+            const int kn = lane + 1;
+            double x = sm.nd.fr[kn][0], y = sm.nd.fr[kn][1], vx = sm.nd.fr[kn][2], vy = sm.nd.fr[kn][3], th = sm.x0[4];
+            const double *cx = cs_.cab[lane], *cv = cs_.cab[3 + lane];   // gx[kn-1-l], gv[kn-1-l] for l < kn, else 0
+#pragma unroll
+            for (int l = 0; l < 3; l++) {
+                const double fx = z[2 * l], fy = z[2 * l + 1];
+                x = fma(cx[l], fx, x); y = fma(cx[l], fy, y); vx = fma(cv[l], fx, vx); vy = fma(cv[l], fy, vy);
+                th += l < kn ? z[6 + l] : 0.0;
+            }
+            double *nk = sm.nd.nodes[kn];
+            nk[0] = x; nk[1] = y; nk[2] = vx; nk[3] = vy; nk[4] = th;
+            double sn, cs;
+            fsincos(th, &sn, &cs);   // inline: interleaves with the atan2 chain below
+            sm.nd.trig[kn][0] = sn; sm.nd.trig[kn][1] = cs;
+            node_objective(P, sm.goal, P.w_q + (kn == 1 ? P.w_p : 0.0), x, y, th, sf, want_hess, sm.nd.nobj[kn]);
+        }
         __syncwarp();
     }
-    const bool has_fen = P.has_fen != 0;
-    const int ms = Ks + (has_fen ? 6 : 4);   // rows per step
+
+    // objective value at the staged nodes and its gradient component for lane a < 9 (0 on the other lanes)
+    template <int NS>
+    static __device__ __forceinline__ double objective(const WarpShared<LipW, NS> &sm) {
+        return sm.nd.nobj[1][0] + sm.nd.nobj[2][0] + sm.nd.nobj[3][0];
+    }
+    template <int NS>
+    static __device__ __forceinline__ double grad(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int lane, int ln) {
+        // d node_kn / d foot_l = gx[kn-1-l],  d th_kn / d turn_l = 1; branch-free: lanes >= 9 compute on clamped indices, select 0
+        const int l = ln < 6 ? ln >> 1 : ln - 6;
+        const int c = ln < 6 ? 1 + (ln & 1) : 3;
+        double g = 0.0;
+#pragma unroll
+        for (int kn = 1; kn <= 3; kn++) {
+            const double wf = cs_.cab[kn - 1][l];
+            const double w = ln < 6 ? wf : (l < kn ? 1.0 : 0.0);
+            g = fma(sm.nd.nobj[kn][c], w, g);
+        }
+        return lane < 9 ? g : 0.0;
+    }
+    template <int NS>
+    static __device__ __forceinline__ void rescale_objective_hessian(WarpShared<LipW, NS> &sm, int lane, double sf) {
+        if (lane < 3) {
+#pragma unroll
+            for (int c = 4; c < 10; c++) sm.nd.nobj[lane + 1][c] *= sf;
+        }
+    }
+
+    // node Hessians -> the 27 sources of the Hessian table
+    template <int NS>
+    static __device__ __forceinline__ void hess_sources(WarpShared<LipW, NS> &sm, const dcbf_params &P, int lane, int Ks, int ms) {
+        const double gm1 = P.gamma - 1.0;
+        const double *yv = sm.ST[2 * N + 3];
+        const bool has_fen = P.has_fen != 0;
+        const int lp = lane - 16;
+        if ((unsigned)lp < 9u) {   // position block on lanes 16..24: node kn = lp/3 + 1, component lp % 3
+            const int kn = lp / 3 + 1, c = lp % 3;
+            double acc = sm.nd.nobj[kn][4 + c];
+            for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * ms + j][c];
+            if (kn < 3) for (int j = 0; j < Ks; j++) acc = fma(gm1, sm.HQ[kn * ms + j][c], acc);
+            sm.nd.NHf[8 * (kn - 1) + c] = acc;
+        } else if (lane < 3) {     // heading / velocity entries of node kn = lane + 1 (rows of step kn - 1)
+            const int kn = lane + 1, i = kn - 1, base = i * ms + Ks;
+            double Yx = yv[base], Yy = yv[base + 1];
+            if (has_fen) Yx += yv[base + 4] + yv[base + 5];
+            const double sn = sm.nd.trig[kn][0], cs = sm.nd.trig[kn][1];
+            const double vx = sm.nd.nodes[kn][2], vy = sm.nd.nodes[kn][3];
+            const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
+            double *H = &sm.nd.NHf[8 * i];
+            H[3] = sm.nd.nobj[kn][7]; H[4] = sm.nd.nobj[kn][8];
+            H[5] = sm.nd.nobj[kn][9] - (Yx * vbx + Yy * vby);
+            H[6] = -sn * Yx - cs * Yy; H[7] = cs * Yx - sn * Yy;
+            sm.nd.NHf[24 + i] = 2.0 * yv[base + 2];
+        }
+    }
+    template <int NS>
+    static __device__ __forceinline__ void hess_curvature(WarpShared<LipW, NS> &, int, double, const double *) {}
+    // Lagrangian Hessian of matrix entry e (packed index) through the table
+    template <int NS>
+    static __device__ __forceinline__ double hess_entry(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int e, double sf) {
+        double acc = 0.0;
+#pragma unroll
+        for (int h = 0; h < NHT; h++) acc = fma(cs_.hc[h][e], sm.nd.NHf[cs_.hs[h][e]], acc);
+        return acc;
+    }
+
+    // objective terms at one node: f, (nx, ny, nt), Hessian (xx, xy, yy, xt, yt, tt) scaled by sf; shared with the DD model
+    static __device__ __forceinline__ void node_objective(const dcbf_params &P, const double *goal, double w, double x, double y, double th, double sf,
+                                                          bool want_hess, double *o) {
+        const double ex = x - goal[0], ey = y - goal[1];
+        const double dx = -ex, dy = -ey;
+        const double r2 = dx * dx + dy * dy, ir2 = frcp(r2);
+        const double phi = th - fatan2(dy, dx);
+        const double px = -dy * ir2, py = dx * ir2;
+        o[0] = w * (ex * ex + ey * ey) + P.w_r * phi * phi;
+        o[1] = 2.0 * w * ex + 2.0 * P.w_r * phi * px;
+        o[2] = 2.0 * w * ey + 2.0 * P.w_r * phi * py;
+        o[3] = 2.0 * P.w_r * phi;
+        if (want_hess) {
+            const double ir4 = ir2 * ir2;
+            const double pxx = -2.0 * dx * dy * ir4, pyy = -pxx, pxy = (dx * dx - dy * dy) * ir4;
+            const double r2w = 2.0 * P.w_r * sf;
+            o[4] = sf * 2.0 * w + r2w * (px * px + phi * pxx);
+            o[5] = r2w * (px * py + phi * pxy);
+            o[6] = sf * 2.0 * w + r2w * (py * py + phi * pyy);
+            o[7] = r2w * px; o[8] = r2w * py; o[9] = r2w;
+        }
+    }
+};
+
+// ===============================================================================================================
+// DD model (MPC_DD_sig_step.py): z = (v0, w0, v1, w1, v2, w2), x+ = x + dt v cos th, y+ = y + dt v sin th, th+ = th + w
+// ===============================================================================================================
+struct DdW {
+    static constexpr int N = 6;
+    static constexpr int NHQ = 7;   // y * (2a', b', 2c', h1x, h1y, h0x, h0y)
+    static constexpr int NROUND = 2;
+    static constexpr bool HAS_CURV = true;
+    static constexpr bool ROLL2 = true;    // two-slot kernel: rolled slot loop, row state in shared memory (measured faster for DD)
+    using NodeData = DdNodeData;
+    enum { RT_NONE = 0, RT_CBF, RT_FENP, RT_FENM, RT_BV, RT_BW };
+
+    static __device__ __forceinline__ const int *desc(const WarpTables *tab) { return tab->desc_dd; }
+    static __device__ __forceinline__ int rows_per_step(const dcbf_params &, int Ks) { return Ks + 4; }
+    static __device__ __forceinline__ int class_start(int cls, int Ks, int) { return cls * Ks; }
+
+    template <int NS>
+    static __device__ __forceinline__ int setup(WarpShared<DdW, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane) {
+        double rec[6];
+        bool sel, is_c;
+        const int Ks = stage_obstacles<DdW, NS>(P, sm, in, b, lane, sm.x0[0], sm.x0[1], rec, sel, is_c);
+        if (lane == 0) { sm.goal[0] = sm.graw[0]; sm.goal[1] = sm.graw[1]; }   // no detour heuristic (MPC_DD_sig_step.py:144-168 is commented out)
+        if (lane < 3) sm.nd.nodes[0][lane] = sm.x0[lane];
+        if (lane < 6) { sm.nd.Jx[0][lane] = 0.0; sm.nd.Jy[0][lane] = 0.0; }
+        {   // the columns of linear and of unused rows keep their zeros for the whole solve (see stage_row)
+            double *st = &sm.ST[0][0];
+            for (int t = lane; t < WarpShared<DdW, NS>::NST * WarpShared<DdW, NS>::RP; t += 32) st[t] = 0.0;
+        }
+        __syncwarp();
+        return Ks;
+    }
+
+    // row order: all D-CBF rows step-major (3 Ks), then per step the four linear rows [fen+, fen-, bound v, bound w].  A row of
+    // step s has zero derivatives with respect to the variables of later steps, so a dot product that involves a variable of step
+    // c may start at row c * Ks (the linear rows of earlier steps it then sweeps are zero in that variable).  With K = 10 the
+    // second slot of a lane holds linear rows only, whose staging is two numbers.
+    static __device__ __forceinline__ RowDesc row_desc(int r, int Ks, int, int m) {
+        RowDesc d;
+        d.type = RT_NONE; d.step = 0; d.obs = 0; d.cls = 0;
+        if (r >= m) return d;
+        if (r < 3 * Ks) { d.type = RT_CBF; d.step = r / Ks; d.obs = r - d.step * Ks; }
+        else { const int w = r - 3 * Ks; d.step = w >> 2; d.type = RT_FENP + (w & 3); }
+        return d;
+    }
+    // MPC_DD_sig_step.py:127-141 (variable bounds as rows; split form of the coupling row)
+    static __device__ __forceinline__ RowBnd row_bounds(const dcbf_params &P, const RowDesc &rd, int) {
+        RowBnd b;
+        b.lo = -1e300; b.hi = 1e300; b.has_lo = false; b.has_hi = false;
+        if (rd.type == RT_CBF) { b.lo = 0.0; b.has_lo = true; }
+        else if (rd.type == RT_FENP || rd.type == RT_FENM) { b.hi = P.bvx_max; b.has_hi = true; }
+        else if (rd.type == RT_BV) { b.lo = P.bvx_min; b.hi = P.bvx_max; b.has_lo = b.has_hi = true; }
+        else if (rd.type == RT_BW) { b.lo = -P.ang_max; b.hi = P.ang_max; b.has_lo = b.has_hi = true; }
+        return b;
+    }
+
+    template <int NS, bool GRAD>
+    static __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<DdW, NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
+        e.c = 0.0;
+        if (GRAD) { e.p0 = e.p1 = e.q0 = e.q1 = e.t_all = e.t_own = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0; }
+        const int i = rd.step;
+        if (rd.type == RT_CBF) {
+            eval_cbf<GRAD>(sm.obs[rd.obs], P.gamma - 1.0, sm.nd.nodes[i + 1][0], sm.nd.nodes[i + 1][1], sm.nd.nodes[i][0], sm.nd.nodes[i][1], e);
+        } else if (rd.type != RT_NONE) {
+            const double v = z[2 * i], w = z[2 * i + 1];
+            const double cv = rd.type == RT_BW ? 0.0 : 1.0;
+            const double cw = rd.type == RT_FENP ? P.s_turn : (rd.type == RT_FENM ? -P.s_turn : (rd.type == RT_BW ? 1.0 : 0.0));
+            e.c = cv * v + cw * w;
+            if (GRAD) { e.t_all = cv; e.t_own = cw; }
+        }
+    }
+
+    // D-CBF rows: chain rule through the node Jacobians.  Linear rows: the gradient is (t_all, t_own) on (v_i, w_i); the other
+    // entries of their columns were zeroed once per problem (setup) and nobody else writes them.
+    template <int NS>
+    static __device__ __forceinline__ void stage_row(WarpShared<DdW, NS> &sm, const CtaShared &, const RowDesc &rd, const RowEval &e, double sig, double y, int r) {
+        constexpr int RP = WarpShared<DdW, NS>::RP;
+        const int i = rd.step, kn = i + 1;
+        double *col = &sm.ST[0][r];
+        if (rd.type == RT_CBF) {
+            const double *jx1 = sm.nd.Jx[kn], *jy1 = sm.nd.Jy[kn], *jx0 = sm.nd.Jx[i], *jy0 = sm.nd.Jy[i];
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                const double g = fma(e.p0, jx1[a], fma(e.p1, jy1[a], fma(e.q0, jx0[a], e.q1 * jy0[a])));
+                col[a * RP] = g; col[(6 + a) * RP] = sig * g;
+            }
+            double *h = sm.HQ[r];
+            h[0] = y * e.hq0; h[1] = y * e.hq1; h[2] = y * e.hq2; h[3] = y * e.p0; h[4] = y * e.p1; h[5] = y * e.q0; h[6] = y * e.q1;
+        } else if (rd.type != RT_NONE) {
+            col[(2 * i) * RP] = e.t_all; col[(2 * i + 1) * RP] = e.t_own;
+            col[(6 + 2 * i) * RP] = sig * e.t_all; col[(6 + 2 * i + 1) * RP] = sig * e.t_own;
+        }
+    }
+
+    // headings and their sines / cosines (lanes 0..2 = th_0..2), then nodes 1..3 with their Jacobians and objective terms
+    template <int NS>
+    static __device__ __noinline__ void nodes(const double *z, int lane, double sf, bool want_hess) {
+        WarpShared<DdW, NS> &sm = g_sm<DdW, NS>;
+        const dcbf_params &P = g_cs.P;
+        const double dt = g_cs.K.dt;
+        if (lane < 3) {
+            double th = sm.x0[2];
+#pragma unroll
+            for (int l = 0; l < 2; l++) th += l < lane ? z[2 * l + 1] : 0.0;
+            double sn, cs;
+            fsincos(th, &sn, &cs);
+            sm.nd.trig[lane][0] = sn; sm.nd.trig[lane][1] = cs;
+        }
+        __syncwarp();
+        if (lane < 3) {
+            const int kn = lane + 1;
+            double x = sm.x0[0], y = sm.x0[1], th = sm.x0[2];
+            double jx[6], jy[6];
+#pragma unroll
+            for (int a = 0; a < 6; a++) { jx[a] = 0.0; jy[a] = 0.0; }
+            // x_k = x_0 + dt sum_{l<k} v_l cos th_l;  d/dv_l = dt cos th_l;  d/dw_l = sum_{l<j<k} -dt v_j sin th_j
+            double sx = 0.0, sy = 0.0;   // running sums of -dt v_j sin th_j / +dt v_j cos th_j over j > l (built backwards)
+#pragma unroll
+            for (int l = 2; l >= 0; l--) {
+                if (l < kn) {
+                    const double sn = sm.nd.trig[l][0], cs = sm.nd.trig[l][1], v = z[2 * l];
+                    x = fma(dt * cs, v, x); y = fma(dt * sn, v, y); th += z[2 * l + 1];
+                    jx[2 * l] = dt * cs; jy[2 * l] = dt * sn;
+                    jx[2 * l + 1] = sx; jy[2 * l + 1] = sy;
+                    sx -= dt * v * sn; sy += dt * v * cs;
+                }
+            }
+            sm.nd.nodes[kn][0] = x; sm.nd.nodes[kn][1] = y; sm.nd.nodes[kn][2] = th;
+#pragma unroll
+            for (int a = 0; a < 6; a++) { sm.nd.Jx[kn][a] = jx[a]; sm.nd.Jy[kn][a] = jy[a]; }
+            LipW::node_objective(P, sm.goal, P.w_q + (kn == 1 ? P.w_p : 0.0), x, y, th, sf, want_hess, sm.nd.nobj[kn]);
+        } else if (lane == 3) {
+            // control smoothness  t sum_i |u_i - u_{i-1}|^2,  u_{-1} = last_u  (MPC_DD_sig_step.py:351-369)
+            double f = 0.0, g[6] = {0, 0, 0, 0, 0, 0};
+            double pv = sm.nd.last_u[0], pw = sm.nd.last_u[1];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double dv = z[2 * i] - pv, dw = z[2 * i + 1] - pw;
+                f += P.w_t * (dv * dv + dw * dw);
+                g[2 * i] += 2.0 * P.w_t * dv; g[2 * i + 1] += 2.0 * P.w_t * dw;
+                if (i > 0) { g[2 * i - 2] -= 2.0 * P.w_t * dv; g[2 * i - 1] -= 2.0 * P.w_t * dw; }
+                pv = z[2 * i]; pw = z[2 * i + 1];
+            }
+            sm.nd.nobj[0][0] = f;
+#pragma unroll
+            for (int a = 0; a < 6; a++) sm.nd.gsm[a] = g[a];
+        }
+        __syncwarp();
+    }
+
+    template <int NS>
+    static __device__ __forceinline__ double objective(const WarpShared<DdW, NS> &sm) {
+        return sm.nd.nobj[0][0] + sm.nd.nobj[1][0] + sm.nd.nobj[2][0] + sm.nd.nobj[3][0];
+    }
+    template <int NS>
+    static __device__ __forceinline__ double grad(const WarpShared<DdW, NS> &sm, const CtaShared &, int lane, int ln) {
+        const int a = ln < 6 ? ln : 5;
+        double g = sm.nd.gsm[a];
+#pragma unroll
+        for (int kn = 1; kn <= 3; kn++) {
+            const double et = ((a & 1) && (a >> 1) < kn) ? 1.0 : 0.0;   // d th_kn / d z_a
+            g = fma(sm.nd.nobj[kn][1], sm.nd.Jx[kn][a], fma(sm.nd.nobj[kn][2], sm.nd.Jy[kn][a], fma(sm.nd.nobj[kn][3], et, g)));
+        }
+        return lane < 6 ? g : 0.0;
+    }
+    template <int NS>
+    static __device__ __forceinline__ void rescale_objective_hessian(WarpShared<DdW, NS> &sm, int lane, double sf) {
+        if (lane < 3) {
+#pragma unroll
+            for (int c = 4; c < 10; c++) sm.nd.nobj[lane + 1][c] *= sf;
+        }
+    }
+
+    // per-node second-order sources: Q_k = sum y Q_r (+ objective), C_k = sum y grad h (+ sf * objective gradient), and the
+    // curvature coefficients of the positions (dd_add_second() in dcbf_core.cuh)
+    template <int NS>
+    static __device__ __forceinline__ void hess_sources(WarpShared<DdW, NS> &sm, const dcbf_params &P, int lane, int Ks, int ms) {
+        const double gm1 = P.gamma - 1.0;
+        const int lp = lane - 16;
+        if ((unsigned)lp < 15u) {   // lanes 16..30: node kn = lp / 5 + 1, component c = lp % 5  (qxx, qxy, qyy, cx, cy)
+            const int kn = lp / 5 + 1, c = lp % 5;
+            // rows of step kn - 1 see node kn as their far end (Q_r, h1); rows of step kn see it as their near end (gm1 Q_r, h0)
+            double acc = 0.0;
+            const int cf = c, cn = c < 3 ? c : c + 2;   // HQ slots: far end 0..2 / 3..4, near end 0..2 (x gm1) / 5..6
+            for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * Ks + j][cf];
+            if (kn < 3) {
+                const double sc = c < 3 ? gm1 : 1.0;   // q0 / q1 already carry gm1
+                for (int j = 0; j < Ks; j++) acc = fma(sc, sm.HQ[kn * Ks + j][cn], acc);
+            }
+            if (c < 3) sm.nd.Q[kn][c] = acc + sm.nd.nobj[kn][4 + c];
+            else sm.nd.Cc[kn][c - 3] = acc;   // the objective part is added by the lanes below (needs sf)
+        }
+    }
+    template <int NS>
+    static __device__ __forceinline__ void hess_curvature(WarpShared<DdW, NS> &sm, int lane, double sf, const double *z) {
+        if (lane >= 1 && lane < 3) {   // l = 1, 2
+            const int l = lane;
+            const double dt = g_cs.K.dt;
+            double CX = 0.0, CY = 0.0;
+            for (int kn = l + 1; kn < 4; kn++) { CX += sm.nd.Cc[kn][0] + sf * sm.nd.nobj[kn][1]; CY += sm.nd.Cc[kn][1] + sf * sm.nd.nobj[kn][2]; }
+            const double sn = sm.nd.trig[l][0], cs = sm.nd.trig[l][1];
+            sm.nd.cvw[l] = dt * (-CX * sn + CY * cs);
+            sm.nd.cww[l] = -dt * z[2 * l] * (CX * cs + CY * sn);
+        }
+    }
+    // Lagrangian Hessian of matrix entry e = tri(a, b), a >= b
+    template <int NS>
+    static __device__ __forceinline__ double hess_entry(const WarpShared<DdW, NS> &sm, const CtaShared &cs_, int e, double sf) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= e) a++;
+        const int b = e - a * (a + 1) / 2;
+        double acc = 2.0 * cs_.P.w_t * sf * cs_.sm_dd[e];
+#pragma unroll
+        for (int kn = 1; kn <= 3; kn++) {
+            const double jxa = sm.nd.Jx[kn][a], jya = sm.nd.Jy[kn][a], jxb = sm.nd.Jx[kn][b], jyb = sm.nd.Jy[kn][b];
+            const double qxx = sm.nd.Q[kn][0], qxy = sm.nd.Q[kn][1], qyy = sm.nd.Q[kn][2];
+            acc += (qxx * jxa + qxy * jya) * jxb + (qxy * jxa + qyy * jya) * jyb;
+            const double hxt = sm.nd.nobj[kn][7], hyt = sm.nd.nobj[kn][8], htt = sm.nd.nobj[kn][9];
+            const double ua = hxt * jxa + hyt * jya, ub = hxt * jxb + hyt * jyb;
+            const double ea = ((a & 1) && (a >> 1) < kn) ? 1.0 : 0.0, eb = ((b & 1) && (b >> 1) < kn) ? 1.0 : 0.0;
+            acc += ea * ub + ua * eb + htt * ea * eb;
+        }
+        // curvature of the positions
+        if (!(a & 1) && (b & 1) && (b >> 1) < (a >> 1)) acc += sm.nd.cvw[a >> 1];
+        if ((a & 1) && (b & 1)) {
+            const int la = a >> 1;
+            if (la < 1) acc += sm.nd.cww[1];
+            if (la < 2) acc += sm.nd.cww[2];
+        }
+        return acc;
+    }
+};
+
+// slot loop of the driver: one row per lane and slot.  ROW_BEGIN binds rd / bb / the row state of slot s, ROW_END writes the state
+// back (registers for NS == 1, sm.RS otherwise)
+#define DCBF_ROW_BEGIN                                                                                         \
+    const int r = s * 32 + lane;                                                                               \
+    const RowDesc rd = ROLLED ? M::row_desc(r, Ks, ms, m) : rdA[ROLLED ? 0 : s];                                \
+    const RowBnd bb = ROLLED ? M::row_bounds(P, rd, leg) : rbA[ROLLED ? 0 : s];                                 \
+    double rs_, rzl_, rzu_, rds_, rel_, reu_;                                                                  \
+    if (!ROLLED) { rs_ = rsA[ROLLED ? 0 : s]; rzl_ = rzlA[ROLLED ? 0 : s]; rzu_ = rzuA[ROLLED ? 0 : s];          \
+                   rds_ = rdsA[ROLLED ? 0 : s]; rel_ = relA[ROLLED ? 0 : s]; reu_ = reuA[ROLLED ? 0 : s]; }      \
+    else { rs_ = sm.RS[0][ROLLED ? r : 0]; rzl_ = sm.RS[ROLLED ? 1 : 0][ROLLED ? r : 0]; rzu_ = sm.RS[ROLLED ? 2 : 0][ROLLED ? r : 0]; \
+           rds_ = sm.RS[ROLLED ? 3 : 0][ROLLED ? r : 0]; rel_ = sm.RS[ROLLED ? 4 : 0][ROLLED ? r : 0]; reu_ = sm.RS[ROLLED ? 5 : 0][ROLLED ? r : 0]; }
+#define DCBF_ROW_END                                                                                           \
+    if (!ROLLED) { rsA[ROLLED ? 0 : s] = rs_; rzlA[ROLLED ? 0 : s] = rzl_; rzuA[ROLLED ? 0 : s] = rzu_;          \
+                   rdsA[ROLLED ? 0 : s] = rds_; relA[ROLLED ? 0 : s] = rel_; reuA[ROLLED ? 0 : s] = reu_; }      \
+    else { sm.RS[0][ROLLED ? r : 0] = rs_; sm.RS[ROLLED ? 1 : 0][ROLLED ? r : 0] = rzl_; sm.RS[ROLLED ? 2 : 0][ROLLED ? r : 0] = rzu_; \
+           sm.RS[ROLLED ? 3 : 0][ROLLED ? r : 0] = rds_; sm.RS[ROLLED ? 4 : 0][ROLLED ? r : 0] = rel_; sm.RS[ROLLED ? 5 : 0][ROLLED ? r : 0] = reu_; }
+// descriptor / bounds only (value passes)
+#define DCBF_ROW_DESC                                                                                          \
+    const int r = s * 32 + lane;                                                                               \
+    const RowDesc rd = ROLLED ? M::row_desc(r, Ks, ms, m) : rdA[ROLLED ? 0 : s];
+
+// eight statistics reduced together (interleaved butterflies): four sums and four maxima
+struct Stat8 { double s0, s1, s2, s3, m0, m1, m2, m3; };
+__device__ __forceinline__ void reduce8_inline(Stat8 &t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t.s0 += __shfl_xor_sync(FULL, t.s0, o); t.s1 += __shfl_xor_sync(FULL, t.s1, o);
+        t.s2 += __shfl_xor_sync(FULL, t.s2, o); t.s3 += __shfl_xor_sync(FULL, t.s3, o);
+        t.m0 = fmax(t.m0, __shfl_xor_sync(FULL, t.m0, o)); t.m1 = fmax(t.m1, __shfl_xor_sync(FULL, t.m1, o));
+        t.m2 = fmax(t.m2, __shfl_xor_sync(FULL, t.m2, o)); t.m3 = fmax(t.m3, __shfl_xor_sync(FULL, t.m3, o));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the solver for one problem (all 32 lanes call it with identical arguments).  Inputs in sm: x0, graw, zc (+ model data).
+// ---------------------------------------------------------------------------------------------------------------
+template <class M, int NS>
+__device__ void solve_warp(const BatchIn &in, int b, int lane, int leg, WState &S) {
+    using Sh = WarpShared<M, NS>;
+    constexpr int RP = Sh::RP;
+    constexpr int N = M::N, NK = N * (N + 1) / 2;
+    constexpr int KQ_RHS_ = KQ_K + NK;   // = packed row N of the system: tri(N, j) = NK + j
+    Sh &sm = g_sm<M, NS>;
+    const CtaShared &cs_ = g_cs;
+    const dcbf_params &P = cs_.P;
+    // ---- problem setup -------------------------------------------------------------------------------------------
+    const int Ks = M::template setup<NS>(sm, P, in, b, lane);
+    const int ms = M::rows_per_step(P, Ks);   // rows per step
     const int m = 3 * ms;
     const int mp = (m + 1) & ~1;             // dot products run over row pairs
-    RowDesc rd[NS];
-    RowBnd rb[NS];
-    double rs[NS], rzl[NS], rzu[NS], rds[NS], rel[NS], reu[NS];
+    // Unrolled kernels (one slot; two slots for the LIP models): descriptor, bounds and row state live in registers.  Rolled
+    // kernels: descriptor and bounds are recomputed per slot (a few integer instructions) and the state sits in sm.RS.
+    constexpr bool ROLLED = Sh::ROLLED;
+    constexpr int NREG = ROLLED ? 1 : NS, UNR = ROLLED ? 1 : NS;
+    RowDesc rdA[NREG];
+    RowBnd rbA[NREG];
+    double rsA[NREG], rzlA[NREG], rzuA[NREG], rdsA[NREG], relA[NREG], reuA[NREG];
     int nz_l = 0;
-#pragma unroll
+#pragma unroll UNR
     for (int s = 0; s < NS; s++) {
-        rd[s] = row_desc(s * 32 + lane, Ks, ms, m);
-        rb[s] = row_bounds(P, rd[s], leg);
-        nz_l += (rb[s].has_lo ? 1 : 0) + (rb[s].has_hi ? 1 : 0);
-        rs[s] = rzl[s] = rzu[s] = rds[s] = rel[s] = reu[s] = 0.0;
+        const RowDesc d0 = M::row_desc(s * 32 + lane, Ks, ms, m);
+        const RowBnd b0 = M::row_bounds(P, d0, leg);
+        nz_l += (b0.has_lo ? 1 : 0) + (b0.has_hi ? 1 : 0);
+        if (!ROLLED) {
+            rdA[ROLLED ? 0 : s] = d0; rbA[ROLLED ? 0 : s] = b0;
+            rsA[ROLLED ? 0 : s] = rzlA[ROLLED ? 0 : s] = rzuA[ROLLED ? 0 : s] = rdsA[ROLLED ? 0 : s] = relA[ROLLED ? 0 : s] = reuA[ROLLED ? 0 : s] = 0.0;
+        }
     }
     const int nz = wsumi(nz_l), nrows = m;
-    // the lane's dot products of the three assembly rounds (packed: operand rows, first contributing step, output slot)
-    int dsc[3];
+    // the lane's dot products of the assembly rounds (packed: operand rows, first contributing step, output slot)
+    int dsc[M::NROUND];
 #pragma unroll
-    for (int t = 0; t < 3; t++) dsc[t] = __ldg(&cs_.tab->desc[32 * t + lane]);
-    const int l8 = lane < 9 ? lane : 8;
-    const int rowbase = lane < 10 ? lane * (lane + 1) / 2 : 0;
+    for (int t = 0; t < M::NROUND; t++) dsc[t] = __ldg(M::desc(cs_.tab) + 32 * t + lane);
+    const int ln = lane < N ? lane : N - 1;   // clamped lane: keeps the per-variable sections branch-free
+    const int rowbase = lane < N + 1 ? lane * (lane + 1) / 2 : 0;
     // ---- solver state ------------------------------------------------------------------------------------------------
-    S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4; 
-    sm.cold[C_RESTO_TARGET] = 0.0; sm.cold[C_RESTO_ENTRY] = 0.0; sm.cold[C_THETA_MAX] = 1e300; sm.cold[C_THETA_MIN] = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0; S.tiny = 0;
+    S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4;
+    sm.cold[C_RESTO_TARGET] = 0.0; sm.cold[C_RESTO_ENTRY] = 0.0; sm.cold[C_THETA_MAX] = 1e300; sm.cold[C_THETA_MIN] = 0.0;
+    S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0; S.tiny = 0;
     S.nresto = 0; S.v2_h1 = 0.0; S.v2_h2 = 0.0;
     S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; sm.cold[C_OBJ] = 0.0; sm.cold[C_VIOL] = 0.0;
     const double tol = P.tol;
     const double *stf = &sm.ST[0][0];
-#ifdef DCBF_DBG
-    S.n_fact = S.n_fail = S.n_trial = S.n_pass = 0;
-#endif
 
-    bool nodes_valid = false;      // sm.nodes / trig / nobj (with Hessian terms) already describe zc (staged by the accepted trial)
+    bool nodes_valid = false;      // the node data (with Hessian terms) already describe zc (staged by the accepted trial)
     double carry_log = 0.0;        // sum of log(gaps) at the accepted trial point = barrier term of the next full pass
     bool carry_ok = false;
     for (;;) {
         const bool resto = S.phase == PH_RESTO;
-#ifdef DCBF_DBG
-        S.n_pass++;
-#endif
-        if (!nodes_valid) w_nodes<NS>(sm.zc, lane, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
+        if (!nodes_valid) M::template nodes<NS>(sm.zc, lane, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
         nodes_valid = false;
-        // objective value and gradient (lane a < 9 owns grad[a]):  d node_kn / d foot_l = gx[kn-1-l],  d th_kn / d turn_l = 1
-        const double fobj = sm.nobj[1][0] + sm.nobj[2][0] + sm.nobj[3][0];
-        double grad_a = 0.0;
-        {   // branch-free (see the note at the factorisation): lanes >= 9 compute on clamped indices and select 0
-            const int l = l8 < 6 ? l8 >> 1 : l8 - 6;
-            const int c = l8 < 6 ? 1 + (l8 & 1) : 3;
-#pragma unroll
-            for (int kn = 1; kn <= 3; kn++) {
-                const double wf = cs_.cab[kn - 1][l];
-                const double w = l8 < 6 ? wf : (l < kn ? 1.0 : 0.0);
-                grad_a = fma(sm.nobj[kn][c], w, grad_a);
-            }
-            grad_a = lane < 9 ? grad_a : 0.0;
-        }
+        const double fobj = M::template objective<NS>(sm);
+        const double grad_a = M::template grad<NS>(sm, cs_, lane, ln);   // lane a < N owns grad[a]
         if (S.first) {
             const double gmax = wmax(fabs(grad_a));
             S.sf = gmax > 100.0 ? fdiv(100.0, gmax) : 1.0;
-            if (lane < 3) {   // the objective Hessian staged above used sf = 1: rescale
-#pragma unroll
-                for (int c = 4; c < 10; c++) sm.nobj[lane + 1][c] *= S.sf;
-            }
+            M::template rescale_objective_hessian<NS>(sm, lane, S.sf);   // the objective Hessian staged above used sf = 1
             __syncwarp();
         }
+        const double sf_eff = resto ? 0.0 : S.sf;
         // ---- rows: evaluate, update row state, stage gradients and weights; statistics stay in registers ----------------------
         Stat8 st8;
         st8.s0 = st8.s1 = st8.s2 = st8.s3 = 0.0; st8.m0 = 0.0; st8.m1 = -1e300; st8.m2 = 0.0; st8.m3 = 0.0;
-#pragma unroll
+#pragma unroll UNR
         for (int s = 0; s < NS; s++) {
-            const int r = s * 32 + lane;
+            DCBF_ROW_BEGIN
             RowEval e;
-            eval_row<NS, true>(P, sm, rd[s], sm.zc, e);
-            const RowBnd &bb = rb[s];
+            M::template eval_row<NS, true>(P, sm, rd, sm.zc, e);
             double sig = 0.0, w1 = 0.0, binv = 0.0, y = 0.0;
             double t_rc = 0.0, t_cmin = 1e300, t_cmax = 0.0, t_z = 0.0, t_log = 0.0, t_v2 = 0.0, t_v = 0.0;
-            if (rd[s].type != RT_NONE) {
+            if (rd.type != 0) {
                 double v = 0.0;
                 if (bb.has_lo && e.c < bb.lo) v = e.c - bb.lo;
                 if (bb.has_hi && e.c > bb.hi) v = e.c - bb.hi;
@@ -498,60 +908,51 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                             sv = fmin(fmax(sv, lr + pl), hr - pu);
                         } else if (bb.has_lo) sv = fmax(sv, lr + 1e-2 * fmax(1.0, fabs(lr)));
                         else if (bb.has_hi) sv = fmin(sv, hr - 1e-2 * fmax(1.0, fabs(hr)));
-                        rs[s] = sv; rzl[s] = bb.has_lo ? 1.0 : 0.0; rzu[s] = bb.has_hi ? 1.0 : 0.0;
+                        rs_ = sv; rzl_ = bb.has_lo ? 1.0 : 0.0; rzu_ = bb.has_hi ? 1.0 : 0.0;
                     } else if (S.pending) {
-                        rs[s] += S.alpha * rds[s];
+                        rs_ += S.alpha * rds_;
                         if (bb.has_lo) {
-                            const double gap = rs[s] - lr;
+                            const double gap = rs_ - lr;
                             const double mg = fdiv(S.mu, gap);
-                            rzl[s] = fmax(fmin(rzl[s] + S.alpha_z * rel[s], DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
+                            rzl_ = fmax(fmin(rzl_ + S.alpha_z * rel_, DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
                         }
                         if (bb.has_hi) {
-                            const double gap = hr - rs[s];
+                            const double gap = hr - rs_;
                             const double mg = fdiv(S.mu, gap);
-                            rzu[s] = fmax(fmin(rzu[s] + S.alpha_z * reu[s], DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
+                            rzu_ = fmax(fmin(rzu_ + S.alpha_z * reu_, DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
                         }
                     }
-                    const double rc = e.c - rs[s];
+                    const double rc = e.c - rs_;
                     double lp = 1.0;
                     if (bb.has_lo) {
-                        const double gap = rs[s] - lr, inv = frcp(gap);
-                        sig += rzl[s] * inv; binv += inv; y -= rzl[s];
-                        const double cz = gap * rzl[s];
-                        t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzl[s];
-                        lp *= gap; rel[s] = inv;
+                        const double gap = rs_ - lr, inv = frcp(gap);
+                        sig += rzl_ * inv; binv += inv; y -= rzl_;
+                        const double cz = gap * rzl_;
+                        t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzl_;
+                        lp *= gap; rel_ = inv;
                     }
                     if (bb.has_hi) {
-                        const double gap = hr - rs[s], inv = frcp(gap);
-                        sig += rzu[s] * inv; binv -= inv; y += rzu[s];
-                        const double cz = gap * rzu[s];
-                        t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzu[s];
-                        lp *= gap; reu[s] = inv;
+                        const double gap = hr - rs_, inv = frcp(gap);
+                        sig += rzu_ * inv; binv -= inv; y += rzu_;
+                        const double cz = gap * rzu_;
+                        t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzu_;
+                        lp *= gap; reu_ = inv;
                     }
                     if (!carry_ok) t_log = dlog(lp);
-                    rds[s] = rc;
+                    rds_ = rc;
                     t_rc = fabs(rc);
                     w1 = sig * rc;
                 }
             }
             // stage the transposed row (rows beyond m stage zeros so that the dot products need no guards)
+            M::template stage_row<NS>(sm, cs_, rd, e, sig, y, r);
             {
-                const double *ab = cs_.cab[rd[s].cls];
-                const int i = rd[s].step;
-                double *col = &sm.ST[0][r];
-#pragma unroll
-                for (int l = 0; l < 3; l++) {
-                    const double ca = ab[l], cb = ab[3 + l];
-                    const double gxv = fma(ca, e.p0, cb * e.q0), gyv = fma(ca, e.p1, cb * e.q1);
-                    const double gtv = (l <= i ? e.t_all : 0.0) + (l == i ? e.t_own : 0.0);
-                    col[(2 * l) * RP] = gxv; col[(2 * l + 1) * RP] = gyv; col[(6 + l) * RP] = gtv;
-                    col[(9 + 2 * l) * RP] = sig * gxv; col[(9 + 2 * l + 1) * RP] = sig * gyv; col[(9 + 6 + l) * RP] = sig * gtv;
-                }
-                col[18 * RP] = sig; col[19 * RP] = w1; col[20 * RP] = binv; col[21 * RP] = y;
+                double *col = &sm.ST[2 * N][r];
+                col[0] = sig; col[RP] = w1; col[2 * RP] = binv; col[3 * RP] = y;
             }
-            sm.HQ[r][0] = y * e.hq0; sm.HQ[r][1] = y * e.hq1; sm.HQ[r][2] = y * e.hq2;
             st8.s0 += t_rc; st8.s1 += t_z; st8.s2 += t_log; st8.s3 += t_v2;
             st8.m0 = fmax(st8.m0, t_rc); st8.m1 = fmax(st8.m1, -t_cmin); st8.m2 = fmax(st8.m2, t_cmax); st8.m3 = fmax(st8.m3, t_v);
+            DCBF_ROW_END
         }
         __syncwarp();   // the row branches reconverge here, before the shuffles
         reduce8_inline(st8);
@@ -559,50 +960,27 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                      st_cmin = -st8.m1, st_cmax = st8.m2, st_vmax = st8.m3;
         carry_ok = false;
         sm.cold[C_ST_THETA] = st_theta; sm.cold[C_ST_LOGSUM] = st_logsum; sm.cold[C_ST_V2] = st_v2; sm.cold[C_ST_VMAX] = st_vmax;
-        // ---- node Hessians -> the 27 sources of the Hessian table ---------------------------------------------------------------
-        {
-            const double gm1 = P.gamma - 1.0;
-            const double *yv = sm.ST[21];
-            const int lp = lane - 16;
-            if ((unsigned)lp < 9u) {   // position block on lanes 16..24: node kn = lp/3 + 1, component lp % 3
-                const int kn = lp / 3 + 1, c = lp % 3;
-                double acc = sm.nobj[kn][4 + c];
-                for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * ms + j][c];
-                if (kn < 3) for (int j = 0; j < Ks; j++) acc = fma(gm1, sm.HQ[kn * ms + j][c], acc);
-                sm.NHf[8 * (kn - 1) + c] = acc;
-            } else if (lane < 3) {     // heading / velocity entries of node kn = lane + 1 (rows of step kn - 1)
-                const int kn = lane + 1, i = kn - 1, base = i * ms + Ks;
-                double Yx = yv[base], Yy = yv[base + 1];
-                if (has_fen) Yx += yv[base + 4] + yv[base + 5];
-                const double sn = sm.trig[kn][0], cs = sm.trig[kn][1];
-                const double vx = sm.nodes[kn][2], vy = sm.nodes[kn][3];
-                const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
-                double *H = &sm.NHf[8 * i];
-                H[3] = sm.nobj[kn][7]; H[4] = sm.nobj[kn][8];
-                H[5] = sm.nobj[kn][9] - (Yx * vbx + Yy * vby);
-                H[6] = -sn * Yx - cs * Yy; H[7] = cs * Yx - sn * Yy;
-                sm.NHf[24 + i] = 2.0 * yv[base + 2];
-            }
-        }
+        // ---- second-order sources of the model --------------------------------------------------------------------------------
+        M::template hess_sources<NS>(sm, P, lane, Ks, ms);
         __syncwarp();
-        // ---- condensed matrix and J^T vectors: three rounds of dot products over row pairs ---------------------------------------
+        if (M::HAS_CURV) {
+            M::template hess_curvature<NS>(sm, lane, sf_eff, sm.zc);
+            __syncwarp();
+        }
+        // ---- condensed matrix and J^T vectors: rounds of dot products over row pairs ---------------------------------------------
 #pragma unroll
-        for (int t = 0; t < 3; t++) {
+        for (int t = 0; t < M::NROUND; t++) {
             const int d = dsc[t];
             if (d >= 0) {
                 const double *pp = stf + (d & 0xff) * RP, *pq = stf + ((d >> 8) & 0xff) * RP;
-                const int lo = (((d >> 16) & 0xf) * ms) & ~1, eo = d >> 20;
+                const int lo = M::class_start((d >> 16) & 0xf, Ks, ms) & ~1, eo = d >> 20;
                 double acc0 = 0.0, acc1 = 0.0;
                 for (int r = mp - 2; r >= lo; r -= 2) {
                     const double2 u = *reinterpret_cast<const double2 *>(pp + r), v = *reinterpret_cast<const double2 *>(pq + r);
                     acc0 = fma(u.x, v.x, acc0); acc1 = fma(u.y, v.y, acc1);
                 }
                 double acc = acc0 + acc1;
-                if (eo >= KQ_K) {   // Lagrangian Hessian through the table
-                    const int e = eo - KQ_K;
-#pragma unroll
-                    for (int h = 0; h < NHT; h++) acc = fma(cs_.hc[h][e], sm.NHf[cs_.hs[h][e]], acc);
-                }
+                if (eo >= KQ_K) acc += M::template hess_entry<NS>(sm, cs_, eo - KQ_K, sf_eff);   // Lagrangian Hessian
                 sm.KQ[eo] = acc;
             }
         }
@@ -615,7 +993,7 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
         double rhs_a = 0.0;
         if (!resto) {
             if (S.first) { sm.cold[C_THETA_MAX] = 1e4 * fmax(1.0, st_theta); sm.cold[C_THETA_MIN] = 1e-4 * fmax(1.0, st_theta); S.first = false; }
-            const double dinf = wmax(lane < 9 ? fabs(fma(S.sf, grad_a, q[18 + l8])) : 0.0);
+            const double dinf = wmax(lane < N ? fabs(fma(S.sf, grad_a, q[2 * N + ln])) : 0.0);
             const double sd = fmax(100.0, fdiv(2.0 * st_zsum, (double)(nrows + nz))) * 0.01;
             const double sc = fmax(100.0, fdiv(st_zsum, (double)(nz > 0 ? nz : 1))) * 0.01;
             const double isd = frcp(sd), isc = frcp(sc);
@@ -645,10 +1023,10 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                 S.iters++;
                 continue;
             }
-            rhs_a = -S.sf * grad_a - q[l8] + S.mu * q[9 + l8];
+            rhs_a = -S.sf * grad_a - q[ln] + S.mu * q[N + ln];
         } else {
             if (st_vmax <= sm.cold[C_RESTO_TARGET]) { S.phase = PH_MAIN; S.reinit = true; continue; }
-            const double gn = wmax(lane < 9 ? fabs(q[l8]) : 0.0);
+            const double gn = wmax(lane < N ? fabs(q[ln]) : 0.0);
             const bool stationary = gn <= 1e-10 * fmax(1.0, st_vmax) || S.lm_lambda > 1e12;
             if (stationary) {
                 if (st_vmax > P.constr_viol_tol) { S.status = 2; break; }
@@ -656,9 +1034,9 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                 S.phase = PH_MAIN; S.reinit = true; continue;
             }
             if (S.iters >= P.max_iter) { S.status = -1; break; }
-            rhs_a = -q[l8];
+            rhs_a = -q[ln];
         }
-        sm.KQ[KQ_RHS + lane] = rhs_a;   // = packed row 9 of the system: tri(9, j) = 45 + j (lanes >= 9 write the tail)
+        sm.KQ[KQ_RHS_ + lane] = rhs_a;   // packed row N of the system (lanes >= N write the tail)
         __syncwarp();
         // ---- restoration: Levenberg-Marquardt trials reuse the assembled K while lambda is escalated ---------------------------
         // ---- main phase: one factorisation with inertia correction by delta ----------------------------------------------------
@@ -668,28 +1046,19 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
             double shift = resto ? S.lm_lambda : 0.0;
             bool ok = false;
             for (int tr = 0; tr < 48; tr++) {
-                // lanes 0..8 own the rows of K, lane 9 the right-hand side (its "row" of the factor is L^-1 rhs).  Branch-free:
-                // every lane runs the column arithmetic (idle lanes on harmless operands), only the stores are predicated,
+                // lanes 0..N-1 own the rows of K, lane N the right-hand side (its "row" of the factor is L^-1 rhs).  Branch-free:
+                // every lane runs the column arithmetic (idle lanes on harmless operands), only the store address is selected,
                 // so the warp reaches each shuffle converged.
-                double Lrow[9];
+                double Lrow[N];
                 ok = true;
-#ifdef DCBF_DBG
-                S.n_fact++;
-#endif
 #pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    const bool act = lane >= j && lane < 10;
+                for (int j = 0; j < N; j++) {
+                    const bool act = lane >= j && lane < N + 1;
                     double s_ = sm.KQ[KQ_K + rowbase + j] + (lane == j ? shift : 0.0);
 #pragma unroll
                     for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[tri(j, c)], s_);
                     const double d = __shfl_sync(FULL, s_, j);
-                    if (!(d > 1e-14)) {
-                        ok = false;
-#ifdef DCBF_DBG
-                        S.n_fail++;
-#endif
-                        break;
-                    }
+                    if (!(d > 1e-14)) { ok = false; break; }
                     const double rinv = drsqrt(d);
                     Lrow[j] = lane == j ? rinv : s_ * rinv;   // diagonal stored as its reciprocal
                     sm.Lf[act ? rowbase + j : 56 + lane] = Lrow[j];
@@ -706,14 +1075,13 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
                 continue;
             }
             if (!resto && shift > 0.0) S.delta_last = shift;
-            // backward substitution: lane i holds component i, starting from y = L^-1 rhs (row 9 of the factor); branch-free
+            // backward substitution: lane i holds component i, starting from y = L^-1 rhs (row N of the factor); branch-free
             {
-                const int li = l8;
-                double bi = sm.Lf[45 + li];
+                double bi = sm.Lf[NK + ln];
 #pragma unroll
-                for (int c = 8; c >= 0; c--) {
+                for (int c = N - 1; c >= 0; c--) {
                     const double xc = __shfl_sync(FULL, bi * sm.Lf[tri(c, c)], c);
-                    const double lc = sm.Lf[tri(c, 0) + (li < c ? li : 0)];
+                    const double lc = sm.Lf[tri(c, 0) + (ln < c ? ln : 0)];
                     bi = lane == c ? xc : (lane < c ? fma(-lc, xc, bi) : bi);
                 }
                 sm.dz[lane] = bi;
@@ -721,18 +1089,20 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
             __syncwarp();
             if (!resto) break;
             // Levenberg-Marquardt trial at full step (violation only)
-            sm.zt[lane] = sm.zc[l8] + sm.dz[l8];
+            sm.zt[lane] = sm.zc[ln] + sm.dz[ln];
             __syncwarp();
-            w_nodes<NS>(sm.zt, lane, 0.0, false);
+            M::template nodes<NS>(sm.zt, lane, 0.0, false);
             v2t = 0.0; vmt = 0.0;
-#pragma unroll
+#pragma unroll UNR
             for (int s = 0; s < NS; s++) {
-                if (rd[s].type == RT_NONE) continue;
+                DCBF_ROW_DESC
+                if (rd.type == 0) continue;
+                const RowBnd bb = ROLLED ? M::row_bounds(P, rd, leg) : rbA[ROLLED ? 0 : s];
                 RowEval e;
-                eval_row<NS, false>(P, sm, rd[s], sm.zt, e);
+                M::template eval_row<NS, false>(P, sm, rd, sm.zt, e);
                 double v = 0.0;
-                if (rb[s].has_lo && e.c < rb[s].lo) v = e.c - rb[s].lo;
-                if (rb[s].has_hi && e.c > rb[s].hi) v = e.c - rb[s].hi;
+                if (bb.has_lo && e.c < bb.lo) v = e.c - bb.lo;
+                if (bb.has_hi && e.c > bb.hi) v = e.c - bb.hi;
                 v2t += v * v; vmt = fmax(vmt, fabs(v));
             }
             __syncwarp();
@@ -748,7 +1118,7 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
         if (S.status == -3) break;
         if (resto) {
             if (lm_accept) {
-                const double dn = wmax(fabs(sm.dz[l8]));
+                const double dn = wmax(lane < N ? fabs(sm.dz[ln]) : 0.0);
                 sm.zc[lane] = sm.zt[lane];
                 S.iters++;
                 S.lm_lambda = fmax(S.lm_lambda * 0.2, 1e-12);
@@ -765,33 +1135,34 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
         double amax = 1.0, az = 1.0, dphi = 0.0;
         {
             const double tau = fmax(0.99, 1.0 - S.mu);
-            dphi = S.sf * grad_a * sm.dz[l8];
-#pragma unroll
+            dphi = S.sf * grad_a * sm.dz[ln];
+#pragma unroll UNR
             for (int s = 0; s < NS; s++) {
-                if (rd[s].type == RT_NONE) continue;
-                const int r = s * 32 + lane;
+                DCBF_ROW_BEGIN
+                if (rd.type == 0) continue;
                 double jd = 0.0;
 #pragma unroll
-                for (int a = 0; a < 9; a++) jd = fma(sm.ST[a][r], sm.dz[a], jd);
-                const RowBnd &e = rb[s];
-                const double d = jd + rds[s];
-                rds[s] = d;
+                for (int a = 0; a < N; a++) jd = fma(sm.ST[a][r], sm.dz[a], jd);
+                const RowBnd &e = bb;
+                const double d = jd + rds_;
+                rds_ = d;
                 if (e.has_lo) {
-                    const double inv = rel[s], gap = rs[s] - relax_lo(e.lo);
-                    const double dzl = S.mu * inv - rzl[s] - rzl[s] * inv * d;
-                    rel[s] = dzl;
+                    const double inv = rel_, gap = rs_ - relax_lo(e.lo);
+                    const double dzl = S.mu * inv - rzl_ - rzl_ * inv * d;
+                    rel_ = dzl;
                     dphi -= S.mu * d * inv;
                     if (d < 0.0) amax = fmin(amax, fdiv(-tau * gap, d));
-                    if (dzl < 0.0) az = fmin(az, fdiv(-tau * rzl[s], dzl));
+                    if (dzl < 0.0) az = fmin(az, fdiv(-tau * rzl_, dzl));
                 }
                 if (e.has_hi) {
-                    const double inv = reu[s], gap = relax_hi(e.hi) - rs[s];
-                    const double dzu = S.mu * inv - rzu[s] + rzu[s] * inv * d;
-                    reu[s] = dzu;
+                    const double inv = reu_, gap = relax_hi(e.hi) - rs_;
+                    const double dzu = S.mu * inv - rzu_ + rzu_ * inv * d;
+                    reu_ = dzu;
                     dphi += S.mu * d * inv;
                     if (d > 0.0) amax = fmin(amax, fdiv(tau * gap, d));
-                    if (dzu < 0.0) az = fmin(az, fdiv(-tau * rzu[s], dzu));
+                    if (dzu < 0.0) az = fmin(az, fdiv(-tau * rzu_, dzu));
                 }
+                DCBF_ROW_END
             }
             __syncwarp();
 #pragma unroll
@@ -808,25 +1179,25 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
         double alpha = amax;
         int accepted = 0;
         for (int ls = 0; ls < DCBF_LS_MAX; ls++, alpha *= 0.5) {
-            sm.zt[lane] = fma(alpha, sm.dz[l8], sm.zc[l8]);
+            sm.zt[lane] = fma(alpha, sm.dz[ln], sm.zc[ln]);
             __syncwarp();
-#ifdef DCBF_DBG
-            S.n_trial++;
-#endif
-            w_nodes<NS>(sm.zt, lane, S.sf, true);
-            const double ft = sm.nobj[1][0] + sm.nobj[2][0] + sm.nobj[3][0];
+            M::template nodes<NS>(sm.zt, lane, S.sf, true);
+            const double ft = M::template objective<NS>(sm);
             double th_t = 0.0, lg_t = 0.0;
             bool okv = true;
-#pragma unroll
+#pragma unroll UNR
             for (int s = 0; s < NS; s++) {
-                if (rd[s].type == RT_NONE) continue;
+                DCBF_ROW_DESC
+                if (rd.type == 0) continue;
+                const RowBnd bb = ROLLED ? M::row_bounds(P, rd, leg) : rbA[ROLLED ? 0 : s];
+                const double rs_ = ROLLED ? sm.RS[0][ROLLED ? r : 0] : rsA[ROLLED ? 0 : s], rds_ = ROLLED ? sm.RS[ROLLED ? 3 : 0][ROLLED ? r : 0] : rdsA[ROLLED ? 0 : s];
                 RowEval e;
-                eval_row<NS, false>(P, sm, rd[s], sm.zt, e);
-                const double stv = rs[s] + alpha * rds[s];
+                M::template eval_row<NS, false>(P, sm, rd, sm.zt, e);
+                const double stv = rs_ + alpha * rds_;
                 th_t += fabs(e.c - stv);
                 double lp = 1.0;
-                if (rb[s].has_lo) { const double gap = stv - relax_lo(rb[s].lo); if (!(gap > 0.0)) okv = false; lp *= gap; }
-                if (rb[s].has_hi) { const double gap = relax_hi(rb[s].hi) - stv; if (!(gap > 0.0)) okv = false; lp *= gap; }
+                if (bb.has_lo) { const double gap = stv - relax_lo(bb.lo); if (!(gap > 0.0)) okv = false; lp *= gap; }
+                if (bb.has_hi) { const double gap = relax_hi(bb.hi) - stv; if (!(gap > 0.0)) okv = false; lp *= gap; }
                 lg_t += dlog(lp);
             }
             __syncwarp();
@@ -866,30 +1237,31 @@ __device__ void solve_lip_warp(const BatchIn &in, int b, int lane, int leg, WSta
         if (alpha < 1e-2 && sm.cold[C_ST_VMAX] > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
         S.iters++;
     }
-    // every exit leaves the loop right after a full pass (or before any trial), so sm.nodes is the rollout of the final iterate
+    // every exit leaves the loop right after a full pass (or before any trial), so the node data are the rollout of the final iterate
 }
 
 template <int NS>
-__device__ __forceinline__ bool w_close(const dcbf_params &P, const WarpShared<NS> &sm) {
+__device__ __forceinline__ bool w_close(const dcbf_params &P, const WarpShared<LipW, NS> &sm) {
     bool close = false;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const double dxg = sm.nodes[i + 1][0] - sm.graw[0], dyg = sm.nodes[i + 1][1] - sm.graw[1];
+        const double dxg = sm.nd.nodes[i + 1][0] - sm.graw[0], dyg = sm.nd.nodes[i + 1][1] - sm.graw[1];
         if ((i == 0 || P.close_any) && sqrt(dxg * dxg + dyg * dyg) <= P.close_radius) close = true;
     }
     return close;
 }
 
 // per-CTA staging of the constants; zeroes the pad columns of the staged rows
-template <int NS>
+template <class M, int NS>
 __device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K, const WarpTables *tab, int lane) {
-    WarpShared<NS> &sm = g_sm<NS>;
-    if (lane == 0) { g_cs.P = P; g_cs.K = K; g_cs.tab = tab; sm.NHf[NSRC] = 0.0; }
+    WarpShared<M, NS> &sm = g_sm<M, NS>;
+    if (lane == 0) { g_cs.P = P; g_cs.K = K; g_cs.tab = tab; }
     for (int t = lane; t < 60; t += 32) (&g_cs.cab[0][0])[t] = __ldg(&tab->cab[0][0] + t);
     for (int t = lane; t < NHT * 48; t += 32) (&g_cs.hc[0][0])[t] = __ldg(&tab->hc[0][0] + t);
     for (int t = lane; t < NHT * 48 / 4; t += 32)
         reinterpret_cast<unsigned *>(&g_cs.hs[0][0])[t] = __ldg(reinterpret_cast<const unsigned *>(&tab->hs[0][0]) + t);
-    for (int t = lane; t < 44; t += 32) sm.ST[t >> 1][32 * NS + (t & 1)] = 0.0;
+    if (lane < 24) g_cs.sm_dd[lane] = __ldg(&tab->sm_dd[lane]);
+    for (int t = lane; t < 2 * WarpShared<M, NS>::NST; t += 32) sm.ST[t >> 1][32 * NS + (t & 1)] = 0.0;
     __syncwarp();
 }
 
