@@ -10,7 +10,7 @@ rate = N * 4096 * steps / max-over-ranks(device time).
   value      inputs resident in HBM, CUDA-event time of the solve kernel launches only (L2 flushed between steps)
   e2e        the same batch through the host-buffer C-ABI call dcbf_solve_host: pinned staging, H2D copy, kernel,
              D2H copy of the full result (u, plans, status, ...) every step
-  roofline   FP64-pipe roofline of solve_lip_kernel: algorithmic flop = sum_i iters_i * F_iter (SURVEY.md 8(d) formula)
+  roofline   FP64-pipe roofline of solve_lip_warp_kernel<1> (one problem per warp): algorithmic flop = sum_i iters_i * F_iter (SURVEY.md 8(d) formula)
              over the measured kernel time, against the FP64 DFMA peak measured on this GPU by dcbf_fp64_peak_tflops
              (MEASURED_PEAKS.json carries no FP64 figure); `hbm` sub-object: batch I/O bytes / time vs measured HBM copy
   cpu_baseline  the oracle's C port (oracle/dcbf_oracle.c) on all host threads over the same 4096 scenarios
@@ -47,7 +47,7 @@ def f_iter(n: int, m: int, m_nl: int, m_b: int, kc: int, ke: int, form: str) -> 
 
 
 F_ITER_SIG_K6 = f_iter(9, 30, 27, 0, 6, 0, "sig_step")   # = 8455
-NCU_DRAM_BYTES_PER_LAUNCH = 1.93e6   # measured once per change with ncu (profiles/r01_summary.md); not re-measured at run time
+NCU_DRAM_BYTES_PER_LAUNCH = 1.45e6   # measured once per change with ncu (profiles/r02_summary.md); not re-measured at run time
 
 
 def io_bytes_per_solve(kc: int) -> int:
@@ -224,7 +224,7 @@ def main():
 
     extra = {}
     if args.sweep and rank == 0:
-        for form, Bs in (("sig_step", 65536), ("sig_step", 1 << 20), ("modi", 65536), ("dd", 65536)):
+        for form, Bs in (("sig_step", 65536), ("sig_step", 1 << 20), ("modi", 65536), ("dd", 4096), ("dd", 65536)):
             s2 = scenarios.make_batch(form, Bs, seed=SEED + 1)
             sv = DcbfSolver(form, device=local)
             sv.set_fields(s2.cir, s2.elp if s2.elp.shape[1] else None)
@@ -241,6 +241,23 @@ def main():
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1))
             extra[f"{form}_{Bs}"] = {"solves_per_s": Bs / (best * 1e-3), "ms": best, "mean_iters": float(r.iters.float().mean())}
+        # control tick (dcbf_tick) on the modi shape: prediction + warm-start rule + re-plan + dense plan trajectory [B,126,2]
+        s3 = scenarios.make_batch("modi", 65536, seed=SEED + 1)
+        sv = DcbfSolver("modi", device=local)
+        sv.set_fields(s3.cir, s3.elp)
+        targs = [t(s3.x0[:, 0:2], torch.float64), t(s3.x0[:, 2:4], torch.float64), t(s3.x0[:, 4], torch.float64),
+                 t(np.concatenate([s3.x0[:, 0:2], np.zeros((65536, 1))], axis=1), torch.float64), t(np.full(65536, 0.1), torch.float64)]
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            e0.record()
+            tk = sv.tick(targs[0], targs[1], targs[2], targs[3], targs[4], t(s3.goal, torch.float64), t(s3.leg, torch.int32), field=t(s3.field, torch.int32))
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        extra["tick_modi_65536"] = {"ticks_per_s": 65536 / (best * 1e-3), "ms": best, "pos_det_bytes": int(tk["pos_det"].numel() * 8)}
+        del tk
         # config 5 shape, one GPU's share at 8 GPUs: closed-loop rollout, 131072 scenarios x 50 steps, no host round trips
         s5 = scenarios.make_batch("sig_step", 131072, seed=SEED + 3)
         sv = DcbfSolver("sig_step", device=local)
@@ -298,7 +315,7 @@ def main():
             "p50_solve_us": float(np.median(lat)), "p95_solve_us": float(np.percentile(lat, 95)),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of solve_lip_warp_kernel<1>, B = 4096)",
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r02_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of solve_lip_warp_kernel<1>, B = 4096)",
                          "kernel": "solve_lip_warp_kernel<1> (one problem per warp)", "algorithmic_bytes": B * io_bytes_per_solve(6),
                          "peak_source": "measured on this GPU by dcbf_fp64_peak_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
                          "flop_per_iter": F_ITER_SIG_K6, "iters_per_step": int(iters.sum()),

@@ -150,6 +150,29 @@ def test_both_kernel_families_match_oracle(gpu, monkeypatch, mode, form, B, seed
     np.testing.assert_allclose(ro["traj"][:, 0, :5].cpu().numpy(), one.x_plan[:, 0].cpu().numpy(), atol=1e-12)
 
 
+@pytest.mark.parametrize("mode", ["thread", "warp"])
+def test_dd_kernel_families_match_oracle(gpu, monkeypatch, mode):
+    """differential-drive formulation: the per-thread kernel and the warp kernel (wp::DdW, 6 variables, node Jacobians per
+    iterate) against the oracle, and against each other on the plan"""
+    B = 2048
+    sc = scenarios.make_batch("dd", B, seed=23)
+    P = c_oracle.params("dd", max_iter=300)
+    ref = c_oracle.solve_batch(P, sc.x0, sc.goal, sc.leg, sc.cir, sc.elp, sc.warm, field=sc.field, last_u=sc.last_u,
+                               threads=os.cpu_count() or 4)
+    monkeypatch.setenv("DCBF_KERNEL", mode)
+    s = _solver(gpu, "dd", sc, max_iter=300)
+    res = s.solve(sc.x0, sc.goal, None, sc.warm, field=sc.field, last_u=sc.last_u)
+    same_class, both, dp, rel = _agreement("dd", res, ref, B)
+    assert same_class.mean() >= 0.995 and np.mean(dp[both] <= POS_TOL) >= 0.995 and np.mean(rel[both] <= OBJ_TOL) >= 0.995
+    monkeypatch.setenv("DCBF_KERNEL", "thread" if mode == "warp" else "warp")
+    s2 = _solver(gpu, "dd", sc, max_iter=300)
+    other = s2.solve(sc.x0, sc.goal, None, sc.warm, field=sc.field, last_u=sc.last_u)
+    st, st2 = res.status.cpu().numpy(), other.status.cpu().numpy()
+    assert np.mean(st == st2) >= 0.998
+    ok = (st == 0) & (st2 == 0)
+    assert np.max(np.abs(res.u.cpu().numpy()[ok] - other.u.cpu().numpy()[ok])) <= POS_TOL
+
+
 def test_warm_started_resolves_match_oracle(gpu):
     """config 2: "half of the batch additionally re-solved warm from the shifted solution of a first solve"
     (warm start u0 = [x_2, x_3, x_3] at the advanced state x_1, flipped leg: MPC_LIP_sig_step.py:188-189,565-575)."""
