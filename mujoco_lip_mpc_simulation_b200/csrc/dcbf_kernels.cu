@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
 // One warp per CTA: the block scheduler hands a freed warp slot to the next problem (iteration counts differ by 3x), and the
 // scratch lives in static shared memory.
 #ifndef DCBF_WARP_MIN_CTAS
-#define DCBF_WARP_MIN_CTAS(NS) ((NS) == 1 ? 12 : 8)   /* register budget 168 / 255: spills to local memory cost more than the lost warps */
+#define DCBF_WARP_MIN_CTAS(NS) (((NS) == 1 ? 12 : 8) / wp::Wpc<wp::LipW, NS>::v)   /* 12 / 8 / 8 warps per SM: register budget 168 / 255 / 255 (spills cost more than the lost warps) */
 #endif
 #ifndef DCBF_WARP_GRID_CAP
 #define DCBF_WARP_GRID_CAP 64   /* CTAs per SM in the grid (grid-stride loop beyond); 0 = one CTA per problem */
@@ -183,18 +183,20 @@ __device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<wp
     __syncwarp();
 }
 
+// Persistent CTAs of WPC warps; every warp pulls its next problem from `counter` (problem i of the index list `order` when the
+// batch was split by size class) and the warps of a CTA meet at the top of every interior-point iteration (wp::cta_tick).
 template <int NS>
-__global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out,
-                                                                                       const int *__restrict__ order, const int *__restrict__ count) {
-    wp::WarpShared<wp::LipW, NS> &sm = wp::g_sm<wp::LipW, NS>;
+__global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out,
+                                                                                       const int *__restrict__ order, const int *__restrict__ count, int *counter) {
+    constexpr int W = wp::Wpc<wp::LipW, NS>::v;
+    const int lane = wp::lane_id(), wid = W > 1 ? wp::warp_in_cta() : 0;
+    wp::WarpShared<wp::LipW, NS> &sm = wp::g_sm<wp::LipW, NS>[wid];
     const wp::CtaShared &cs_ = wp::g_cs;
-    const int lane = wp::lane_id();
-    // with an index list (size-class split, see classify_lip_kernel) the grid covers the whole batch and the CTAs beyond the
-    // list's length leave at once
     const int n = count ? *count : B;
-    if ((int)blockIdx.x >= n) return;
-    wp::stage_cta<wp::LipW, NS>(P, K, tab, lane);
-    for (int i_ = blockIdx.x; i_ < n; i_ += gridDim.x) {
+    wp::stage_cta<wp::LipW, NS>(P, K, tab, lane, wid);
+    for (;;) {
+        const int i_ = wp::next_problem(counter, lane);
+        if (i_ >= n) break;
         const int b = order ? order[i_] : i_;
         if (lane == 0) {
             double x0[5], u0[15], g[2];
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_ker
         }
         const int leg = in.leg ? in.leg[b] : 1;
         wp::WState S;
-        wp::solve_warp<wp::LipW, NS>(in, b, lane, leg, S);
+        wp::solve_warp<wp::LipW, NS>(in, b, lane, wid, leg, S);
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
         if (lane < 15) {
             const double v = sm.nd.nodes[lane / 5 + 1][lane % 5];
@@ -234,22 +236,26 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_ker
         }
         __syncwarp();
     }
+    if (W > 1) { while (wp::cta_tick(0) > 0) {} }   // out of work: keep arriving until the other warps of the CTA are done
 }
 
 // differential-drive formulation, one problem per warp (wp::DdW): same driver, 6 variables, node Jacobians per iterate
 template <int NS>
-__global__ void __launch_bounds__(32, 12) solve_dd_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out) {
-    wp::WarpShared<wp::DdW, NS> &sm = wp::g_sm<wp::DdW, NS>;
+__global__ void __launch_bounds__(32 * wp::Wpc<wp::DdW, NS>::v, 12 / wp::Wpc<wp::DdW, NS>::v) solve_dd_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out, int *counter) {
+    constexpr int W = wp::Wpc<wp::DdW, NS>::v;
+    const int lane = wp::lane_id(), wid = W > 1 ? wp::warp_in_cta() : 0;
+    wp::WarpShared<wp::DdW, NS> &sm = wp::g_sm<wp::DdW, NS>[wid];
     const wp::CtaShared &cs_ = wp::g_cs;
-    const int lane = wp::lane_id();
-    wp::stage_cta<wp::DdW, NS>(P, K, tab, lane);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    wp::stage_cta<wp::DdW, NS>(P, K, tab, lane, wid);
+    for (;;) {
+        const int b = wp::next_problem(counter, lane);
+        if (b >= B) break;
         if (lane < 3) sm.x0[lane] = in.x0[3 * (size_t)b + lane];
         if (lane >= 8 && lane < 10) { sm.graw[lane - 8] = in.goal[2 * (size_t)b + lane - 8]; sm.nd.last_u[lane - 8] = in.last_u ? in.last_u[2 * (size_t)b + lane - 8] : 0.0; }
         if (lane >= 16 && lane < 22) sm.zc[lane - 16] = in.warm[6 * (size_t)b + lane - 16];
         __syncwarp();
         wp::WState S;
-        wp::solve_warp<wp::DdW, NS>(in, b, lane, 1, S);
+        wp::solve_warp<wp::DdW, NS>(in, b, lane, wid, 1, S);
         // ---- outputs: plan re-roll of gen_dd_control (MPC_DD_sig_step.py:83-99) = the staged nodes of the final iterate ------
         if (lane < 9 && out.x_plan) out.x_plan[9 * (size_t)b + lane] = sm.nd.nodes[lane / 3 + 1][lane % 3];
         if (lane < 6 && out.u) out.u[6 * (size_t)b + lane] = sm.zc[lane];
@@ -265,15 +271,19 @@ __global__ void __launch_bounds__(32, 12) solve_dd_warp_kernel(dcbf_params P, Co
         }
         __syncwarp();
     }
+    if (W > 1) { while (wp::cta_tick(0) > 0) {} }
 }
 
 template <int NS>
-__global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, int steps, BatchIn in, RolloutOut out) {
-    wp::WarpShared<wp::LipW, NS> &sm = wp::g_sm<wp::LipW, NS>;
+__global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, int steps, BatchIn in, RolloutOut out, int *counter) {
+    constexpr int W = wp::Wpc<wp::LipW, NS>::v;
+    const int lane = wp::lane_id(), wid = W > 1 ? wp::warp_in_cta() : 0;
+    wp::WarpShared<wp::LipW, NS> &sm = wp::g_sm<wp::LipW, NS>[wid];
     const wp::CtaShared &cs_ = wp::g_cs;
-    const int lane = wp::lane_id();
-    wp::stage_cta<wp::LipW, NS>(P, K, tab, lane);
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    wp::stage_cta<wp::LipW, NS>(P, K, tab, lane, wid);
+    for (;;) {
+        const int b = wp::next_problem(counter, lane);
+        if (b >= B) break;
         int leg = in.leg ? in.leg[b] : 1;
         if (lane == 0) {
             double x0[5], u0[15], g[2];
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_k
         int done = 0, ninf = 0, tot = 0;
         for (int st = 0; st < steps; st++) {
             wp::WState S;
-            wp::solve_warp<wp::LipW, NS>(in, b, lane, leg, S);
+            wp::solve_warp<wp::LipW, NS>(in, b, lane, wid, leg, S);
             tot += S.iters;
             if (S.status == 2) ninf++;
             const bool close = wp::w_close<NS>(cs_.P, sm);
@@ -327,6 +337,7 @@ __global__ void __launch_bounds__(32, DCBF_WARP_MIN_CTAS(NS)) rollout_lip_warp_k
         }
         __syncwarp();
     }
+    if (W > 1) { while (wp::cta_tick(0) > 0) {} }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -402,23 +413,31 @@ static int warp_slots(const dcbf_ctx *ctx) {
     const int m = ctx->P.formulation == DCBF_DD ? 3 * (ctx->Kc + ctx->Ke + 4) : 3 * (ctx->Kc + ctx->Ke + (ctx->P.has_fen ? 6 : 4));
     return m <= 32 ? 1 : (m <= 64 ? 2 : 4);
 }
+// persistent grid of the warp kernels: as many CTAs as are resident (occupancy of the launch bounds), never more than the work
+template <class M, int NS>
+static int warp_grid(const dcbf_ctx *ctx, int n, int ctas_per_sm) {
+    const int W = wp::Wpc<M, NS>::v;
+    const int need = (n + W - 1) / W, resident = ctx->sm_count * ctas_per_sm;
+    return need < resident ? (need < 1 ? 1 : need) : resident;
+}
+
 template <int NS>
-static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st, const int *order = nullptr,
+static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st, int slot = 0, const int *order = nullptr,
                              const int *count = nullptr) {
-    int grid = B;
-    const int cap = ctx->sm_count * DCBF_WARP_GRID_CAP;
-    if (!order && cap > 0 && grid > cap) grid = cap;
-    solve_lip_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, count);
+    int *counter = ctx->d_counter + 1 + slot;
+    CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    const int grid = warp_grid<wp::LipW, NS>(ctx, B, DCBF_WARP_MIN_CTAS(NS));
+    solve_lip_warp_kernel<NS><<<grid, 32 * wp::Wpc<wp::LipW, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, count, counter);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
 
 template <int NS>
 static int launch_solve_dd_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
-    int grid = B;
-    const int cap = ctx->sm_count * DCBF_WARP_GRID_CAP;
-    if (cap > 0 && grid > cap) grid = cap;
-    solve_dd_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out);
+    int *counter = ctx->d_counter + 1;
+    CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    const int grid = warp_grid<wp::DdW, NS>(ctx, B, 12 / wp::Wpc<wp::DdW, NS>::v);
+    solve_dd_warp_kernel<NS><<<grid, 32 * wp::Wpc<wp::DdW, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, counter);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -437,12 +456,16 @@ static int launch_solve_split(dcbf_ctx *ctx, int B, const BatchIn &in, const Sol
     CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
     classify_lip_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->P, B, in, small_max_obs, counts, small, large);
     CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->d_counter + 2, 0, sizeof(int), st));   // the aux stream's counter is cleared before the fork
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-    int rc = launch_solve_warp<NS>(ctx, B, in, out, st, large, counts + 1);          // the long problems first
+    int rc = launch_solve_warp<NS>(ctx, B, in, out, st, 0, large, counts + 1);          // the long problems first
     if (rc != DCBF_OK) return rc;
-    rc = launch_solve_warp<1>(ctx, B, in, out, ctx->aux_stream, small, counts);
-    if (rc != DCBF_OK) return rc;
+    {
+        const int grid = warp_grid<wp::LipW, 1>(ctx, B, DCBF_WARP_MIN_CTAS(1));
+        solve_lip_warp_kernel<1><<<grid, 32 * wp::Wpc<wp::LipW, 1>::v, 0, ctx->aux_stream>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, small, counts, ctx->d_counter + 2);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     ctx->launches += 2;
@@ -451,10 +474,10 @@ static int launch_solve_split(dcbf_ctx *ctx, int B, const BatchIn &in, const Sol
 
 template <int NS>
 static int launch_rollout_warp(dcbf_ctx *ctx, int B, int steps, const BatchIn &in, const RolloutOut &out, cudaStream_t st) {
-    int grid = B;
-    const int cap = ctx->sm_count * DCBF_WARP_GRID_CAP;
-    if (cap > 0 && grid > cap) grid = cap;
-    rollout_lip_warp_kernel<NS><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, steps, in, out);
+    int *counter = ctx->d_counter + 1;
+    CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    const int grid = warp_grid<wp::LipW, NS>(ctx, B, DCBF_WARP_MIN_CTAS(NS));
+    rollout_lip_warp_kernel<NS><<<grid, 32 * wp::Wpc<wp::LipW, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, steps, in, out, counter);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -511,7 +534,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     const char *km = getenv("DCBF_KERNEL");
     ctx->kernel_mode = km ? (km[0] == 't' ? 1 : (km[0] == 'w' ? 2 : 0)) : 0;
     const char *wb = getenv("DCBF_WARP_MAX_BATCH");
-    if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
+    if (cudaMalloc(&ctx->d_counter, 8 * sizeof(int)) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     {
         wp::WarpTables *W = new (std::nothrow) wp::WarpTables();
         const bool ok = W && wp::build_warp_tables(ctx->K, *W) && cudaMalloc(&ctx->d_tab, sizeof(wp::WarpTables)) == cudaSuccess &&

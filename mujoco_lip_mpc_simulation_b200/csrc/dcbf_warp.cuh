@@ -207,10 +207,35 @@ struct CtaShared {
     const WarpTables *tab;
 };
 
-// one warp per CTA: the per-problem scratch and the constants are static shared-memory objects, so every function sees
-// them as shared-space symbols (LDS/STS with immediate offsets, no generic pointers through the out-of-line calls)
-template <class M, int NS> __shared__ WarpShared<M, NS> g_sm;
+// Warps per CTA.  The kernel body is ~130 KB, several times the SM's instruction cache: with independent warps every warp streams
+// the whole iteration through the GPC-level instruction cache and its request rate saturates (ncu: gcc instruction requests 74 % of
+// peak, sm__icc hit rate 71 %, 1.05 instructions per clock per SM whatever the occupancy).  The warps of a CTA therefore meet at a
+// barrier at the top of every interior-point iteration (cta_tick): they walk through the iteration code together and share the
+// fetched lines.  Static shared memory bounds the count (48 KB per CTA).
+#ifndef DCBF_WPC_LIP
+#define DCBF_WPC_LIP(NS) 1
+#endif
+#ifndef DCBF_WPC_DD
+#define DCBF_WPC_DD(NS) ((NS) == 2 ? 2 : 1)
+#endif
+struct LipW;
+struct DdW;
+template <class M, int NS> struct Wpc { static constexpr int v = DCBF_WPC_LIP(NS); };
+template <int NS> struct Wpc<DdW, NS> { static constexpr int v = DCBF_WPC_DD(NS); };
+
+// per-problem scratch (one per warp) and the constants are static shared-memory objects, so every function sees them as
+// shared-space symbols (no generic pointers through the out-of-line calls)
+template <class M, int NS> __shared__ WarpShared<M, NS> g_sm[Wpc<M, NS>::v];
 __shared__ CtaShared g_cs;
+
+// iteration barrier of a CTA: returns the number of threads that still have work (a warp without work keeps arriving until the
+// count is zero).  One out-of-line copy so that every arrival is the same instruction.
+__device__ __noinline__ int cta_tick(int working) { return __syncthreads_count(working); }
+__device__ __forceinline__ int warp_in_cta() {
+    int t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    return t >> 5;
+}
 
 // %laneid through a volatile asm: the value stays in a register (the compiler otherwise re-reads SR_TID.X at every use)
 __device__ __forceinline__ int lane_id() {
@@ -436,8 +461,8 @@ struct LipW {
     // nodes 1..3 at the point z (lanes 0..2, directly from the free response and the constant influence coefficients), per-node
     // trigonometry and objective terms; collective, out of line
     template <int NS>
-    static __device__ __noinline__ void nodes(const double *z, int lane, double sf, bool want_hess) {
-        WarpShared<LipW, NS> &sm = g_sm<LipW, NS>;
+    static __device__ __noinline__ void nodes(const double *z, int lane, int wid, double sf, bool want_hess) {
+        WarpShared<LipW, NS> &sm = g_sm<LipW, NS>[wid];
         const CtaShared &cs_ = g_cs;
         const dcbf_params &P = cs_.P;
         if (lane < 3) {
@@ -644,8 +669,8 @@ struct DdW {
 
     // headings and their sines / cosines (lanes 0..2 = th_0..2), then nodes 1..3 with their Jacobians and objective terms
     template <int NS>
-    static __device__ __noinline__ void nodes(const double *z, int lane, double sf, bool want_hess) {
-        WarpShared<DdW, NS> &sm = g_sm<DdW, NS>;
+    static __device__ __noinline__ void nodes(const double *z, int lane, int wid, double sf, bool want_hess) {
+        WarpShared<DdW, NS> &sm = g_sm<DdW, NS>[wid];
         const dcbf_params &P = g_cs.P;
         const double dt = g_cs.K.dt;
         if (lane < 3) {
@@ -818,12 +843,12 @@ __device__ __forceinline__ void reduce8_inline(Stat8 &t) {
 // the solver for one problem (all 32 lanes call it with identical arguments).  Inputs in sm: x0, graw, zc (+ model data).
 // ---------------------------------------------------------------------------------------------------------------
 template <class M, int NS>
-__device__ void solve_warp(const BatchIn &in, int b, int lane, int leg, WState &S) {
+__device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg, WState &S) {
     using Sh = WarpShared<M, NS>;
     constexpr int RP = Sh::RP;
     constexpr int N = M::N, NK = N * (N + 1) / 2;
     constexpr int KQ_RHS_ = KQ_K + NK;   // = packed row N of the system: tri(N, j) = NK + j
-    Sh &sm = g_sm<M, NS>;
+    Sh &sm = g_sm<M, NS>[wid];
     const CtaShared &cs_ = g_cs;
     const dcbf_params &P = cs_.P;
     // ---- problem setup -------------------------------------------------------------------------------------------
@@ -869,8 +894,9 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int leg, WState &
     double carry_log = 0.0;        // sum of log(gaps) at the accepted trial point = barrier term of the next full pass
     bool carry_ok = false;
     for (;;) {
+        if (Wpc<M, NS>::v > 1) cta_tick(1);   // the warps of the CTA start every iteration together (shared instruction fetch)
         const bool resto = S.phase == PH_RESTO;
-        if (!nodes_valid) M::template nodes<NS>(sm.zc, lane, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
+        if (!nodes_valid) M::template nodes<NS>(sm.zc, lane, wid, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
         nodes_valid = false;
         const double fobj = M::template objective<NS>(sm);
         const double grad_a = M::template grad<NS>(sm, cs_, lane, ln);   // lane a < N owns grad[a]
@@ -1091,7 +1117,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int leg, WState &
             // Levenberg-Marquardt trial at full step (violation only)
             sm.zt[lane] = sm.zc[ln] + sm.dz[ln];
             __syncwarp();
-            M::template nodes<NS>(sm.zt, lane, 0.0, false);
+            M::template nodes<NS>(sm.zt, lane, wid, 0.0, false);
             v2t = 0.0; vmt = 0.0;
 #pragma unroll UNR
             for (int s = 0; s < NS; s++) {
@@ -1181,7 +1207,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int leg, WState &
         for (int ls = 0; ls < DCBF_LS_MAX; ls++, alpha *= 0.5) {
             sm.zt[lane] = fma(alpha, sm.dz[ln], sm.zc[ln]);
             __syncwarp();
-            M::template nodes<NS>(sm.zt, lane, S.sf, true);
+            M::template nodes<NS>(sm.zt, lane, wid, S.sf, true);
             const double ft = M::template objective<NS>(sm);
             double th_t = 0.0, lg_t = 0.0;
             bool okv = true;
@@ -1251,18 +1277,27 @@ __device__ __forceinline__ bool w_close(const dcbf_params &P, const WarpShared<L
     return close;
 }
 
-// per-CTA staging of the constants; zeroes the pad columns of the staged rows
+// per-CTA staging of the constants; zeroes the pad columns of the staged rows of every warp
 template <class M, int NS>
-__device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K, const WarpTables *tab, int lane) {
-    WarpShared<M, NS> &sm = g_sm<M, NS>;
-    if (lane == 0) { g_cs.P = P; g_cs.K = K; g_cs.tab = tab; }
-    for (int t = lane; t < 60; t += 32) (&g_cs.cab[0][0])[t] = __ldg(&tab->cab[0][0] + t);
-    for (int t = lane; t < NHT * 48; t += 32) (&g_cs.hc[0][0])[t] = __ldg(&tab->hc[0][0] + t);
-    for (int t = lane; t < NHT * 48 / 4; t += 32)
+__device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K, const WarpTables *tab, int lane, int wid) {
+    constexpr int W = Wpc<M, NS>::v;
+    WarpShared<M, NS> &sm = g_sm<M, NS>[wid];
+    const int t0 = wid * 32 + lane;
+    if (t0 == 0) { g_cs.P = P; g_cs.K = K; g_cs.tab = tab; }
+    for (int t = t0; t < 60; t += 32 * W) (&g_cs.cab[0][0])[t] = __ldg(&tab->cab[0][0] + t);
+    for (int t = t0; t < NHT * 48; t += 32 * W) (&g_cs.hc[0][0])[t] = __ldg(&tab->hc[0][0] + t);
+    for (int t = t0; t < NHT * 48 / 4; t += 32 * W)
         reinterpret_cast<unsigned *>(&g_cs.hs[0][0])[t] = __ldg(reinterpret_cast<const unsigned *>(&tab->hs[0][0]) + t);
-    if (lane < 24) g_cs.sm_dd[lane] = __ldg(&tab->sm_dd[lane]);
+    if (t0 < 24) g_cs.sm_dd[t0] = __ldg(&tab->sm_dd[t0]);
     for (int t = lane; t < 2 * WarpShared<M, NS>::NST; t += 32) sm.ST[t >> 1][32 * NS + (t & 1)] = 0.0;
-    __syncwarp();
+    __syncthreads();
+}
+
+// next problem of this warp: dynamic assignment from a counter (problems take 11..30+ iterations)
+__device__ __forceinline__ int next_problem(int *counter, int lane) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(counter, 1);
+    return __shfl_sync(FULL, i, 0);
 }
 
 #endif  // __CUDACC__
