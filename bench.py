@@ -8,8 +8,8 @@ N GPUs every rank owns its own 4096-scenario batch (weak scaling, no data-path c
 rate = N * 4096 * steps / max-over-ranks(device time).
 
   value      inputs resident in HBM, CUDA-event time of the solve kernel launches only (L2 flushed between steps)
-  e2e        the same batch through the host-buffer C-ABI call dcbf_solve_host: pinned staging, H2D copy, kernel,
-             D2H copy of the full result (u, plans, status, ...) every step
+  e2e        the same batch through the host-buffer C-ABI call dcbf_solve_host with page-locked host buffers: H2D copies of
+             the inputs, kernel, D2H copies of the full result (u, plans, status, ...) every step
   roofline   FP64-pipe roofline of solve_lip_warp_kernel<1> (one problem per warp): algorithmic flop = sum_i iters_i * F_iter (SURVEY.md 8(d) formula)
              over the measured kernel time, against the FP64 DFMA peak measured on this GPU by dcbf_fp64_peak_tflops
              (MEASURED_PEAKS.json carries no FP64 figure); `hbm` sub-object: batch I/O bytes / time vs measured HBM copy
@@ -193,16 +193,20 @@ def main():
     flop_per_step = float(iters.sum()) * F_ITER_SIG_K6
 
     # ---- timed region 2: end to end through the host-buffer C-ABI call ----------------------------------------------
+    # inputs and results live in page-locked host memory (the copies inside the timed call are DMA transfers from / to them)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    hx0, hgoal, hleg, hwarm, hfield = pin(sc.x0), pin(sc.goal), pin(sc.leg.astype(np.int32)), pin(sc.warm), pin(sc.field.astype(np.int32))
     solver.set_fields_host(sc.cir)
-    hres = solver.solve_host(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)      # allocates staging once
-    for _ in range(2):
-        solver.solve_host(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field, out=hres)
+    hres = SolveResult(pin(np.empty((B, 15))), pin(np.empty((B, 3, 5))), pin(np.empty((B, 3, 3))), pin(np.empty(B, np.int32)),
+                       pin(np.empty(B, np.int32)), pin(np.empty(B)), pin(np.empty(B)), pin(np.empty(B, np.uint8)))
+    for _ in range(3):
+        solver.solve_host(hx0, hgoal, hleg, hwarm, field=hfield, out=hres)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        solver.solve_host(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field, out=hres)
+        solver.solve_host(hx0, hgoal, hleg, hwarm, field=hfield, out=hres)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     if world > 1:

@@ -740,6 +740,12 @@ int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, cons
 }
 
 // ---- host-buffer entry points ---------------------------------------------------------------------------------------
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static int ensure_staging(dcbf_ctx *ctx, size_t bytes) {
     if (ctx->h_pin_bytes < bytes) {
         if (ctx->h_pin) CK(cudaFreeHost(ctx->h_pin));
@@ -804,28 +810,38 @@ int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *go
     int rc = ensure_staging(ctx, total);
     if (rc != DCBF_OK) return rc;
     char *hp = (char *)ctx->h_pin, *dp = (char *)ctx->d_buf;
-    memcpy(hp + o_x0, x0, 8 * nx * b);
-    memcpy(hp + o_goal, goal, 16 * b);
-    memcpy(hp + o_warm, warm, 8 * nu * b);
-    if (last_u) memcpy(hp + o_lastu, last_u, 16 * b);
-    if (leg) memcpy(hp + o_leg, leg, 4 * b);
-    if (field) memcpy(hp + o_field, field, 4 * b);
-    CK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // Page-locked caller buffers are copied by the DMA engines directly; pageable ones go through the pinned staging block (one
+    // copy each way).  The check costs ~1 us per pointer, so tiny batches (where the staging memcpy is free) skip it.
+    struct Piece { const void *src; void *dst; size_t off, bytes; };
+    const Piece ins[6] = {{x0, nullptr, o_x0, 8 * nx * b}, {goal, nullptr, o_goal, 16 * b}, {warm, nullptr, o_warm, 8 * nu * b},
+                          {last_u, nullptr, o_lastu, 16 * b}, {leg, nullptr, o_leg, 4 * b}, {field, nullptr, o_field, 4 * b}};
+    const Piece outs[8] = {{nullptr, u, o_u, 8 * nu * b}, {nullptr, x_plan, o_xp, 8 * 3 * nx * b}, {nullptr, dd ? nullptr : p_plan, o_pp, 8 * 9 * b},
+                           {nullptr, obj, o_obj, 8 * b}, {nullptr, viol, o_viol, 8 * b}, {nullptr, status, o_st, 4 * b},
+                           {nullptr, iters, o_it, 4 * b}, {nullptr, close2goal, o_cl, b}};
+    bool in_pinned = B >= 256, out_pinned = B >= 256;
+    for (int i = 0; i < 6 && in_pinned; i++) if (ins[i].src && !is_pinned_host(ins[i].src)) in_pinned = false;
+    for (int i = 0; i < 8 && out_pinned; i++) if (outs[i].dst && !is_pinned_host(outs[i].dst)) out_pinned = false;
+    if (in_pinned) {
+        for (int i = 0; i < 6; i++)
+            if (ins[i].src) CK(cudaMemcpyAsync(dp + ins[i].off, ins[i].src, ins[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        for (int i = 0; i < 6; i++) if (ins[i].src) memcpy(hp + ins[i].off, ins[i].src, ins[i].bytes);
+        CK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     rc = dcbf_solve(ctx, B, (double *)(dp + o_x0), (double *)(dp + o_goal), leg ? (int32_t *)(dp + o_leg) : nullptr,
                     field ? (int32_t *)(dp + o_field) : nullptr, (double *)(dp + o_warm), last_u ? (double *)(dp + o_lastu) : nullptr,
                     (double *)(dp + o_u), (double *)(dp + o_xp), dd ? nullptr : (double *)(dp + o_pp), (int32_t *)(dp + o_st),
                     (int32_t *)(dp + o_it), (double *)(dp + o_obj), (double *)(dp + o_viol), (uint8_t *)(dp + o_cl), ctx->stream);
     if (rc != DCBF_OK) return rc;
-    CK(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (u) memcpy(u, hp + o_u, 8 * nu * b);
-    if (x_plan) memcpy(x_plan, hp + o_xp, 8 * 3 * nx * b);
-    if (p_plan && !dd) memcpy(p_plan, hp + o_pp, 8 * 9 * b);
-    if (obj) memcpy(obj, hp + o_obj, 8 * b);
-    if (viol) memcpy(viol, hp + o_viol, 8 * b);
-    if (status) memcpy(status, hp + o_st, 4 * b);
-    if (iters) memcpy(iters, hp + o_it, 4 * b);
-    if (close2goal) memcpy(close2goal, hp + o_cl, b);
+    if (out_pinned) {
+        for (int i = 0; i < 8; i++)
+            if (outs[i].dst) CK(cudaMemcpyAsync(outs[i].dst, dp + outs[i].off, outs[i].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < 8; i++) if (outs[i].dst) memcpy(outs[i].dst, hp + outs[i].off, outs[i].bytes);
+    }
     return DCBF_OK;
 }
 

@@ -289,6 +289,22 @@ def test_host_buffer_entry_point_equals_device_entry_point(gpu):
     np.testing.assert_array_equal(h.close2goal.astype(bool), d.close2goal.cpu().numpy())
 
 
+def test_host_entry_point_with_page_locked_buffers(gpu):
+    """dcbf_solve_host copies straight from / to page-locked caller buffers (no staging); same results as the staged path"""
+    sc = scenarios.make_batch("sig_step", 512, seed=31)
+    s = _solver(gpu, "sig_step", sc)
+    s.set_fields_host(sc.cir)
+    ref = s.solve_host(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    from mujoco_lip_mpc_simulation_b200.batch import SolveResult
+    out = SolveResult(pin(np.empty((512, 15))), pin(np.empty((512, 3, 5))), pin(np.empty((512, 3, 3))), pin(np.empty(512, np.int32)),
+                      pin(np.empty(512, np.int32)), pin(np.empty(512)), pin(np.empty(512)), pin(np.empty(512, np.uint8)))
+    s.solve_host(pin(sc.x0), pin(sc.goal), pin(sc.leg.astype(np.int32)), pin(sc.warm), field=pin(sc.field.astype(np.int32)), out=out)
+    assert np.array_equal(out.status, ref.status) and np.array_equal(out.iters, ref.iters)
+    assert np.array_equal(out.p_plan, ref.p_plan) and np.array_equal(out.x_plan, ref.x_plan) and np.array_equal(out.u, ref.u)
+    assert np.array_equal(out.close2goal, ref.close2goal)
+
+
 def test_error_codes(gpu):
     lib = _lib.load()
     P = _lib.DcbfParams()
