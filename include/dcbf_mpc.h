@@ -17,6 +17,9 @@
  *                            MPC_DD_sig_step.py:70-99,123-193) i.e. the cyipopt.Problem(...).solve(u0) call
  *   dcbf_rollout         <- the plan -> apply -> re-plan loop of MPC_LIP_sig_step.py:565-575
  *   dcbf_solve_host      <- same as dcbf_solve for callers that hold host (numpy) buffers
+ *   dcbf_alip_foot       <- the closed-form ALIP foot placement behind the DD re-plan (Logger.ALIP_gen_foot_input,
+ *                           data_procs/logger_dd.py:356-363 -> ALIP.AMprediction / computeSw2CoM / computeStepping /
+ *                           regulate_lateral_step / getTimedState, ALIP_plan/planner.py:188-261,346-370)
  *   dcbf_tick            <- one control tick of Logger.gen_nex_foot_input (data_procs/logger_mpc.py:318-341):
  *                           LIP prediction to the end of the running step (MPCCBF.get_next_states,
  *                           MPC_LIP_modi.py:149-178), the warm-start rule, the re-plan, and the dense plan trajectory
@@ -135,6 +138,18 @@ int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo
               const double *prev_plan, const uint8_t *mode, double *x_next, double *warm, double *u, double *x_plan,
               double *p_plan, int32_t *status, int32_t *iters, double *obj, double *viol, uint8_t *close2goal,
               double *pos_det, void *stream);
+
+/* Angular-momentum LIP one-step foot placement for B scenarios (device pointers), the step behind the DD re-plan in
+ * data_procs/logger_dd.py:356-363.  Inputs: x_alip[B][2] = (p_x, L_y) and y_alip[B][2] = (p_y, L_x) relative to the stance foot,
+ * time[B] into the running step, support[B] (+1 right, -1 left), speed = desired forward speed read as speed[b * speed_stride]
+ * (pass the `u` output of dcbf_solve of the DD formulation with speed_stride = 6 to chain the two on the stream).  Model constants:
+ * H (CoM height), T (step time), m (mass), W (step width) -- ALIPParam / ALIP.__init__ (ALIP_plan/planner.py:15-61, 545).
+ * Outputs (any may be NULL): foot[B][2] = (px_sp2sw, py_sp2sw) with the lateral regulation of planner.py:346-370,
+ * am[B][2] = (Ly_est, Lx_est) (planner.py:210-230), next[B][4] = (p_x, L_y, p_y, L_x) at the end of the step
+ * (getTimedState over T - time, planner.py:188-208).  Moving-platform (DRS) terms are zero (planner.py:47-50). */
+int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double *y_alip, const double *time, const int32_t *support,
+                   const double *speed, int32_t speed_stride, double H, double T, double m, double W, double *foot, double *am,
+                   double *next, void *stream);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t dcbf_launch_count(const dcbf_ctx *ctx);

@@ -71,3 +71,12 @@ class ALIP:
         px_sw, py_sw = self.computeSw2CoM(Ly_est, Lx_est, Ly_des, support)
         p = np.asarray(p_sp2CoM, dtype=np.float64)
         return p[..., 0] - px_sw, self.regulate_lateral_step(support, p[..., 1] - py_sw)
+
+    def getFootPlacement(self, speed, support, time, x_alip, y_alip):
+        """(px, py, Ly_est, Lx_est) as data_procs/logger_dd.py:359 calls it.  The five-argument variant lives in the reference's
+        missing top-level ALIP.py (only an orphan .pyc ships); the composition follows planner.py:263-320, which is the same
+        chain on a full-order state: AMprediction at `time`, then computeStepping with the stance-to-CoM offset (x[0], y[0])."""
+        x_alip, y_alip = np.asarray(x_alip, dtype=np.float64), np.asarray(y_alip, dtype=np.float64)
+        Ly_est, Lx_est = self.AMprediction(x_alip, y_alip, time)
+        ux, uy = self.computeStepping(np.stack([x_alip[..., 0], y_alip[..., 0]], axis=-1), Ly_est, Lx_est, speed, support)
+        return ux, uy, Ly_est, Lx_est

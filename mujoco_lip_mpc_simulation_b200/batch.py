@@ -239,6 +239,28 @@ class DcbfSolver:
         self._check(rc, "dcbf_tick")
         return dict(x_next=xn, warm=warm, plan=SolveResult(u, xp, pp, st, it, obj, viol, cl.bool()), pos_det=pd)
 
+    def alip_foot(self, x_alip, y_alip, time, support, speed, speed_stride=1, H=1.0, T=0.4, m=45.0, W=0.2):
+        """ALIP one-step foot placement on the device (dcbf_alip_foot); `speed` may be the `u` tensor of a DD solve with
+        speed_stride=6 (v_0 of every scenario) so that the two calls chain on the stream."""
+        xa = self._dev(x_alip, torch.float64).reshape(-1, 2)
+        B = xa.shape[0]
+        ya = self._dev(y_alip, torch.float64).reshape(B, 2)
+        tm = self._dev(time, torch.float64).reshape(-1)
+        if tm.shape[0] != B:
+            tm = tm.expand(B).contiguous()
+        sup = self._dev(support, torch.int32).reshape(-1)
+        if sup.shape[0] != B:
+            sup = sup.expand(B).contiguous()
+        sp = self._dev(speed, torch.float64).reshape(-1)
+        assert sp.numel() >= (B - 1) * speed_stride + 1
+        kw = dict(device=self.tdev, dtype=torch.float64)
+        foot, am, nxt = torch.empty((B, 2), **kw), torch.empty((B, 2), **kw), torch.empty((B, 4), **kw)
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_alip_foot(self._ctx, B, _ptr(xa), _ptr(ya), _ptr(tm), _ptr(sup), _ptr(sp), int(speed_stride),
+                                         float(H), float(T), float(m), float(W), _ptr(foot), _ptr(am), _ptr(nxt), self._stream())
+        self._check(rc, "dcbf_alip_foot")
+        return dict(foot=foot, am=am, next=nxt)
+
     # ------------------------------------------------------------------------------------------------------
     def set_fields_host(self, cir, elp=None):
         cir = np.ascontiguousarray(np.zeros((1, 0, 3)) if cir is None else cir, dtype=np.float64)

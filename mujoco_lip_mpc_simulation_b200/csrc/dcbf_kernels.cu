@@ -389,6 +389,37 @@ __global__ void pos_det_kernel(int B, const double *__restrict__ ch, const doubl
     reinterpret_cast<double2 *>(pos_det)[t] = make_double2(ox, oy);
 }
 
+// ALIP one-step foot placement (ALIP_plan/planner.py:188-261, 346-370), one thread per scenario
+__global__ void alip_foot_kernel(int B, const double *__restrict__ xa, const double *__restrict__ ya, const double *__restrict__ time,
+                                 const int32_t *__restrict__ support, const double *__restrict__ speed, int stride, double H, double T,
+                                 double m, double W, double *__restrict__ foot, double *__restrict__ am, double *__restrict__ next) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double l = sqrt(9.81 / H), mhl = m * H * l;
+    const double t = fmin(time[b], T);
+    const double px = xa[2 * (size_t)b], Ly = xa[2 * (size_t)b + 1], py = ya[2 * (size_t)b], Lx = ya[2 * (size_t)b + 1];
+    const double ch = cosh(l * (T - t)), sh = sinh(l * (T - t));
+    // AMprediction: angular momentum at the end of the step
+    const double Ly_est = mhl * sh * px + ch * Ly, Lx_est = -mhl * sh * py + ch * Lx;
+    // computeSw2CoM + computeStepping
+    const double chT = cosh(l * T), shT = sinh(l * T), den = mhl * shT;
+    const double Ly_des = m * H * speed[(size_t)b * stride];
+    const double px_sw = Ly_des / den - chT / den * Ly_est;
+    const double base = 0.5 * m * H * W * (l * shT) / (1.0 + chT);
+    const int sup = support[b];
+    const double Lx_des = sup == 1 ? base : -base;
+    const double py_sw = -Lx_des / den + chT / den * Lx_est;
+    double ux = px - px_sw, uy = py - py_sw;
+    if (sup == 1) uy = fmin(fmax(uy, 0.1), 0.45);            // regulate_lateral_step
+    else if (sup == -1) uy = fmin(fmax(uy, -0.45), -0.1);
+    if (foot) { foot[2 * (size_t)b] = ux; foot[2 * (size_t)b + 1] = uy; }
+    if (am) { am[2 * (size_t)b] = Ly_est; am[2 * (size_t)b + 1] = Lx_est; }
+    if (next) {   // getTimedState over the rest of the step
+        next[4 * (size_t)b + 0] = ch * px + sh / mhl * Ly; next[4 * (size_t)b + 1] = mhl * sh * px + ch * Ly;
+        next[4 * (size_t)b + 2] = ch * py - sh / mhl * Lx; next[4 * (size_t)b + 3] = -mhl * sh * py + ch * Lx;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // FP64 peak microbenchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------------------------------------
@@ -712,6 +743,19 @@ int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo
         CK(cudaGetLastError());
         ctx->launches++;
     }
+    return DCBF_OK;
+}
+
+int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double *y_alip, const double *time, const int32_t *support,
+                   const double *speed, int32_t speed_stride, double H, double T, double m, double W, double *foot, double *am,
+                   double *next, void *stream) {
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
+    if (B == 0) return DCBF_OK;
+    if (!x_alip || !y_alip || !time || !support || !speed || speed_stride < 1 || !(H > 0.0) || !(T > 0.0) || !(m > 0.0)) return DCBF_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    alip_foot_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, x_alip, y_alip, time, support, speed, speed_stride, H, T, m, W, foot, am, next);
+    CK(cudaGetLastError());
+    ctx->launches++;
     return DCBF_OK;
 }
 

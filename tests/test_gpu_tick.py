@@ -76,3 +76,31 @@ def test_tick_without_previous_plan_is_a_cold_start():
     assert torch.equal(out["plan"].status, ref.status)
     assert torch.allclose(out["plan"].p_plan, ref.p_plan, rtol=0, atol=1e-9)
     del z2
+
+
+def test_alip_foot_placement_chained_behind_the_dd_solve():
+    """dcbf_alip_foot against the host mirror of ALIP_plan/planner.py (pinned to the reference by tests/test_helpers_cpu.py),
+    reading the forward speed straight from the DD plan (speed_stride = 6)"""
+    from mujoco_lip_mpc_simulation_b200.ALIP_plan.planner import ALIP, ALIPParam
+    B = 512
+    rng = np.random.default_rng(9)
+    sc = scenarios.make_batch("dd", B, seed=24)
+    s = DcbfSolver("dd", device=0)
+    s.set_fields(sc.cir, sc.elp)
+    plan = s.solve(sc.x0, sc.goal, None, sc.warm, field=sc.field, last_u=sc.last_u)
+    x_alip = np.stack([rng.uniform(-0.1, 0.2, B), rng.uniform(5.0, 40.0, B)], axis=1)
+    y_alip = np.stack([rng.uniform(-0.2, 0.2, B), rng.uniform(-15.0, 15.0, B)], axis=1)
+    time = rng.uniform(0.0, 0.45, B)          # beyond T the reference clamps
+    sup = rng.choice([-1, 1], size=B).astype(np.int32)
+    out = s.alip_foot(x_alip, y_alip, time, sup, plan.u, speed_stride=6)
+    torch.cuda.synchronize()
+    a = ALIP(ALIPParam(H=1.0, T=0.4, m=45.0))
+    speed = plan.u.cpu().numpy()[:, 0]
+    ux, uy, Ly, Lx = a.getFootPlacement(speed, sup, time, x_alip, y_alip)
+    np.testing.assert_allclose(out["foot"].cpu().numpy(), np.stack([ux, uy], axis=1), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(out["am"].cpu().numpy(), np.stack([Ly, Lx], axis=1), rtol=1e-12, atol=1e-10)
+    xt, yt = a.getTimedState(x_alip, y_alip, 0.4 - np.minimum(time, 0.4))
+    np.testing.assert_allclose(out["next"].cpu().numpy(), np.concatenate([xt, yt], axis=1), rtol=1e-12, atol=1e-10)
+    # the regulation clamps are hit on both sides
+    uyg = out["foot"].cpu().numpy()[:, 1]
+    assert np.all((np.abs(uyg) >= 0.1 - 1e-15) & (np.abs(uyg) <= 0.45 + 1e-15)) and np.all(np.sign(uyg) == sup)
