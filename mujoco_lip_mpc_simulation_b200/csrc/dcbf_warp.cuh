@@ -244,10 +244,19 @@ __device__ __forceinline__ int lane_id() {
     return l;
 }
 
-__device__ __noinline__ double wmax(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
+// max / min over the warp of NON-NEGATIVE doubles: their bit patterns order like unsigned integers, so two 32-bit hardware
+// reductions (redux.sync) replace five shuffle rounds.  A NaN operand wins the max (and is then caught by the caller's checks).
+__device__ __forceinline__ double wmax(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double wmin(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
 }
 __device__ __forceinline__ int wsumi(int v) {
 #pragma unroll
@@ -827,16 +836,16 @@ struct DdW {
     const int r = s * 32 + lane;                                                                               \
     const RowDesc rd = ROLLED ? M::row_desc(r, Ks, ms, m) : rdA[ROLLED ? 0 : s];
 
-// eight statistics reduced together (interleaved butterflies): four sums and four maxima
+// eight statistics reduced together: four sums (interleaved shuffle butterflies) and four extrema of non-negative numbers
+// (hardware reductions); m1 carries the MINIMUM of the complementarity products
 struct Stat8 { double s0, s1, s2, s3, m0, m1, m2, m3; };
 __device__ __forceinline__ void reduce8_inline(Stat8 &t) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         t.s0 += __shfl_xor_sync(FULL, t.s0, o); t.s1 += __shfl_xor_sync(FULL, t.s1, o);
         t.s2 += __shfl_xor_sync(FULL, t.s2, o); t.s3 += __shfl_xor_sync(FULL, t.s3, o);
-        t.m0 = fmax(t.m0, __shfl_xor_sync(FULL, t.m0, o)); t.m1 = fmax(t.m1, __shfl_xor_sync(FULL, t.m1, o));
-        t.m2 = fmax(t.m2, __shfl_xor_sync(FULL, t.m2, o)); t.m3 = fmax(t.m3, __shfl_xor_sync(FULL, t.m3, o));
     }
+    t.m0 = wmax(t.m0); t.m1 = wmin(t.m1); t.m2 = wmax(t.m2); t.m3 = wmax(t.m3);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -909,7 +918,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         const double sf_eff = resto ? 0.0 : S.sf;
         // ---- rows: evaluate, update row state, stage gradients and weights; statistics stay in registers ----------------------
         Stat8 st8;
-        st8.s0 = st8.s1 = st8.s2 = st8.s3 = 0.0; st8.m0 = 0.0; st8.m1 = -1e300; st8.m2 = 0.0; st8.m3 = 0.0;
+        st8.s0 = st8.s1 = st8.s2 = st8.s3 = 0.0; st8.m0 = 0.0; st8.m1 = 1e300; st8.m2 = 0.0; st8.m3 = 0.0;
 #pragma unroll UNR
         for (int s = 0; s < NS; s++) {
             DCBF_ROW_BEGIN
@@ -977,13 +986,13 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 col[0] = sig; col[RP] = w1; col[2 * RP] = binv; col[3 * RP] = y;
             }
             st8.s0 += t_rc; st8.s1 += t_z; st8.s2 += t_log; st8.s3 += t_v2;
-            st8.m0 = fmax(st8.m0, t_rc); st8.m1 = fmax(st8.m1, -t_cmin); st8.m2 = fmax(st8.m2, t_cmax); st8.m3 = fmax(st8.m3, t_v);
+            st8.m0 = fmax(st8.m0, t_rc); st8.m1 = fmin(st8.m1, t_cmin); st8.m2 = fmax(st8.m2, t_cmax); st8.m3 = fmax(st8.m3, t_v);
             DCBF_ROW_END
         }
         __syncwarp();   // the row branches reconverge here, before the shuffles
         reduce8_inline(st8);
         const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? carry_log : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
-                     st_cmin = -st8.m1, st_cmax = st8.m2, st_vmax = st8.m3;
+                     st_cmin = st8.m1, st_cmax = st8.m2, st_vmax = st8.m3;
         carry_ok = false;
         sm.cold[C_ST_THETA] = st_theta; sm.cold[C_ST_LOGSUM] = st_logsum; sm.cold[C_ST_V2] = st_v2; sm.cold[C_ST_VMAX] = st_vmax;
         // ---- second-order sources of the model --------------------------------------------------------------------------------
@@ -1133,10 +1142,8 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             }
             __syncwarp();
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                v2t += __shfl_xor_sync(FULL, v2t, o);
-                vmt = fmax(vmt, __shfl_xor_sync(FULL, vmt, o));
-            }
+            for (int o = 16; o > 0; o >>= 1) v2t += __shfl_xor_sync(FULL, v2t, o);
+            vmt = wmax(vmt);
             if (v2t < sm.cold[C_ST_V2] * (1.0 - 1e-12)) { lm_accept = true; break; }
             S.lm_lambda *= 10.0;
             if (S.lm_lambda > 1e12) break;
@@ -1192,11 +1199,8 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             }
             __syncwarp();
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {   // three reductions interleaved
-                amax = fmin(amax, __shfl_xor_sync(FULL, amax, o));
-                az = fmin(az, __shfl_xor_sync(FULL, az, o));
-                dphi += __shfl_xor_sync(FULL, dphi, o);
-            }
+            for (int o = 16; o > 0; o >>= 1) dphi += __shfl_xor_sync(FULL, dphi, o);
+            amax = wmin(amax); az = wmin(az);   // step sizes are positive
         }
         // ---- filter line search -------------------------------------------------------------------------------------------------
         const double theta = sm.cold[C_ST_THETA];

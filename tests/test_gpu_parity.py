@@ -289,6 +289,23 @@ def test_host_buffer_entry_point_equals_device_entry_point(gpu):
     np.testing.assert_array_equal(h.close2goal.astype(bool), d.close2goal.cpu().numpy())
 
 
+def test_size_class_split_is_transparent(gpu, monkeypatch):
+    """modi batches from 16 384 scenarios on are split by selected-obstacle count (classify pre-pass, 32-row kernel and two-slot
+    kernel on forked streams); every scenario must get the result of the unsplit launch"""
+    B = 16384
+    sc = scenarios.make_batch("modi", B, seed=41)
+    monkeypatch.setenv("DCBF_SPLIT", "0")
+    ref = _solver(gpu, "modi", sc).solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
+    monkeypatch.setenv("DCBF_SPLIT", "16384")
+    s = _solver(gpu, "modi", sc)
+    l0 = s.launches
+    res = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
+    torch.cuda.synchronize()
+    assert s.launches - l0 == 3                      # classify + two solve kernels
+    assert torch.equal(res.status, ref.status) and torch.equal(res.iters, ref.iters)
+    assert torch.equal(res.p_plan, ref.p_plan) and torch.equal(res.x_plan, ref.x_plan)
+
+
 def test_host_entry_point_with_page_locked_buffers(gpu):
     """dcbf_solve_host copies straight from / to page-locked caller buffers (no staging); same results as the staged path"""
     sc = scenarios.make_batch("sig_step", 512, seed=31)
