@@ -839,12 +839,23 @@ struct DdW {
 // eight statistics reduced together: four sums (interleaved shuffle butterflies) and four extrema of non-negative numbers
 // (hardware reductions); m1 carries the MINIMUM of the complementarity products
 struct Stat8 { double s0, s1, s2, s3, m0, m1, m2, m3; };
-__device__ __forceinline__ void reduce8_inline(Stat8 &t) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        t.s0 += __shfl_xor_sync(FULL, t.s0, o); t.s1 += __shfl_xor_sync(FULL, t.s1, o);
-        t.s2 += __shfl_xor_sync(FULL, t.s2, o); t.s3 += __shfl_xor_sync(FULL, t.s3, o);
-    }
+// four sums with ten 64-bit shuffles instead of twenty: the first two butterfly rounds halve the number of values a lane carries
+// (lanes keep the pair / the value their half is responsible for and send the other), three more rounds finish one value per
+// 8-lane group, four broadcasts hand every lane all four totals
+__device__ __forceinline__ void reduce4_sums(double &s0, double &s1, double &s2, double &s3, int lane) {
+    const bool up = (lane & 16) != 0, b3 = (lane & 8) != 0;
+    double a = up ? s2 : s0, b = up ? s3 : s1;
+    a += __shfl_xor_sync(FULL, up ? s0 : s2, 16);
+    b += __shfl_xor_sync(FULL, up ? s1 : s3, 16);
+    double c = b3 ? b : a;
+    c += __shfl_xor_sync(FULL, b3 ? a : b, 8);
+    c += __shfl_xor_sync(FULL, c, 4);
+    c += __shfl_xor_sync(FULL, c, 2);
+    c += __shfl_xor_sync(FULL, c, 1);
+    s0 = __shfl_sync(FULL, c, 0); s1 = __shfl_sync(FULL, c, 8); s2 = __shfl_sync(FULL, c, 16); s3 = __shfl_sync(FULL, c, 24);
+}
+__device__ __forceinline__ void reduce8_inline(Stat8 &t, int lane) {
+    reduce4_sums(t.s0, t.s1, t.s2, t.s3, lane);
     t.m0 = wmax(t.m0); t.m1 = wmin(t.m1); t.m2 = wmax(t.m2); t.m3 = wmax(t.m3);
 }
 
@@ -990,7 +1001,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             DCBF_ROW_END
         }
         __syncwarp();   // the row branches reconverge here, before the shuffles
-        reduce8_inline(st8);
+        reduce8_inline(st8, lane);
         const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? carry_log : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
                      st_cmin = st8.m1, st_cmax = st8.m2, st_vmax = st8.m3;
         carry_ok = false;
