@@ -8,6 +8,7 @@
 //   fatan2   : one division (the octant reduction picks numerator and denominator first),
 //              Cephes atan rational P4/Q5 on |t| <= 0.66                                         < 2e-16 absolute
 //   frcp/fdiv: MUFU.RCP64H seed + two Newton steps (+ one residual step for the quotient)       <= 1 ulp (normal range)
+//   frsqrt   : MUFU.RSQ64H seed + two Newton steps                                              <= 2 ulp (pivots of the Cholesky)
 // The file compiles for the host too (tests/hostsim, tests/test_math_cpu.py checks every function against libm).
 #pragma once
 #include <math.h>
@@ -42,6 +43,19 @@ DCBF_MHD double fdiv(double a, double b) {
     return fma(fma(-b, q, a), r, q);
 #else
     return a / b;
+#endif
+}
+
+// 1 / sqrt(x) for normal positive x: MUFU.RSQ64H seed + two Newton steps
+DCBF_MHD double frsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = fma(r, fma(-hx * r, r, 0.5), r);   // r (1.5 - 0.5 x r^2)
+    return fma(r, fma(-hx * r, r, 0.5), r);
+#else
+    return 1.0 / sqrt(x);
 #endif
 }
 

@@ -1105,7 +1105,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                     for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[tri(j, c)], s_);
                     const double d = __shfl_sync(FULL, s_, j);
                     if (!(d > 1e-14)) { ok = false; break; }
-                    const double rinv = drsqrt(d);
+                    const double rinv = frsqrt(d);
                     Lrow[j] = lane == j ? rinv : s_ * rinv;   // diagonal stored as its reciprocal
                     sm.Lf[act ? rowbase + j : 56 + lane] = Lrow[j];
                     __syncwarp();

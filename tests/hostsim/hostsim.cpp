@@ -66,7 +66,7 @@ int hostsim_rollout(const dcbf_params *P, int B, int steps, const double *x0, co
 
 // lean elementary functions of the kernels (dcbf_math.cuh), evaluated on the host for the accuracy test
 int hostsim_math(int n, const double *a, double *sn, double *cs, const double *y, const double *x, double *at) {
-    for (int i = 0; i < n; i++) { fsincos(a[i], sn + i, cs + i); at[i] = fatan2(y[i], x[i]); }
+    for (int i = 0; i < n; i++) { fsincos(a[i], sn + i, cs + i); at[i] = fatan2(y[i], x[i]); }   // frcp / fdiv / frsqrt are plain divisions on the host
     return 0;
 }
 
