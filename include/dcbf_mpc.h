@@ -151,6 +151,10 @@ int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double 
                    const double *speed, int32_t speed_stride, double H, double T, double m, double W, double *foot, double *am,
                    double *next, void *stream);
 
+/* Test hook: the lean FP64 elementary functions of the kernels (csrc/dcbf_math.cuh) evaluated on the device.
+ * out[n][6] = (sin a, cos a, atan2(a, b), 1 / b, a / b, 1 / sqrt(|b|)); a, b, out are device pointers. */
+int dcbf_math_probe(dcbf_ctx *ctx, int32_t n, const double *a, const double *b, double *out, void *stream);
+
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t dcbf_launch_count(const dcbf_ctx *ctx);
 

@@ -32,7 +32,7 @@ class DcbfParams(C.Structure):
 # every symbol include/dcbf_mpc.h declares
 EXPORTS = ["dcbf_abi_version", "dcbf_default_params", "dcbf_create", "dcbf_destroy", "dcbf_last_error",
            "dcbf_set_fields", "dcbf_num_rows", "dcbf_num_vars", "dcbf_eval", "dcbf_solve", "dcbf_rollout",
-           "dcbf_set_fields_host", "dcbf_solve_host", "dcbf_launch_count", "dcbf_fp64_peak_tflops", "dcbf_tick", "dcbf_alip_foot"]
+           "dcbf_set_fields_host", "dcbf_solve_host", "dcbf_launch_count", "dcbf_fp64_peak_tflops", "dcbf_tick", "dcbf_alip_foot", "dcbf_math_probe"]
 
 
 def needs_build() -> bool:
@@ -88,6 +88,7 @@ def load():
     lib.dcbf_solve_host.argtypes = [vp, C.c_int32] + [ip] * 14
     lib.dcbf_tick.argtypes = [vp, C.c_int32] + [dp] * 21 + [vp]
     lib.dcbf_alip_foot.argtypes = [vp, C.c_int32] + [dp] * 5 + [C.c_int32] + [C.c_double] * 4 + [dp] * 3 + [vp]
+    lib.dcbf_math_probe.argtypes = [vp, C.c_int32, dp, dp, dp, vp]
     lib.dcbf_launch_count.argtypes = [vp]
     lib.dcbf_launch_count.restype = C.c_int64
     lib.dcbf_fp64_peak_tflops.argtypes = [vp, C.c_int32]

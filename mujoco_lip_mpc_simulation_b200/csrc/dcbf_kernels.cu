@@ -389,6 +389,15 @@ __global__ void pos_det_kernel(int B, const double *__restrict__ ch, const doubl
     reinterpret_cast<double2 *>(pos_det)[t] = make_double2(ox, oy);
 }
 
+__global__ void math_probe_kernel(int n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c;
+    fsincos(a[i], &s, &c);
+    double *o = out + 6 * (size_t)i;
+    o[0] = s; o[1] = c; o[2] = fatan2(a[i], b[i]); o[3] = dcbf::frcp(b[i]); o[4] = dcbf::fdiv(a[i], b[i]); o[5] = dcbf::frsqrt(fabs(b[i]));
+}
+
 // ALIP one-step foot placement (ALIP_plan/planner.py:188-261, 346-370), one thread per scenario
 __global__ void alip_foot_kernel(int B, const double *__restrict__ xa, const double *__restrict__ ya, const double *__restrict__ time,
                                  const int32_t *__restrict__ support, const double *__restrict__ speed, int stride, double H, double T,
@@ -754,6 +763,16 @@ int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double 
     if (!x_alip || !y_alip || !time || !support || !speed || speed_stride < 1 || !(H > 0.0) || !(T > 0.0) || !(m > 0.0)) return DCBF_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     alip_foot_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, x_alip, y_alip, time, support, speed, speed_stride, H, T, m, W, foot, am, next);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
+int dcbf_math_probe(dcbf_ctx *ctx, int32_t n, const double *a, const double *b, double *out, void *stream) {
+    if (!ctx || n < 0 || (n > 0 && (!a || !b || !out))) return DCBF_ERR_ARG;
+    if (n == 0) return DCBF_OK;
+    CK(cudaSetDevice(ctx->device));
+    math_probe_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, a, b, out);
     CK(cudaGetLastError());
     ctx->launches++;
     return DCBF_OK;

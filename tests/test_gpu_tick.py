@@ -104,3 +104,24 @@ def test_alip_foot_placement_chained_behind_the_dd_solve():
     # the regulation clamps are hit on both sides
     uyg = out["foot"].cpu().numpy()[:, 1]
     assert np.all((np.abs(uyg) >= 0.1 - 1e-15) & (np.abs(uyg) <= 0.45 + 1e-15)) and np.all(np.sign(uyg) == sup)
+
+
+def test_lean_elementary_functions_on_the_device():
+    """csrc/dcbf_math.cuh as compiled for sm_100a (rcp / rsqrt seeds + Newton, Cody-Waite sincos, one-division atan2) against
+    numpy: <= 1-2 ulp on the argument ranges of the solver"""
+    from mujoco_lip_mpc_simulation_b200.batch import _ptr
+    rng = np.random.default_rng(3)
+    n = 200000
+    a = np.concatenate([rng.uniform(-7, 7, n // 2), rng.uniform(-300, 300, n // 2)])
+    b = np.concatenate([rng.uniform(-12, 12, n // 2), 10.0 ** rng.uniform(-12, 3, n // 2) * rng.choice([-1, 1], n // 2)])
+    s = DcbfSolver("sig_step", device=0)
+    ta, tb = torch.as_tensor(a, device="cuda"), torch.as_tensor(b, device="cuda")
+    out = torch.empty((n, 6), dtype=torch.float64, device="cuda")
+    assert s.lib.dcbf_math_probe(s._ctx, n, _ptr(ta), _ptr(tb), _ptr(out), s._stream()) == 0
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.max(np.abs(o[:, 0] - np.sin(a))) <= 3e-16 and np.max(np.abs(o[:, 1] - np.cos(a))) <= 3e-16
+    assert np.max(np.abs(o[:, 2] - np.arctan2(a, b))) <= 5e-16
+    assert np.max(np.abs(o[:, 3] * b - 1.0)) <= 3e-16
+    assert np.max(np.abs(o[:, 4] - a / b) / np.abs(a / b)) <= 3e-16
+    assert np.max(np.abs(o[:, 5] * np.sqrt(np.abs(b)) - 1.0)) <= 5e-16
