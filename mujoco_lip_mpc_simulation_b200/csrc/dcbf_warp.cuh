@@ -244,6 +244,13 @@ __device__ __forceinline__ int lane_id() {
     return l;
 }
 
+// alpha * a^2.3 > t^1.1 (switching condition of the filter) on the MUFU log2: the condition only selects which acceptance test a
+// trial has to pass, single precision is plenty
+__device__ __forceinline__ bool switch_cond_fast(double alpha, double a, double t) {
+    if (!(t > 0.0)) return alpha > 0.0;
+    return __log2f((float)alpha) + 2.3f * __log2f((float)a) > 1.1f * __log2f((float)t);
+}
+
 // max / min over the warp of NON-NEGATIVE doubles: their bit patterns order like unsigned integers, so two 32-bit hardware
 // reductions (redux.sync) replace five shuffle rounds.  A NaN operand wins the max (and is then caught by the caller's checks).
 __device__ __forceinline__ double wmax(double v) {
@@ -946,6 +953,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                     sig = v != 0.0 ? 1.0 : 0.0; w1 = v; y = v;
                 } else {
                     const double lr = bb.has_lo ? relax_lo(bb.lo) : 0.0, hr = bb.has_hi ? relax_hi(bb.hi) : 0.0;
+                    const bool upd = !S.reinit && S.pending;
                     if (S.reinit) {
                         double sv = e.c;
                         if (bb.has_lo && bb.has_hi) {
@@ -957,21 +965,15 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                         rs_ = sv; rzl_ = bb.has_lo ? 1.0 : 0.0; rzu_ = bb.has_hi ? 1.0 : 0.0;
                     } else if (S.pending) {
                         rs_ += S.alpha * rds_;
-                        if (bb.has_lo) {
-                            const double gap = rs_ - lr;
-                            const double mg = fdiv(S.mu, gap);
-                            rzl_ = fmax(fmin(rzl_ + S.alpha_z * rel_, DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
-                        }
-                        if (bb.has_hi) {
-                            const double gap = hr - rs_;
-                            const double mg = fdiv(S.mu, gap);
-                            rzu_ = fmax(fmin(rzu_ + S.alpha_z * reu_, DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
-                        }
                     }
                     const double rc = e.c - rs_;
                     double lp = 1.0;
                     if (bb.has_lo) {
                         const double gap = rs_ - lr, inv = frcp(gap);
+                        if (upd) {   // multiplier step with the kappa_sigma safeguard (mu / gap = mu * inv)
+                            const double mg = S.mu * inv;
+                            rzl_ = fmax(fmin(rzl_ + S.alpha_z * rel_, DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
+                        }
                         sig += rzl_ * inv; binv += inv; y -= rzl_;
                         const double cz = gap * rzl_;
                         t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzl_;
@@ -979,6 +981,10 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                     }
                     if (bb.has_hi) {
                         const double gap = hr - rs_, inv = frcp(gap);
+                        if (upd) {
+                            const double mg = S.mu * inv;
+                            rzu_ = fmax(fmin(rzu_ + S.alpha_z * reu_, DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
+                        }
                         sig += rzu_ * inv; binv -= inv; y += rzu_;
                         const double cz = gap * rzu_;
                         t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzu_;
@@ -1254,7 +1260,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             for (int qf = 0; qf < S.nf; qf++)
                 if (th_t >= sm.filt_th[qf] && ph_t >= sm.filt_ph[qf]) in_filter = true;
             if (in_filter) continue;
-            const bool sw = dphi < 0.0 && theta <= sm.cold[C_THETA_MIN] && switch_cond(alpha, -dphi, theta);
+            const bool sw = dphi < 0.0 && theta <= sm.cold[C_THETA_MIN] && switch_cond_fast(alpha, -dphi, theta);
             if (sw) { if (ph_t <= phi + 1e-8 * alpha * dphi + eps_phi) accepted = 1; }
             else if (th_t <= (1.0 - 1e-5) * theta || ph_t <= phi - 1e-5 * theta + eps_phi) accepted = 2;
             if (accepted) { carry_log = lg_t; break; }
