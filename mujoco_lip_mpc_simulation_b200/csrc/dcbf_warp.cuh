@@ -538,8 +538,19 @@ struct LipW {
         if ((unsigned)lp < 9u) {   // position block on lanes 16..24: node kn = lp/3 + 1, component lp % 3
             const int kn = lp / 3 + 1, c = lp % 3;
             double acc = sm.nd.nobj[kn][4 + c];
-            for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * ms + j][c];
-            if (kn < 3) for (int j = 0; j < Ks; j++) acc = fma(gm1, sm.HQ[kn * ms + j][c], acc);
+            if (NS == 1) {   // at most six D-CBF rows per step: fixed trip count, rows beyond Ks masked (no loop bookkeeping)
+                const int r0 = (kn - 1) * ms, r1 = kn < 3 ? kn * ms : r0;
+                const double g1 = kn < 3 ? gm1 : 0.0;
+#pragma unroll
+                for (int j = 0; j < KsMax<1>::v; j++) {
+                    const int jj = j < Ks ? j : 0;
+                    const double a0 = sm.HQ[r0 + jj][c], a1 = sm.HQ[r1 + jj][c];
+                    acc += j < Ks ? fma(g1, a1, a0) : 0.0;
+                }
+            } else {
+                for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * ms + j][c];
+                if (kn < 3) for (int j = 0; j < Ks; j++) acc = fma(gm1, sm.HQ[kn * ms + j][c], acc);
+            }
             sm.nd.NHf[8 * (kn - 1) + c] = acc;
         } else if (lane < 3) {     // heading / velocity entries of node kn = lane + 1 (rows of step kn - 1)
             const int kn = lane + 1, i = kn - 1, base = i * ms + Ks;
@@ -882,7 +893,6 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
     const int Ks = M::template setup<NS>(sm, P, in, b, lane);
     const int ms = M::rows_per_step(P, Ks);   // rows per step
     const int m = 3 * ms;
-    const int mp = (m + 1) & ~1;             // dot products run over row pairs
     // Unrolled kernels (one slot; two slots for the LIP models): descriptor, bounds and row state live in registers.  Rolled
     // kernels: descriptor and bounds are recomputed per slot (a few integer instructions) and the state sits in sm.RS.
     constexpr bool ROLLED = Sh::ROLLED;
@@ -1025,13 +1035,19 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             const int d = dsc[t];
             if (d >= 0) {
                 const double *pp = stf + (d & 0xff) * RP, *pq = stf + ((d >> 8) & 0xff) * RP;
-                const int lo = M::class_start((d >> 16) & 0xf, Ks, ms) & ~1, eo = d >> 20;
-                double acc0 = 0.0, acc1 = 0.0;
-                for (int r = mp - 2; r >= lo; r -= 2) {
+                const int eo = d >> 20;
+                // Fixed trip count over the whole padded row range (rows beyond m and rows of earlier steps hold zeros): the loop
+                // unrolls completely.  A per-lane start row (rows of steps before the entry's class cannot contribute) executed
+                // fewer FMAs but twice the instructions -- remainder ladders, divergence bookkeeping, address decoding per block.
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 32 * NS; r += 4) {
                     const double2 u = *reinterpret_cast<const double2 *>(pp + r), v = *reinterpret_cast<const double2 *>(pq + r);
+                    const double2 u2 = *reinterpret_cast<const double2 *>(pp + r + 2), v2 = *reinterpret_cast<const double2 *>(pq + r + 2);
                     acc0 = fma(u.x, v.x, acc0); acc1 = fma(u.y, v.y, acc1);
+                    acc2 = fma(u2.x, v2.x, acc2); acc3 = fma(u2.y, v2.y, acc3);
                 }
-                double acc = acc0 + acc1;
+                double acc = (acc0 + acc1) + (acc2 + acc3);
                 if (eo >= KQ_K) acc += M::template hess_entry<NS>(sm, cs_, eo - KQ_K, sf_eff);   // Lagrangian Hessian
                 sm.KQ[eo] = acc;
             }
