@@ -977,29 +977,26 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                         rs_ += S.alpha * rds_;
                     }
                     const double rc = e.c - rs_;
-                    double lp = 1.0;
-                    if (bb.has_lo) {
-                        const double gap = rs_ - lr, inv = frcp(gap);
-                        if (upd) {   // multiplier step with the kappa_sigma safeguard (mu / gap = mu * inv)
-                            const double mg = S.mu * inv;
-                            rzl_ = fmax(fmin(rzl_ + S.alpha_z * rel_, DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
-                        }
-                        sig += rzl_ * inv; binv += inv; y -= rzl_;
-                        const double cz = gap * rzl_;
-                        t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzl_;
-                        lp *= gap; rel_ = inv;
+                    // both sides in straight-line code (an absent side has gap 1 and multiplier 0): the lanes of a warp hold rows with a
+                    // lower bound, an upper bound or both, so the two guarded blocks ran for the whole warp anyway -- plus their
+                    // divergence bookkeeping
+                    const double gl = bb.has_lo ? rs_ - lr : 1.0, gh = bb.has_hi ? hr - rs_ : 1.0;
+                    const double il = frcp(gl), ih = frcp(gh);
+                    if (upd) {   // multiplier step with the kappa_sigma safeguard (mu / gap = mu * inv)
+                        const double ml = S.mu * il, mh = S.mu * ih;
+                        const double zl = fmax(fmin(rzl_ + S.alpha_z * rel_, DCBF_KAPPA_SIGMA * ml), ml * (1.0 / DCBF_KAPPA_SIGMA));
+                        const double zu = fmax(fmin(rzu_ + S.alpha_z * reu_, DCBF_KAPPA_SIGMA * mh), mh * (1.0 / DCBF_KAPPA_SIGMA));
+                        rzl_ = bb.has_lo ? zl : 0.0; rzu_ = bb.has_hi ? zu : 0.0;
                     }
-                    if (bb.has_hi) {
-                        const double gap = hr - rs_, inv = frcp(gap);
-                        if (upd) {
-                            const double mg = S.mu * inv;
-                            rzu_ = fmax(fmin(rzu_ + S.alpha_z * reu_, DCBF_KAPPA_SIGMA * mg), mg * (1.0 / DCBF_KAPPA_SIGMA));
-                        }
-                        sig += rzu_ * inv; binv -= inv; y += rzu_;
-                        const double cz = gap * rzu_;
-                        t_cmin = fmin(t_cmin, cz); t_cmax = fmax(t_cmax, cz); t_z += rzu_;
-                        lp *= gap; reu_ = inv;
-                    }
+                    sig = fma(rzl_, il, rzu_ * ih);
+                    binv = (bb.has_lo ? il : 0.0) - (bb.has_hi ? ih : 0.0);
+                    y = rzu_ - rzl_;
+                    const double czl = gl * rzl_, czu = gh * rzu_;
+                    t_cmin = fmin(bb.has_lo ? czl : 1e300, bb.has_hi ? czu : 1e300);
+                    t_cmax = fmax(czl, czu);
+                    t_z = rzl_ + rzu_;
+                    const double lp = gl * gh;
+                    rel_ = il; reu_ = ih;
                     if (!carry_ok) t_log = dlog(lp);
                     rds_ = rc;
                     t_rc = fabs(rc);
@@ -1209,25 +1206,20 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 double jd = 0.0;
 #pragma unroll
                 for (int a = 0; a < N; a++) jd = fma(sm.ST[a][r], sm.dz[a], jd);
-                const RowBnd &e = bb;
                 const double d = jd + rds_;
                 rds_ = d;
-                if (e.has_lo) {
-                    const double inv = rel_, gap = rs_ - relax_lo(e.lo);
-                    const double dzl = S.mu * inv - rzl_ - rzl_ * inv * d;
-                    rel_ = dzl;
-                    dphi -= S.mu * d * inv;
-                    if (d < 0.0) amax = fmin(amax, fdiv(-tau * gap, d));
-                    if (dzl < 0.0) az = fmin(az, fdiv(-tau * rzl_, dzl));
-                }
-                if (e.has_hi) {
-                    const double inv = reu_, gap = relax_hi(e.hi) - rs_;
-                    const double dzu = S.mu * inv - rzu_ + rzu_ * inv * d;
-                    reu_ = dzu;
-                    dphi += S.mu * d * inv;
-                    if (d > 0.0) amax = fmin(amax, fdiv(tau * gap, d));
-                    if (dzu < 0.0) az = fmin(az, fdiv(-tau * rzu_, dzu));
-                }
+                // both sides in straight-line code (see the full pass); rel_ / reu_ hold the reciprocal gaps on entry
+                const double il = rel_, ih = reu_;
+                const double gl = bb.has_lo ? rs_ - relax_lo(bb.lo) : 1.0, gh = bb.has_hi ? relax_hi(bb.hi) - rs_ : 1.0;
+                const double dzl = S.mu * il - rzl_ - rzl_ * il * d;
+                const double dzu = S.mu * ih - rzu_ + rzu_ * ih * d;
+                rel_ = dzl; reu_ = dzu;
+                dphi += S.mu * d * ((bb.has_hi ? ih : 0.0) - (bb.has_lo ? il : 0.0));
+                const double tl = -tau * gl, th = tau * gh;
+                const double a1 = fdiv(tl, d), a2 = fdiv(th, d);
+                amax = fmin(amax, fmin(bb.has_lo && d < 0.0 ? a1 : 1.0, bb.has_hi && d > 0.0 ? a2 : 1.0));
+                const double z1 = fdiv(-tau * rzl_, dzl), z2 = fdiv(-tau * rzu_, dzu);
+                az = fmin(az, fmin(bb.has_lo && dzl < 0.0 ? z1 : 1.0, bb.has_hi && dzu < 0.0 ? z2 : 1.0));
                 DCBF_ROW_END
             }
             __syncwarp();
@@ -1258,10 +1250,9 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 M::template eval_row<NS, false>(P, sm, rd, sm.zt, e);
                 const double stv = rs_ + alpha * rds_;
                 th_t += fabs(e.c - stv);
-                double lp = 1.0;
-                if (bb.has_lo) { const double gap = stv - relax_lo(bb.lo); if (!(gap > 0.0)) okv = false; lp *= gap; }
-                if (bb.has_hi) { const double gap = relax_hi(bb.hi) - stv; if (!(gap > 0.0)) okv = false; lp *= gap; }
-                lg_t += dlog(lp);
+                const double gl = bb.has_lo ? stv - relax_lo(bb.lo) : 1.0, gh = bb.has_hi ? relax_hi(bb.hi) - stv : 1.0;
+                okv = okv && gl > 0.0 && gh > 0.0;
+                lg_t += dlog(gl * gh);
             }
             __syncwarp();
 #pragma unroll
