@@ -538,18 +538,17 @@ struct LipW {
         if ((unsigned)lp < 9u) {   // position block on lanes 16..24: node kn = lp/3 + 1, component lp % 3
             const int kn = lp / 3 + 1, c = lp % 3;
             double acc = sm.nd.nobj[kn][4 + c];
+            const int r0 = (kn - 1) * ms, r1 = kn < 3 ? kn * ms : r0;
+            const double g1 = kn < 3 ? gm1 : 0.0;
             if (NS == 1) {   // at most six D-CBF rows per step: fixed trip count, rows beyond Ks masked (no loop bookkeeping)
-                const int r0 = (kn - 1) * ms, r1 = kn < 3 ? kn * ms : r0;
-                const double g1 = kn < 3 ? gm1 : 0.0;
 #pragma unroll
                 for (int j = 0; j < KsMax<1>::v; j++) {
                     const int jj = j < Ks ? j : 0;
                     const double a0 = sm.HQ[r0 + jj][c], a1 = sm.HQ[r1 + jj][c];
                     acc += j < Ks ? fma(g1, a1, a0) : 0.0;
                 }
-            } else {
-                for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * ms + j][c];
-                if (kn < 3) for (int j = 0; j < Ks; j++) acc = fma(gm1, sm.HQ[kn * ms + j][c], acc);
+            } else {         // same arithmetic in the same order (the size-class split must not change a result)
+                for (int j = 0; j < Ks; j++) acc += fma(g1, sm.HQ[r1 + j][c], sm.HQ[r0 + j][c]);
             }
             sm.nd.NHf[8 * (kn - 1) + c] = acc;
         } else if (lane < 3) {     // heading / velocity entries of node kn = lane + 1 (rows of step kn - 1)
