@@ -118,6 +118,13 @@ inline bool build_warp_tables(const Consts &k, WarpTables &W) {
             }
         }
     }
+    // the kernels unroll the table per assembly round: round 0 up to 6 terms, round 1 up to 2, round 2 no matrix entries (LipW::round_terms)
+    for (int t = 0; t < 72; t++) {
+        const int out = W.desc[t] >> 20, rnd = t / 32;
+        if (out < KQ_K) continue;
+        const int lim = rnd == 0 ? 6 : (rnd == 1 ? 2 : 0);
+        for (int h = lim; h < NHT; h++) if (W.hc[h][out - KQ_K] != 0.0) return false;
+    }
     // ---- gradient coefficient vectors ------------------------------------------------------------------------------------
     for (int c = 0; c < 10; c++) for (int j = 0; j < 6; j++) W.cab[c][j] = 0.0;
     for (int i = 0; i < 3; i++) for (int l = 0; l < 3; l++) {
@@ -430,28 +437,20 @@ struct LipW {
         const double (*nodes)[5] = sm.nd.nodes;
         if (rd.type == RT_CBF) {
             eval_cbf<GRAD>(sm.obs[rd.obs], P.gamma - 1.0, nodes[kn][0], nodes[kn][1], nodes[i][0], nodes[i][1], e);
-        } else if (rd.type == RT_LEG) {
-            const double lx = nodes[i][0] - z[2 * i], ly = nodes[i][1] - z[2 * i + 1];
-            e.c = lx * lx + ly * ly;
-            if (GRAD) { e.q0 = 2.0 * lx; e.q1 = 2.0 * ly; }
-        } else if (rd.type == RT_DTH) {
-            e.c = z[6 + i];
-            if (GRAD) e.t_own = 1.0;
-        } else if (rd.type != RT_NONE) {   // v_bx, v_by, fen+, fen-
+        } else if (rd.type != RT_NONE) {
+            // every other row is  al * v_bx + be * v_by + ga * turn_i + de * |pos_i - foot_i|^2  with coefficients of the row type
+            // (one code path for the twelve non-D-CBF lanes instead of three)
+            const int t = rd.type;
+            const double al = (t == RT_VBX || t == RT_FENP || t == RT_FENM) ? 1.0 : 0.0, be = t == RT_VBY ? 1.0 : 0.0;
+            const double ga = t == RT_DTH ? 1.0 : (t == RT_FENP ? P.s_turn : (t == RT_FENM ? -P.s_turn : 0.0)), de = t == RT_LEG ? 1.0 : 0.0;
             const double sn = sm.nd.trig[kn][0], cs = sm.nd.trig[kn][1];
             const double vx = nodes[kn][2], vy = nodes[kn][3];
             const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
-            if (rd.type == RT_VBY) {
-                e.c = vby;
-                if (GRAD) { e.p0 = -sn; e.p1 = cs; e.t_all = -vbx; }
-            } else {
-                if (GRAD) { e.p0 = cs; e.p1 = sn; e.t_all = vby; }
-                if (rd.type == RT_VBX) e.c = vbx;
-                else {
-                    const double sg = rd.type == RT_FENP ? P.s_turn : -P.s_turn;
-                    e.c = vbx + sg * z[6 + i];
-                    if (GRAD) e.t_own = sg;
-                }
+            const double lx = nodes[i][0] - z[2 * i], ly = nodes[i][1] - z[2 * i + 1];
+            e.c = (al * vbx + be * vby) + (ga * z[6 + i] + de * (lx * lx + ly * ly));
+            if (GRAD) {
+                e.p0 = al * cs - be * sn; e.p1 = al * sn + be * cs; e.t_all = al * vby - be * vbx; e.t_own = ga;
+                e.q0 = de * 2.0 * lx; e.q1 = de * 2.0 * ly;
             }
         }
     }
@@ -567,14 +566,17 @@ struct LipW {
     }
     template <int NS>
     static __device__ __forceinline__ void hess_curvature(WarpShared<LipW, NS> &, int, double, const double *) {}
-    // Lagrangian Hessian of matrix entry e (packed index) through the table
+    // Lagrangian Hessian of matrix entry e (packed index) through the table.  TERMS = the largest number of table terms an entry of
+    // this assembly round has (round 0 holds the entries among the variables of step 0: up to 6; round 1: 2; round 2 has vector
+    // entries only) -- build_warp_tables() verifies the bound
     template <int NS>
-    static __device__ __forceinline__ double hess_entry(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int e, double sf) {
+    static __device__ __forceinline__ double hess_entry(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int e, double sf, int terms) {
         double acc = 0.0;
 #pragma unroll
-        for (int h = 0; h < NHT; h++) acc = fma(cs_.hc[h][e], sm.nd.NHf[cs_.hs[h][e]], acc);
+        for (int h = 0; h < NHT; h++) if (h < terms) acc = fma(cs_.hc[h][e], sm.nd.NHf[cs_.hs[h][e]], acc);   // `terms` is a constant after unrolling
         return acc;
     }
+    static __host__ __device__ constexpr int round_terms(int t) { return t == 0 ? 6 : (t == 1 ? 2 : 0); }
 
     // objective terms at one node: f, (nx, ny, nt), Hessian (xx, xy, yy, xt, yt, tt) scaled by sf; shared with the DD model
     static __device__ __forceinline__ void node_objective(const dcbf_params &P, const double *goal, double w, double x, double y, double th, double sf,
@@ -805,8 +807,9 @@ struct DdW {
         }
     }
     // Lagrangian Hessian of matrix entry e = tri(a, b), a >= b
+    static __host__ __device__ constexpr int round_terms(int) { return 1; }
     template <int NS>
-    static __device__ __forceinline__ double hess_entry(const WarpShared<DdW, NS> &sm, const CtaShared &cs_, int e, double sf) {
+    static __device__ __forceinline__ double hess_entry(const WarpShared<DdW, NS> &sm, const CtaShared &cs_, int e, double sf, int) {
         int a = 0;
         while ((a + 1) * (a + 2) / 2 <= e) a++;
         const int b = e - a * (a + 1) / 2;
@@ -1044,7 +1047,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                     acc2 = fma(u2.x, v2.x, acc2); acc3 = fma(u2.y, v2.y, acc3);
                 }
                 double acc = (acc0 + acc1) + (acc2 + acc3);
-                if (eo >= KQ_K) acc += M::template hess_entry<NS>(sm, cs_, eo - KQ_K, sf_eff);   // Lagrangian Hessian
+                if (M::round_terms(t) > 0 && eo >= KQ_K) acc += M::template hess_entry<NS>(sm, cs_, eo - KQ_K, sf_eff, M::round_terms(t));   // Lagrangian Hessian
                 sm.KQ[eo] = acc;
             }
         }
