@@ -224,9 +224,34 @@ def gen_helpers():
     print("helpers:", len(out), "arrays")
 
 
+def gen_data_log():
+    """A sample of the reference's RECORDED runs (data_log/LIP_me*.pkl, written by data_procs/logger_mpc.py:449-474 on the authors'
+    machine): plan trajectories with their feasible / failed label and the obstacle field of the run.  These are outputs of the
+    real reference pipeline (cyipopt included), not of anything in this repository."""
+    import pickle
+    rec = {k: [] for k in ("plan", "label", "run")}
+    fields_c, fields_e = [], []
+    for ri, name in enumerate(("me1", "me2", "me3", "me7", "me12")):
+        pre = os.path.join(ref_loader.REFERENCE_ROOT, "data_log", f"LIP_{name}_")
+        load = lambda k: pickle.load(open(pre + k + ".pkl", "rb"))   # noqa: E731
+        fields_c.append(np.asarray(load("cir"), dtype=np.float64)); fields_e.append(np.asarray(load("ellp"), dtype=np.float64))
+        for lab, key in ((0, "pred_feasi_end"), (2, "pred_fail_end")):
+            plans = load(key)
+            take = plans[:: max(1, len(plans) // 12)][:12]
+            for a in take:
+                rec["plan"].append(np.asarray(a, dtype=np.float64)); rec["label"].append(lab); rec["run"].append(ri)
+    np.savez_compressed(os.path.join(OUT, "data_log_plans.npz"), plan=np.array(rec["plan"]), label=np.array(rec["label"]),
+                        run=np.array(rec["run"]), cir=np.array(fields_c), elp=np.array(fields_e))
+    print("data_log:", len(rec["plan"]), "recorded plans,", int(np.sum(np.array(rec["label"]) == 2)), "labelled infeasible")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--data-log-only" in sys.argv:
+        gen_data_log()
+        sys.exit(0)
     gen_helpers()
+    gen_data_log()
     if "--helpers-only" in sys.argv:
         sys.exit(0)
     for form, seed in (("sig_step", 101), ("modi", 102), ("dd", 103)):

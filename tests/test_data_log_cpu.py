@@ -1,0 +1,72 @@
+"""CPU tests against the reference's RECORDED runs (tests/golden/data_log_plans.npz: plan trajectories, feasible / failed labels and
+obstacle fields copied out of /root/reference/data_log/LIP_me*.pkl by oracle/gen_golden.py:gen_data_log).  These arrays were produced
+by the real reference pipeline -- MPCCBF.gen_control_test with cyipopt on the authors' machine -- so they pin what nothing else in the
+repository can: the dense plan trajectory (xk_track_det) bit for bit, and the meaning of the pred_fail label (Ipopt status 2) in terms
+of the D-CBF rows."""
+import os
+
+import numpy as np
+
+from mujoco_lip_mpc_simulation_b200 import _lipmodel, data_log
+from oracle import lip_np
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "data_log_plans.npz"))
+SAFE_DIS, GAMMA = 0.4, 0.2      # main_sim_mpc.py:11, MPC_LIP_modi.py:405
+
+
+def test_recorded_plan_trajectories_are_lip_flows_of_a_plan():
+    for a in G["plan"]:
+        x, v, p, res = data_log.plan_from_pos_det(a)
+        assert res <= 1e-12
+        # the restated xk_track_det reproduces the record from the recovered plan
+        seg = np.concatenate([_lipmodel.track_det(np.concatenate([x[j], v[j], [0.0]]), np.concatenate([p[j], [0.0]]), 0.4) for j in range(3)])
+        np.testing.assert_allclose(seg, a, rtol=0, atol=1e-12)
+        # consecutive segments chain through the step-to-step map  x+ = A x + B p
+        k = _lipmodel.constants()
+        for j in range(2):
+            nxt = k.A @ np.concatenate([x[j], v[j], [0.0]]) + k.B @ np.concatenate([p[j], [0.0]])
+            np.testing.assert_allclose(nxt[0:2], x[j + 1], atol=1e-9)
+            np.testing.assert_allclose(nxt[2:4], v[j + 1], atol=1e-8)
+
+
+def _cbf_rows(plan, cir, elp):
+    x, v, p, _ = data_log.plan_from_pos_det(plan)
+    k = _lipmodel.constants()
+    pos = [x[0], x[1], x[2], (k.A @ np.concatenate([x[2], v[2], [0.0]]) + k.B @ np.concatenate([p[2], [0.0]]))[0:2]]
+    cs = cir + np.array([0.0, 0.0, SAFE_DIS])
+    es = elp + np.array([0.0, 0.0, SAFE_DIS, SAFE_DIS, 0.0])
+    rows = []
+    for i in range(3):
+        for c in cs:
+            rows.append(lip_np.h_circle(c, *pos[i + 1]) + (GAMMA - 1.0) * lip_np.h_circle(c, *pos[i]))
+        for e in es:
+            rows.append(lip_np.h_ellipse(e, *pos[i + 1]) + (GAMMA - 1.0) * lip_np.h_ellipse(e, *pos[i]))
+    return np.array(rows)
+
+
+def test_recorded_labels_match_the_dcbf_rows():
+    """the plans the reference filed under pred_fail (Ipopt status 2) violate a D-CBF row, the others do not."""
+    worst = np.array([_cbf_rows(a, G["cir"][r], G["elp"][r]).min() for a, r in zip(G["plan"], G["run"])])
+    fail, feasi = G["label"] == 2, G["label"] == 0
+    assert np.mean(worst[fail] < -1e-4) >= 0.9, worst[fail]
+    assert np.mean(worst[feasi] >= -1e-4) >= 0.95, worst[feasi]
+
+
+def test_run_files_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    traj = np.concatenate([rng.normal(size=(6, 7)), np.zeros((6, 1))], axis=1)
+    traj[4, 7] = 2.0
+    traj = np.concatenate([traj, np.full((2, 8), np.nan)])
+    plans = rng.normal(size=(8, 126, 2))
+    run = data_log.run_from_rollout(traj, G["cir"][0], G["elp"][0], plans=plans)
+    assert len(run["pos"]) == 6 and len(run["pred_fail_end"]) == 1 and len(run["pred_feasi_end"]) == 5
+    pre = str(tmp_path / "LIP_test_")
+    data_log.write_run(pre, run)
+    back = data_log.read_run(pre)
+    assert set(back) == set(run)
+    assert isinstance(back["cir"], list) and isinstance(back["cir"][0], list) and isinstance(back["pred_full_end"], list)
+    for kk in ("pos", "time", "foot", "heading", "body_vel", "real_end"):
+        assert isinstance(back[kk], np.ndarray)
+        np.testing.assert_array_equal(back[kk], run[kk])
+    np.testing.assert_array_equal(back["pred_fail_end"][0], plans[4])
+    np.testing.assert_array_equal(back["pred_end"][2], plans[2][[0, 41]])

@@ -125,3 +125,28 @@ def test_lean_elementary_functions_on_the_device():
     assert np.max(np.abs(o[:, 3] * b - 1.0)) <= 3e-16
     assert np.max(np.abs(o[:, 4] - a / b) / np.abs(a / b)) <= 3e-16
     assert np.max(np.abs(o[:, 5] * np.sqrt(np.abs(b)) - 1.0)) <= 5e-16
+
+
+def test_eval_kernel_reproduces_recorded_labels():
+    """the D-CBF rows of the evaluation kernel (dcbf_eval, modi) at the plans the reference RECORDED (tests/golden/data_log_plans.npz,
+    see tests/test_data_log_cpu.py): plans filed under pred_fail (Ipopt status 2) violate a D-CBF row, the others do not"""
+    import os
+    from mujoco_lip_mpc_simulation_b200 import data_log
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "data_log_plans.npz"))
+    cir = G["cir"] + np.array([0.0, 0.0, 0.4])
+    elp = G["elp"] + np.array([0.0, 0.0, 0.4, 0.4, 0.0])
+    n = len(G["plan"])
+    x0, z = np.zeros((n, 5)), np.zeros((n, 9))
+    for b, a in enumerate(G["plan"]):
+        x, v, p, _ = data_log.plan_from_pos_det(a)
+        x0[b, 0:2], x0[b, 2:4] = x[0], v[0]
+        z[b, 0::3], z[b, 1::3] = p[:, 0], p[:, 1]
+    s = DcbfSolver("modi", device=0)
+    s.set_fields(cir, elp)
+    ev = s.evaluate(x0, np.tile([10.0, 10.0], (n, 1)), np.ones(n, np.int32), z, field=G["run"].astype(np.int32), want_hess=False)
+    c = ev["c"].cpu().numpy().reshape(n, 3, 5 + 8)          # per step: v_bx, v_by, 4 circles, 4 ellipses, leg, turn, coupling
+    worst = c[:, :, 2:10].reshape(n, -1).min(axis=1)
+    fail, feasi = G["label"] == 2, G["label"] == 0
+    assert np.mean(worst[fail] < -1e-4) >= 0.9 and np.mean(worst[feasi] >= -1e-4) >= 0.95
+    # and the leg-length row holds to Ipopt's bound relaxation on every recorded plan (SURVEY.md section 4)
+    assert np.max(c[:, :, 10]) <= 0.09 + 1e-6
