@@ -240,8 +240,22 @@ def gen_data_log():
             take = plans[:: max(1, len(plans) // 12)][:12]
             for a in take:
                 rec["plan"].append(np.asarray(a, dtype=np.float64)); rec["label"].append(lab); rec["run"].append(ri)
+    # differential-drive runs (data_procs/logger_dd.py:445-466): plans are the four states [x, y, theta] of gen_dd_control
+    dd = {k: [] for k in ("plan", "label", "run")}
+    dd_c, dd_e = [], []
+    for ri, name in enumerate(("me1", "me4", "me9", "me15")):
+        pre = os.path.join(ref_loader.REFERENCE_ROOT, "data_log", f"DD_{name}_")
+        load = lambda k: pickle.load(open(pre + k + ".pkl", "rb"))   # noqa: E731
+        dd_c.append(np.asarray(load("cir"), dtype=np.float64)); dd_e.append(np.asarray(load("ellp"), dtype=np.float64))
+        for lab, key in ((0, "pred_feasi_end"), (2, "pred_fail_end")):
+            plans = load(key)
+            for a in plans[:: max(1, len(plans) // 16)][:16]:
+                dd["plan"].append(np.asarray(a, dtype=np.float64)); dd["label"].append(lab); dd["run"].append(ri)
     np.savez_compressed(os.path.join(OUT, "data_log_plans.npz"), plan=np.array(rec["plan"]), label=np.array(rec["label"]),
-                        run=np.array(rec["run"]), cir=np.array(fields_c), elp=np.array(fields_e))
+                        run=np.array(rec["run"]), cir=np.array(fields_c), elp=np.array(fields_e),
+                        dd_plan=np.array(dd["plan"]), dd_label=np.array(dd["label"]), dd_run=np.array(dd["run"]),
+                        dd_cir=np.array(dd_c), dd_elp=np.array(dd_e))
+    print("data_log DD:", len(dd["plan"]), "recorded plans,", int(np.sum(np.array(dd["label"]) == 2)), "labelled infeasible")
     print("data_log:", len(rec["plan"]), "recorded plans,", int(np.sum(np.array(rec["label"]) == 2)), "labelled infeasible")
 
 

@@ -52,6 +52,32 @@ def test_recorded_labels_match_the_dcbf_rows():
     assert np.mean(worst[feasi] >= -1e-4) >= 0.95, worst[feasi]
 
 
+def _dd_controls(plan, dt=0.4):
+    """(v_i, w_i) of a recorded DD plan: x+ = x + dt v cos th, y+ = y + dt v sin th, th+ = th + w (MPC_DD_sig_step.py:356-363)"""
+    d = np.diff(plan, axis=0)
+    v = (d[:, 0] * np.cos(plan[:3, 2]) + d[:, 1] * np.sin(plan[:3, 2])) / dt
+    return v, d[:, 2]
+
+
+def test_recorded_dd_plans_follow_the_unicycle_model_and_their_labels():
+    worst, defect = [], 0.0
+    for a, r in zip(G["dd_plan"], G["dd_run"]):
+        v, w = _dd_controls(a)
+        roll = lip_np.dd_rollout(a[0], np.stack([v, w], axis=1).ravel())
+        defect = max(defect, float(np.max(np.abs(np.asarray(roll)[1:] - a[1:]))))
+        cs = G["dd_cir"][r] + np.array([0.0, 0.0, SAFE_DIS])
+        es = G["dd_elp"][r] + np.array([0.0, 0.0, SAFE_DIS, SAFE_DIS, 0.0])
+        rows = []
+        for i in range(3):
+            rows += [lip_np.h_circle(c, *a[i + 1, :2]) + (GAMMA - 1.0) * lip_np.h_circle(c, *a[i, :2]) for c in cs]
+            rows += [lip_np.h_ellipse(e, *a[i + 1, :2]) + (GAMMA - 1.0) * lip_np.h_ellipse(e, *a[i, :2]) for e in es]
+        worst.append(min(rows))
+    assert defect <= 1e-12          # the recorded states are exactly the unicycle rollout of the recovered controls
+    worst = np.array(worst)
+    fail, feasi = G["dd_label"] == 2, G["dd_label"] == 0
+    assert np.mean(worst[fail] < -1e-4) >= 0.95 and np.mean(worst[feasi] >= -1e-4) >= 0.9   # SURVEY.md section 4: 100 % / 95 %
+
+
 def test_run_files_round_trip(tmp_path):
     rng = np.random.default_rng(0)
     traj = np.concatenate([rng.normal(size=(6, 7)), np.zeros((6, 1))], axis=1)

@@ -150,3 +150,21 @@ def test_eval_kernel_reproduces_recorded_labels():
     assert np.mean(worst[fail] < -1e-4) >= 0.9 and np.mean(worst[feasi] >= -1e-4) >= 0.95
     # and the leg-length row holds to Ipopt's bound relaxation on every recorded plan
     assert np.max(c[:, :, 10]) <= 0.09 + 1e-6
+
+
+def test_dd_eval_kernel_reproduces_recorded_labels():
+    """same for the differential-drive runs (data_log/DD_me*.pkl): recorded states -> controls -> dcbf_eval (dd) rows"""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "data_log_plans.npz"))
+    P = G["dd_plan"]
+    n = len(P)
+    d = np.diff(P, axis=1)
+    v = (d[:, :, 0] * np.cos(P[:, :3, 2]) + d[:, :, 1] * np.sin(P[:, :3, 2])) / 0.4
+    z = np.stack([v, d[:, :, 2]], axis=2).reshape(n, 6)
+    s = DcbfSolver("dd", device=0)
+    s.set_fields(G["dd_cir"] + np.array([0.0, 0.0, 0.4]), G["dd_elp"] + np.array([0.0, 0.0, 0.4, 0.4, 0.0]))
+    ev = s.evaluate(P[:, 0], np.tile([10.0, 10.0], (n, 1)), None, z, field=G["dd_run"].astype(np.int32), last_u=np.zeros((n, 2)), want_hess=False)
+    c = ev["c"].cpu().numpy().reshape(n, 3, 9)              # per step: 4 circles, 4 ellipses, coupling row
+    worst = c[:, :, :8].reshape(n, -1).min(axis=1)
+    fail, feasi = G["dd_label"] == 2, G["dd_label"] == 0
+    assert np.mean(worst[fail] < -1e-4) >= 0.95 and np.mean(worst[feasi] >= -1e-4) >= 0.9
