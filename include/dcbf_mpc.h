@@ -20,6 +20,8 @@
  *   dcbf_alip_foot       <- the closed-form ALIP foot placement behind the DD re-plan (Logger.ALIP_gen_foot_input,
  *                           data_procs/logger_dd.py:356-363 -> ALIP.AMprediction / computeSw2CoM / computeStepping /
  *                           regulate_lateral_step / getTimedState, ALIP_plan/planner.py:188-261,346-370)
+ *   dcbf_gen_fields /    <- rand_obs.gen_ran_obs_list (rand_obs.py:31-81) and the start state of the __main__ loop
+ *   dcbf_gen_states         (MPC_LIP_sig_step.py:553-568), batched, for the 1 M-scenario configuration
  *   dcbf_tick            <- one control tick of Logger.gen_nex_foot_input (data_procs/logger_mpc.py:318-341):
  *                           LIP prediction to the end of the running step (MPCCBF.get_next_states,
  *                           MPC_LIP_modi.py:149-178), the warm-start rule, the re-plan, and the dense plan trajectory
@@ -150,6 +152,29 @@ int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo
 int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double *y_alip, const double *time, const int32_t *support,
                    const double *speed, int32_t speed_stride, double H, double T, double m, double W, double *foot, double *am,
                    double *next, void *stream);
+
+/* Scenario generation on the device (rand_obs.py:31-81: random_circle / random_obs / gen_ran_obs_list restated for F fields
+ * at once).  Circles (x, y, r) with x, y in [0, margin), r in [0.35, radius], all rounded to two decimals, are rejection
+ * sampled against the keep-out discs (10, 10, 0.3) and (0, 0, 1.0) and against each other until `num` of them satisfy
+ * |c_i - c_j| >= r_i + r_j + 2 half_gap (rand_obs.py:31-54); with mix != 0 every odd-numbered one becomes an ellipse
+ * (a = r, b in [a/2, a), phi a whole number of degrees; rand_obs.py:57-72).  Unlike the reference loop this one terminates:
+ * a field that stalls for 2000 draws is restarted, at most 64 times; draws[F] (may be NULL) receives the candidates drawn
+ * or -1 for a field that could not be built (its obstacles are NaN).  The draws are Philox4x32-10 outputs keyed by
+ * (seed, field, draw number): the batch does not depend on the launch geometry and oracle/scenario_gen.py reproduces it
+ * bit for bit.  Outputs: cir[F][Kc][3], elp[F][Ke][5] with Kc = num, Ke = 0 (mix = 0) or Kc = ceil(num/2), Ke = floor(num/2);
+ * radii and semi-axes already inflated by safe_dis -- the layout dcbf_set_fields takes.  1 <= num <= 32. */
+int dcbf_gen_fields(dcbf_ctx *ctx, int32_t F, uint64_t seed, int32_t num, int32_t mix, double margin, double radius,
+                    double half_gap, double safe_dis, double *cir, double *elp, int32_t *draws, void *stream);
+
+/* Start states for B scenarios on the context's current fields (SURVEY.md 8(d) distribution, the batched form of the
+ * hand-written start of MPC_LIP_sig_step.py:553-568): position uniform in [0, 8)^2, redrawn (at most 64 times) until every
+ * obstacle's level set is >= 0.05 there; heading = bearing to the goal + U(-0.3, 0.3); leg = +-1; body velocity
+ * vx in [0.4, 0.8), |vy| in [0.15, bvy_max) with the sign of -leg (bvy_max <= 0: the formulation's bound).  field[B] may be
+ * NULL (field 0).  Outputs (any may be NULL): x0[B][5|3], goal[B][2], leg[B], warm[B][15|6] (cold start [x0, x0, x0]; dd:
+ * (0.8, 0) x 3), last_u[B][2] (dd), attempts[B] = positions tried, -1 if none was clear (x0 is NaN then). */
+int dcbf_gen_states(dcbf_ctx *ctx, int32_t B, uint64_t seed, const int32_t *field, double goal_x, double goal_y,
+                    double bvy_max, double *x0, double *goal, int32_t *leg, double *warm, double *last_u,
+                    int32_t *attempts, void *stream);
 
 /* Test hook: the lean FP64 elementary functions of the kernels (csrc/dcbf_math.cuh) evaluated on the device.
  * out[n][6] = (sin a, cos a, atan2(a, b), 1 / b, a / b, 1 / sqrt(|b|)); a, b, out are device pointers. */

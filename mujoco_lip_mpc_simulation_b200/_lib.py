@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libdcbf_mpc.so")
-SOURCES = ["dcbf_kernels.cu", "dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_warp.cuh", "dcbf_math.cuh"]
+SOURCES = ["dcbf_kernels.cu", "dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_warp.cuh", "dcbf_math.cuh", "dcbf_gen.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -32,7 +32,8 @@ class DcbfParams(C.Structure):
 # every symbol include/dcbf_mpc.h declares
 EXPORTS = ["dcbf_abi_version", "dcbf_default_params", "dcbf_create", "dcbf_destroy", "dcbf_last_error",
            "dcbf_set_fields", "dcbf_num_rows", "dcbf_num_vars", "dcbf_eval", "dcbf_solve", "dcbf_rollout",
-           "dcbf_set_fields_host", "dcbf_solve_host", "dcbf_launch_count", "dcbf_fp64_peak_tflops", "dcbf_tick", "dcbf_alip_foot", "dcbf_math_probe"]
+           "dcbf_set_fields_host", "dcbf_solve_host", "dcbf_launch_count", "dcbf_fp64_peak_tflops", "dcbf_tick", "dcbf_alip_foot", "dcbf_math_probe",
+           "dcbf_gen_fields", "dcbf_gen_states"]
 
 
 def needs_build() -> bool:
@@ -89,6 +90,8 @@ def load():
     lib.dcbf_tick.argtypes = [vp, C.c_int32] + [dp] * 21 + [vp]
     lib.dcbf_alip_foot.argtypes = [vp, C.c_int32] + [dp] * 5 + [C.c_int32] + [C.c_double] * 4 + [dp] * 3 + [vp]
     lib.dcbf_math_probe.argtypes = [vp, C.c_int32, dp, dp, dp, vp]
+    lib.dcbf_gen_fields.argtypes = [vp, C.c_int32, C.c_uint64, C.c_int32, C.c_int32] + [C.c_double] * 4 + [dp, dp, vp, vp]
+    lib.dcbf_gen_states.argtypes = [vp, C.c_int32, C.c_uint64, vp] + [C.c_double] * 3 + [dp, dp, vp, dp, dp, vp, vp]
     lib.dcbf_launch_count.argtypes = [vp]
     lib.dcbf_launch_count.restype = C.c_int64
     lib.dcbf_fp64_peak_tflops.argtypes = [vp, C.c_int32]

@@ -261,6 +261,37 @@ class DcbfSolver:
         self._check(rc, "dcbf_alip_foot")
         return dict(foot=foot, am=am, next=nxt)
 
+    def gen_fields(self, F, seed, num, mix=False, margin=8.5, radius=1.0, half_gap=0.8, safe_dis=0.4, install=True):
+        """F random obstacle fields on the device (dcbf_gen_fields: rand_obs.py:31-81 batched, with bounded restarts).
+        Returns dict(cir[F,Kc,3], elp[F,Ke,5], draws[F]); install=True also makes them the context's fields."""
+        Kc, Ke = ((num + 1) // 2, num // 2) if mix else (num, 0)
+        kw = dict(device=self.tdev, dtype=torch.float64)
+        cir, elp = torch.empty((F, Kc, 3), **kw), torch.empty((F, Ke, 5), **kw)
+        draws = torch.empty((F,), device=self.tdev, dtype=torch.int32)
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_gen_fields(self._ctx, int(F), int(seed) & 0xFFFFFFFFFFFFFFFF, int(num), int(bool(mix)), float(margin),
+                                          float(radius), float(half_gap), float(safe_dis), _ptr(cir), _ptr(elp) if Ke else None,
+                                          _ptr(draws), self._stream())
+        self._check(rc, "dcbf_gen_fields")
+        if install:
+            self.set_fields(cir, elp)
+        return dict(cir=cir, elp=elp, draws=draws)
+
+    def gen_states(self, B, seed, field=None, goal=(10.0, 10.0), bvy_max=0.0):
+        """B start states on the context's fields (dcbf_gen_states).  Returns dict(x0, goal, leg, warm, last_u|None, attempts)."""
+        fld = None if field is None else self._dev(field, torch.int32).reshape(B)
+        kw = dict(device=self.tdev, dtype=torch.float64)
+        x0, g, warm = torch.empty((B, self.nx), **kw), torch.empty((B, 2), **kw), torch.empty((B, self.nu), **kw)
+        leg = torch.empty((B,), device=self.tdev, dtype=torch.int32)
+        att = torch.empty((B,), device=self.tdev, dtype=torch.int32)
+        last_u = torch.empty((B, 2), **kw) if self.dd else None
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_gen_states(self._ctx, int(B), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(fld) if fld is not None else None,
+                                          float(goal[0]), float(goal[1]), float(bvy_max), _ptr(x0), _ptr(g), _ptr(leg), _ptr(warm),
+                                          _ptr(last_u) if last_u is not None else None, _ptr(att), self._stream())
+        self._check(rc, "dcbf_gen_states")
+        return dict(x0=x0, goal=g, leg=leg, warm=warm, last_u=last_u, attempts=att, field=fld)
+
     # ------------------------------------------------------------------------------------------------------
     def set_fields_host(self, cir, elp=None):
         cir = np.ascontiguousarray(np.zeros((1, 0, 3)) if cir is None else cir, dtype=np.float64)

@@ -15,6 +15,7 @@
 
 #include "dcbf_lanes.cuh"
 #include "dcbf_warp.cuh"
+#include "dcbf_gen.cuh"
 #include <stdlib.h>
 
 using namespace dcbf;
@@ -398,6 +399,31 @@ __global__ void math_probe_kernel(int n, const double *__restrict__ a, const dou
     o[0] = s; o[1] = c; o[2] = fatan2(a[i], b[i]); o[3] = dcbf::frcp(b[i]); o[4] = dcbf::fdiv(a[i], b[i]); o[5] = dcbf::frsqrt(fabs(b[i]));
 }
 
+// Scenario generation (dcbf_gen.cuh): one thread per obstacle field / per start state
+__global__ void gen_fields_kernel(int F, uint64_t seed, gen::FieldSpec S, double *__restrict__ cir, double *__restrict__ elp,
+                                  int32_t *__restrict__ draws) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int Kc = S.mix ? (S.num + 1) / 2 : S.num, Ke = S.mix ? S.num / 2 : 0;
+    const int n = gen::make_field(S, seed, (uint32_t)f, cir + 3 * (size_t)Kc * f, elp + 5 * (size_t)Ke * f);
+    if (draws) draws[f] = n;
+}
+struct GenSinCos { __device__ void operator()(double a, double *s, double *c) const { sincos(a, s, c); } };
+struct GenAtan2 { __device__ double operator()(double y, double x) const { return atan2(y, x); } };
+__global__ void gen_states_kernel(int B, uint64_t seed, gen::StateSpec S, const int32_t *__restrict__ field, const double *__restrict__ cir_rec,
+                                  int Kc, const double *__restrict__ elp_rec, int Ke, double *__restrict__ x0, double *__restrict__ goal,
+                                  int32_t *__restrict__ leg, double *__restrict__ warm, double *__restrict__ last_u, int32_t *__restrict__ attempts) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int fld = field ? field[b] : 0;
+    const int nx = S.dd ? 3 : 5, nw = S.dd ? 6 : 15;
+    const int n = gen::make_state(S, seed, (uint32_t)b, cir_rec + (size_t)fld * Kc * DCBF_CIR_REC, Kc, DCBF_CIR_REC,
+                                  elp_rec + (size_t)fld * Ke * DCBF_ELP_REC, Ke, DCBF_ELP_REC, x0 ? x0 + (size_t)nx * b : nullptr,
+                                  goal ? goal + 2 * (size_t)b : nullptr, leg ? leg + b : nullptr, warm ? warm + (size_t)nw * b : nullptr,
+                                  last_u ? last_u + 2 * (size_t)b : nullptr, GenSinCos(), GenAtan2());
+    if (attempts) attempts[b] = n;
+}
+
 // ALIP one-step foot placement (ALIP_plan/planner.py:188-261, 346-370), one thread per scenario
 __global__ void alip_foot_kernel(int B, const double *__restrict__ xa, const double *__restrict__ ya, const double *__restrict__ time,
                                  const int32_t *__restrict__ support, const double *__restrict__ speed, int stride, double H, double T,
@@ -773,6 +799,34 @@ int dcbf_math_probe(dcbf_ctx *ctx, int32_t n, const double *a, const double *b, 
     if (n == 0) return DCBF_OK;
     CK(cudaSetDevice(ctx->device));
     math_probe_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, a, b, out);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
+int dcbf_gen_fields(dcbf_ctx *ctx, int32_t F, uint64_t seed, int32_t num, int32_t mix, double margin, double radius, double half_gap,
+                    double safe_dis, double *cir, double *elp, int32_t *draws, void *stream) {
+    if (!ctx || F < 0 || num < 1 || num > DCBF_GEN_MAX_OBS || !(margin > 0.0) || !(radius >= 0.35) || !(half_gap >= 0.0)) return DCBF_ERR_ARG;
+    if (F == 0) return DCBF_OK;
+    if (!cir || (mix && num > 1 && !elp)) return DCBF_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    gen::FieldSpec S = {num, mix ? 1 : 0, margin, radius, half_gap, safe_dis, 2000, 64};
+    gen_fields_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, seed, S, cir, elp, draws);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
+int dcbf_gen_states(dcbf_ctx *ctx, int32_t B, uint64_t seed, const int32_t *field, double goal_x, double goal_y, double bvy_max,
+                    double *x0, double *goal, int32_t *leg, double *warm, double *last_u, int32_t *attempts, void *stream) {
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
+    if (B == 0) return DCBF_OK;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    CK(cudaSetDevice(ctx->device));
+    const int dd = ctx->P.formulation == DCBF_DD;
+    gen::StateSpec S = {dd, goal_x, goal_y, 8.0, 0.05, 0.3, 0.4, 0.8, 0.15, bvy_max > 0.0 ? bvy_max : ctx->P.bvy_max, 64};
+    gen_states_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, seed, S, field, ctx->cir_rec, ctx->Kc, ctx->elp_rec, ctx->Ke, x0, goal,
+                                                                        leg, warm, last_u, attempts);
     CK(cudaGetLastError());
     ctx->launches++;
     return DCBF_OK;

@@ -146,6 +146,23 @@ def make_batch(form: str, B: int, seed: int, n_fields: int | None = None, num_ob
     return ScenarioBatch(form, x0, g, leg, cir, elp, field, warm, None, safe_dis)
 
 
+def make_batch_device(solver, B: int, seed: int, n_fields: int | None = None, num_obs: int | None = None, goal=(10.0, 10.0),
+                      safe_dis: float = 0.4):
+    """The scenario distribution of make_batch drawn on the GPU (DcbfSolver.gen_fields / gen_states: dcbf_gen_fields,
+    dcbf_gen_states), nothing touches the host: n_fields obstacle fields (default one per scenario, up to 65536) are built and
+    installed as the solver's fields, then B start states on them.  Returns the dict of device tensors gen_states produces
+    plus cir / elp / draws; pass x0, goal, leg, warm, field, last_u straight to DcbfSolver.solve."""
+    form = {0: "sig_step", 1: "modi", 2: "dd"}[solver.form]
+    num, mix, half_gap = (num_obs or 6, False, 0.8) if form == "sig_step" else (num_obs or 10, True, 0.4)
+    F = min(B, n_fields or 65536)
+    fields = solver.gen_fields(F, seed * 7919 + 13, num, mix=mix, half_gap=half_gap, safe_dis=safe_dis)
+    import torch
+    fld = (torch.arange(B, device=solver.tdev, dtype=torch.int32) % F).contiguous()
+    out = solver.gen_states(B, seed, field=fld, goal=goal)
+    out.update(fields)
+    return out
+
+
 def config1():
     """The reference's own single scenario, MPC_LIP_sig_step.py:553-568."""
     cir = (np.array([[1, 1, 0.5], [2, 2, 0.5], [6, 4, 0.8], [7, 7, 1.0]]) + np.array([0, 0, 0.32]))[None]

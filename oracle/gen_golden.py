@@ -259,13 +259,66 @@ def gen_data_log():
     print("data_log:", len(rec["plan"]), "recorded plans,", int(np.sum(np.array(rec["label"]) == 2)), "labelled infeasible")
 
 
+def gen_rand_obs():
+    """Obstacle fields drawn by the reference generator itself (rand_obs.gen_ran_obs_list, rand_obs.py:74-81) under
+    random.seed(k): the reference never seeds, so these are samples of its distribution, used to pin the PROPERTIES the batched
+    generator must reproduce (ranges, rounding, separation) -- tests/test_scenario_gen_cpu.py."""
+    import random
+    ref_loader._install_stubs()
+    if ref_loader.REFERENCE_ROOT not in sys.path:
+        sys.path.append(ref_loader.REFERENCE_ROOT)
+    import importlib
+    ro = importlib.import_module("rand_obs")
+    import signal
+
+    class _Stall(Exception):
+        pass
+
+    def _alarm(*_):
+        raise _Stall()
+    signal.signal(signal.SIGALRM, _alarm)
+
+    def draw(seed, num, typ):
+        # random_circle has no exit when the circles placed so far leave no room (rand_obs.py:33-52): give each seed 2 s
+        random.seed(seed)
+        signal.setitimer(signal.ITIMER_REAL, 2.0)
+        try:
+            return ro.gen_ran_obs_list(num, typ)
+        except _Stall:
+            return None
+        finally:
+            signal.setitimer(signal.ITIMER_REAL, 0.0)
+    cir6, mixc, mixe, stalled = [], [], [], 0
+    k = 0
+    while len(cir6) < 48 and k < 400:
+        r = draw(1000 + k, 6, "cir"); k += 1
+        if r is None:
+            stalled += 1
+        else:
+            cir6.append(r[0])
+    k = 0
+    while len(mixc) < 48 and k < 400:
+        r = draw(2000 + k, 6, "mix"); k += 1
+        if r is None:
+            stalled += 1
+        else:
+            mixc.append(r[0]); mixe.append(r[1])
+    np.savez_compressed(os.path.join(OUT, "rand_obs_fields.npz"), cir6=np.array(cir6, dtype=np.float64),
+                        mix_cir=np.array(mixc, dtype=np.float64), mix_elp=np.array(mixe, dtype=np.float64), stalled=np.int64(stalled))
+    print("rand_obs:", len(cir6), "circle fields and", len(mixc), "mixed fields from the reference generator;", stalled, "seeds never finished")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--rand-obs-only" in sys.argv:
+        gen_rand_obs()
+        sys.exit(0)
     if "--data-log-only" in sys.argv:
         gen_data_log()
         sys.exit(0)
     gen_helpers()
     gen_data_log()
+    gen_rand_obs()
     if "--helpers-only" in sys.argv:
         sys.exit(0)
     for form, seed in (("sig_step", 101), ("modi", 102), ("dd", 103)):

@@ -9,6 +9,7 @@
 
 #include "../../mujoco_lip_mpc_simulation_b200/csrc/dcbf_lanes.cuh"
 #include "../../mujoco_lip_mpc_simulation_b200/csrc/dcbf_warp.cuh"   // host part only: the constant tables of the warp kernels
+#include "../../mujoco_lip_mpc_simulation_b200/csrc/dcbf_gen.cuh"    // scenario generator (same functions the kernels call)
 
 using namespace dcbf;
 
@@ -81,6 +82,35 @@ int hostsim_warp_tables(int *desc, double *hc, int *hs, double *cab, double *T) 
     double Tm[24][9];
     wp::build_feature_map(K, Tm);
     for (int f = 0; f < 24; f++) for (int v = 0; v < 9; v++) T[9 * f + v] = Tm[f][v];
+    return 0;
+}
+
+// scenario generator of csrc/dcbf_gen.cuh on the host (the kernels call the same two functions)
+int hostsim_philox(uint32_t *c, uint32_t k0, uint32_t k1) { gen::philox4x32_10(c, k0, k1); return 0; }
+
+int hostsim_gen_fields(int F, uint64_t seed, int num, int mix, double margin, double radius, double half_gap, double safe_dis,
+                       int stall, int max_restarts, double *cir, double *elp, int32_t *draws) {
+    gen::FieldSpec S = {num, mix, margin, radius, half_gap, safe_dis, stall, max_restarts};
+    const int Kc = mix ? (num + 1) / 2 : num, Ke = mix ? num / 2 : 0;
+    for (int f = 0; f < F; f++) draws[f] = gen::make_field(S, seed, (uint32_t)f, cir + 3 * (size_t)Kc * f, elp + 5 * (size_t)Ke * f);
+    return 0;
+}
+
+int hostsim_gen_states(int B, uint64_t seed, int dd, double gx, double gy, double bvy_max, const int32_t *field, int F, int Kc,
+                       const double *cir, int Ke, const double *elp, double *x0, double *goal, int32_t *leg, double *warm,
+                       double *last_u, int32_t *attempts) {
+    std::vector<double> cr, er;
+    prep(F, Kc, cir, Ke, elp, cr, er);
+    gen::StateSpec S = {dd, gx, gy, 8.0, 0.05, 0.3, 0.4, 0.8, 0.15, bvy_max, 64};
+    const int nx = dd ? 3 : 5, nw = dd ? 6 : 15;
+    for (int b = 0; b < B; b++) {
+        const int fld = field ? field[b] : 0;
+        attempts[b] = gen::make_state(S, seed, (uint32_t)b, cr.data() + (size_t)fld * Kc * DCBF_CIR_REC, Kc, DCBF_CIR_REC,
+                                      er.data() + (size_t)fld * Ke * DCBF_ELP_REC, Ke, DCBF_ELP_REC, x0 + (size_t)nx * b, goal + 2 * (size_t)b,
+                                      leg + b, warm + (size_t)nw * b, dd ? last_u + 2 * (size_t)b : nullptr,
+                                      [](double a, double *s, double *c) { *s = sin(a); *c = cos(a); },
+                                      [](double y, double x) { return atan2(y, x); });
+    }
     return 0;
 }
 

@@ -30,7 +30,7 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "hostsim", "libhostsim.so")
-        srcs = [os.path.join(_HERE, "hostsim", "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in ("dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_math.cuh", "dcbf_warp.cuh")]
+        srcs = [os.path.join(_HERE, "hostsim", "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in ("dcbf_core.cuh", "dcbf_lanes.cuh", "dcbf_math.cuh", "dcbf_warp.cuh", "dcbf_gen.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["sh", os.path.join(_HERE, "hostsim", "build.sh")])
         _LIB = C.CDLL(so)
@@ -147,3 +147,30 @@ def warp_tables():
     rc = lib().hostsim_warp_tables(_p(desc, C.c_int32), _p(hc), _p(hs, C.c_int32), _p(cab), _p(T))
     assert rc == 0
     return dict(desc=desc, hc=hc, hs=hs, cab=cab, T=T)
+
+
+def philox(counter, k0, k1):
+    c = np.ascontiguousarray(counter, dtype=np.uint32).copy()
+    lib().hostsim_philox(_p(c, C.c_uint32), C.c_uint32(k0), C.c_uint32(k1))
+    return c
+
+
+def gen_fields(F, seed, num, mix, margin=8.5, radius=1.0, half_gap=0.8, safe_dis=0.4, stall=2000, max_restarts=64):
+    """make_field of csrc/dcbf_gen.cuh for fields 0..F-1 (the function gen_fields_kernel calls per thread)."""
+    Kc, Ke = ((num + 1) // 2, num // 2) if mix else (num, 0)
+    cir, elp, draws = np.zeros((F, Kc, 3)), np.zeros((F, max(Ke, 1), 5)), np.zeros(F, np.int32)
+    lib().hostsim_gen_fields(F, C.c_uint64(seed), num, int(mix), C.c_double(margin), C.c_double(radius), C.c_double(half_gap),
+                             C.c_double(safe_dis), stall, max_restarts, _p(cir), _p(elp), _p(draws, C.c_int32))
+    return cir, elp[:, :Ke], draws
+
+
+def gen_states(B, seed, cir, elp, field=None, dd=False, goal=(10.0, 10.0), bvy_max=0.3):
+    F, cir, elp = _fields(cir, elp)
+    nx, nw = (3, 6) if dd else (5, 15)
+    field = None if field is None else np.ascontiguousarray(field, dtype=np.int32)
+    x0, g, warm, last_u = np.zeros((B, nx)), np.zeros((B, 2)), np.zeros((B, nw)), np.zeros((B, 2))
+    leg, att = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    lib().hostsim_gen_states(B, C.c_uint64(seed), int(dd), C.c_double(goal[0]), C.c_double(goal[1]), C.c_double(bvy_max),
+                             _p(field, C.c_int32), F, cir.shape[1], _p(cir), elp.shape[1], _p(elp), _p(x0), _p(g), _p(leg, C.c_int32),
+                             _p(warm), _p(last_u), _p(att, C.c_int32))
+    return dict(x0=x0, goal=g, leg=leg, warm=warm, last_u=last_u if dd else None, attempts=att)
