@@ -20,6 +20,8 @@
  *   dcbf_alip_foot       <- the closed-form ALIP foot placement behind the DD re-plan (Logger.ALIP_gen_foot_input,
  *                           data_procs/logger_dd.py:356-363 -> ALIP.AMprediction / computeSw2CoM / computeStepping /
  *                           regulate_lateral_step / getTimedState, ALIP_plan/planner.py:188-261,346-370)
+ *   dcbf_heading_input   <- Logger.tube_func + Logger.avg_hd, the heading-rate input of that prediction
+ *                           (data_procs/logger_mpc.py:208-215,278-300)
  *   dcbf_gen_fields /    <- rand_obs.gen_ran_obs_list (rand_obs.py:31-81) and the start state of the __main__ loop
  *   dcbf_gen_states         (MPC_LIP_sig_step.py:553-568), batched, for the 1 M-scenario configuration
  *   dcbf_tick            <- one control tick of Logger.gen_nex_foot_input (data_procs/logger_mpc.py:318-341):
@@ -152,6 +154,18 @@ int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo
 int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double *y_alip, const double *time, const int32_t *support,
                    const double *speed, int32_t speed_stride, double H, double T, double m, double W, double *foot, double *am,
                    double *next, void *stream);
+
+/* Heading input of the LIP prediction, the per-tick tail of Logger.update_n_record (data_procs/logger_mpc.py:278-281):
+ *   nex_turn <- tube_func(nex_turn, cur_hd)      the last plan's turn, scaled by 0.4 inside the +-0.15 rad tube and 0.7 outside
+ *                                                (logger_mpc.py:284-300), wrapped by angle_A_minus_B (:169-175)
+ *   hd_input <- avg_hd(cur_hd)                   (nex_turn + the three heading increments of the last plan, the first taken
+ *                                                from cur_hd) / 4   (logger_mpc.py:208-215)
+ * cur_hd[B]; nex_turn[B] is read and overwritten; the plan headings of scenario b are mpc_hds[b*hds_stride + k*hds_step],
+ * k = 0..2 (pass x_plan + 4 with stride 15 and step 5 to read them from the last dcbf_tick / dcbf_solve output); the result
+ * goes to hd_input[b*out_stride] (pass glo_p + 2 with stride 3 to write the third input column of dcbf_tick in place).
+ * After a re-plan the caller resets nex_turn from the new plan's first turn p_plan[b][0][2] (logger_mpc.py:341). */
+int dcbf_heading_input(dcbf_ctx *ctx, int32_t B, const double *cur_hd, double *nex_turn, const double *mpc_hds,
+                       int32_t hds_stride, int32_t hds_step, double *hd_input, int32_t out_stride, void *stream);
 
 /* Scenario generation on the device (rand_obs.py:31-81: random_circle / random_obs / gen_ran_obs_list restated for F fields
  * at once).  Circles (x, y, r) with x, y in [0, margin), r in [0.35, radius], all rounded to two decimals, are rejection

@@ -109,3 +109,27 @@ def tube(heading_list, init_tube_value, width, gain_in, gain_out=0.7):
             v += (gain_in if -width < d else gain_out) * d
         new[i] = v
     return new
+
+
+def angle_a_minus_b(a, b):
+    """Logger.angle_A_minus_B (data_procs/logger_mpc.py:169-175), elementwise."""
+    r = np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)
+    r = np.where((r < 0) & (np.abs(r) > math.pi), r + 2 * math.pi, np.where((r > 0) & (np.abs(r) > math.pi), r - 2 * math.pi, r))
+    return r
+
+
+def logger_tube(turning, cur_hd, width=0.15, gain_in=0.4, gain_out=0.7):
+    """Logger.tube_func (data_procs/logger_mpc.py:284-300): the pending turn scaled by 0.4 inside the tube and 0.7 outside."""
+    t, cur = np.asarray(turning, dtype=np.float64), np.asarray(cur_hd, dtype=np.float64)
+    gain = np.where(t > 0, np.where(width > t, gain_in, gain_out), np.where(-width < t, gain_in, gain_out))
+    tube = np.where(t != 0, cur + gain * t, cur)
+    return angle_a_minus_b(tube, cur)
+
+
+def avg_hd(cur_hd, nex_turn, mpc_hds):
+    """Logger.avg_hd (data_procs/logger_mpc.py:208-215): (nex_turn + three heading increments of the last plan) / 4."""
+    cur, h = np.asarray(cur_hd, dtype=np.float64), np.asarray(mpc_hds, dtype=np.float64)
+    s = np.asarray(nex_turn, dtype=np.float64) + angle_a_minus_b(h[..., 0], cur)
+    s = s + angle_a_minus_b(h[..., 1], h[..., 0])
+    s = s + angle_a_minus_b(h[..., 2], h[..., 1])
+    return s / 4.0

@@ -261,6 +261,30 @@ class DcbfSolver:
         self._check(rc, "dcbf_alip_foot")
         return dict(foot=foot, am=am, next=nxt)
 
+    def heading_input(self, cur_hd, nex_turn, x_plan=None, mpc_hds=None, glo_p=None):
+        """Logger.tube_func + Logger.avg_hd for B scenarios (dcbf_heading_input).  nex_turn [B] (device tensor) is updated in
+        place.  The plan headings come from x_plan [B,3,5] (a dcbf_tick / solve output, read in place) or mpc_hds [B,3]; the
+        result is written into glo_p[:, 2] when glo_p [B,3] is given (the input of the next tick) and returned."""
+        cur = self._dev(cur_hd, torch.float64).reshape(-1)
+        B = cur.shape[0]
+        assert isinstance(nex_turn, torch.Tensor) and nex_turn.is_cuda and nex_turn.dtype == torch.float64 and nex_turn.is_contiguous()
+        if x_plan is not None:
+            src = self._dev(x_plan, torch.float64).reshape(B, 15)
+            base, stride, step = src.data_ptr() + 4 * 8, 15, 5
+        else:
+            src = self._dev(mpc_hds, torch.float64).reshape(B, 3)
+            base, stride, step = src.data_ptr(), 3, 1
+        if glo_p is not None:
+            assert isinstance(glo_p, torch.Tensor) and glo_p.is_cuda and glo_p.is_contiguous() and glo_p.shape == (B, 3)
+            out, optr, ostride = glo_p[:, 2], glo_p.data_ptr() + 2 * 8, 3
+        else:
+            out = torch.empty((B,), device=self.tdev, dtype=torch.float64)
+            optr, ostride = out.data_ptr(), 1
+        with torch.cuda.device(self.tdev):
+            rc = self.lib.dcbf_heading_input(self._ctx, B, _ptr(cur), _ptr(nex_turn), base, stride, step, optr, ostride, self._stream())
+        self._check(rc, "dcbf_heading_input")
+        return out
+
     def gen_fields(self, F, seed, num, mix=False, margin=8.5, radius=1.0, half_gap=0.8, safe_dis=0.4, install=True):
         """F random obstacle fields on the device (dcbf_gen_fields: rand_obs.py:31-81 batched, with bounded restarts).
         Returns dict(cir[F,Kc,3], elp[F,Ke,5], draws[F]); install=True also makes them the context's fields."""

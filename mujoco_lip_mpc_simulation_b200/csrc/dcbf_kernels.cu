@@ -424,6 +424,34 @@ __global__ void gen_states_kernel(int B, uint64_t seed, gen::StateSpec S, const 
     if (attempts) attempts[b] = n;
 }
 
+// Heading input of the LIP prediction (Logger.update_n_record tail, data_procs/logger_mpc.py:278-281): the turn of the last plan decays through
+// tube_func (:284-300) and is averaged with the plan's heading increments by avg_hd (:208-215).  Round-to-nearest operations in the
+// reference's order, so the result is the reference's to the bit.
+__device__ __forceinline__ double angle_a_minus_b(double a, double b) {   // logger_mpc.py:169-175
+    double r = __dsub_rn(a, b);
+    if (r < 0.0 && fabs(r) > 3.141592653589793) r = __dadd_rn(r, 2.0 * 3.141592653589793);
+    else if (r > 0.0 && fabs(r) > 3.141592653589793) r = __dsub_rn(r, 2.0 * 3.141592653589793);
+    return r;
+}
+__global__ void heading_input_kernel(int B, const double *__restrict__ cur_hd, double *__restrict__ nex_turn, const double *__restrict__ hds,
+                                     int hds_stride, int hds_step, double *__restrict__ out, int out_stride) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double cur = cur_hd[b], t = nex_turn[b];
+    double tube = cur;
+    if (t > 0.0) tube = __dadd_rn(cur, __dmul_rn(0.15 > t ? 0.4 : 0.7, t));
+    else if (t < 0.0) tube = __dadd_rn(cur, __dmul_rn(-0.15 < t ? 0.4 : 0.7, t));
+    const double nt = angle_a_minus_b(tube, cur);
+    const double *h = hds + (size_t)hds_stride * b;
+    const double h0 = h[0], h1 = h[hds_step], h2 = h[2 * hds_step];
+    double sum = nt;
+    sum = __dadd_rn(sum, angle_a_minus_b(h0, cur));
+    sum = __dadd_rn(sum, angle_a_minus_b(h1, h0));
+    sum = __dadd_rn(sum, angle_a_minus_b(h2, h1));
+    nex_turn[b] = nt;
+    out[(size_t)out_stride * b] = sum / 4.0;
+}
+
 // ALIP one-step foot placement (ALIP_plan/planner.py:188-261, 346-370), one thread per scenario
 __global__ void alip_foot_kernel(int B, const double *__restrict__ xa, const double *__restrict__ ya, const double *__restrict__ time,
                                  const int32_t *__restrict__ support, const double *__restrict__ speed, int stride, double H, double T,
@@ -799,6 +827,18 @@ int dcbf_math_probe(dcbf_ctx *ctx, int32_t n, const double *a, const double *b, 
     if (n == 0) return DCBF_OK;
     CK(cudaSetDevice(ctx->device));
     math_probe_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, a, b, out);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
+int dcbf_heading_input(dcbf_ctx *ctx, int32_t B, const double *cur_hd, double *nex_turn, const double *mpc_hds, int32_t hds_stride,
+                       int32_t hds_step, double *hd_input, int32_t out_stride, void *stream) {
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
+    if (B == 0) return DCBF_OK;
+    if (!cur_hd || !nex_turn || !mpc_hds || !hd_input || hds_stride < 1 || hds_step < 1 || out_stride < 1) return DCBF_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    heading_input_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, cur_hd, nex_turn, mpc_hds, hds_stride, hds_step, hd_input, out_stride);
     CK(cudaGetLastError());
     ctx->launches++;
     return DCBF_OK;

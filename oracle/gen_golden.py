@@ -19,6 +19,7 @@ Writes small .npz fixtures under tests/golden/:
 """
 from __future__ import annotations
 
+import math
 import os
 import sys
 
@@ -220,6 +221,25 @@ def gen_helpers():
                alip_step_r=np.array(st_r, dtype=float), alip_step_l=np.array(st_l, dtype=float),
                alip_reg=np.array([al.regulate_lateral_step(1, 0.05), al.regulate_lateral_step(1, 0.5), al.regulate_lateral_step(-1, -0.05),
                                   al.regulate_lateral_step(-1, -0.3), al.regulate_lateral_step(0, 0.7)]))
+    # heading input of the LIP prediction: Logger.tube_func / avg_hd / angle_A_minus_B (data_procs/logger_mpc.py:169-175,208-215,284-300)
+    import contextlib, io
+    spec = importlib.util.spec_from_file_location("_dcbf_ref_logger_mpc", ref_loader.REFERENCE_ROOT + "/data_procs/logger_mpc.py")
+    lg_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lg_mod)
+    L = lg_mod.Logger
+    n_h = 64
+    cur = rng.uniform(-3.2, 3.2, n_h)
+    turn = np.concatenate([rng.uniform(-0.4, 0.4, n_h - 4), [0.0, 0.15, -0.15, 0.149]])
+    hds = cur[:, None] + np.cumsum(rng.uniform(-0.3, 0.3, (n_h, 3)), axis=1)
+    hds[:8] += rng.choice([-2 * math.pi, 2 * math.pi], size=(8, 1))     # headings on the other side of the +-pi cut
+    nt, hp = np.zeros(n_h), np.zeros(n_h)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for i in range(n_h):
+            me = types.SimpleNamespace(nex_turn=float(turn[i]), mpc_hds_list=[float(v) for v in hds[i]])
+            me.angle_A_minus_B = lambda a, b, me=me: L.angle_A_minus_B(me, a, b)
+            me.nex_turn = L.tube_func(me, me.nex_turn, float(cur[i]))
+            nt[i], hp[i] = me.nex_turn, L.avg_hd(me, float(cur[i]))
+    out.update(hdin_cur=cur, hdin_turn=turn, hdin_hds=hds, hdin_nex_turn=nt, hdin_pr=hp)
     np.savez_compressed(os.path.join(OUT, "helpers.npz"), **out)
     print("helpers:", len(out), "arrays")
 

@@ -168,3 +168,29 @@ def test_dd_eval_kernel_reproduces_recorded_labels():
     worst = c[:, :, :8].reshape(n, -1).min(axis=1)
     fail, feasi = G["dd_label"] == 2, G["dd_label"] == 0
     assert np.mean(worst[fail] < -1e-4) >= 0.95 and np.mean(worst[feasi] >= -1e-4) >= 0.9
+
+
+def test_heading_input_kernel_matches_reference_logger():
+    """dcbf_heading_input against Logger.tube_func / avg_hd outputs frozen from the reference (tests/golden/helpers.npz), bit for
+    bit, reading the plan headings in place from an x_plan buffer and writing the third column of the next tick's glo_p."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "helpers.npz"))
+    s = DcbfSolver("modi")
+    dev = s.tdev
+    B = len(G["hdin_cur"])
+    x_plan = torch.zeros((B, 3, 5), device=dev, dtype=torch.float64)
+    x_plan[:, :, 4] = torch.as_tensor(G["hdin_hds"], device=dev)
+    nex_turn = torch.as_tensor(G["hdin_turn"], device=dev).clone()
+    glo_p = torch.full((B, 3), 7.0, device=dev, dtype=torch.float64)
+    out = s.heading_input(G["hdin_cur"], nex_turn, x_plan=x_plan, glo_p=glo_p)
+    assert np.array_equal(nex_turn.cpu().numpy(), G["hdin_nex_turn"])
+    assert np.array_equal(out.cpu().numpy(), G["hdin_pr"])
+    assert torch.equal(glo_p[:, :2], torch.full((B, 2), 7.0, device=dev, dtype=torch.float64))
+    # dense [B,3] headings and a separate output give the same numbers
+    nt2 = torch.as_tensor(G["hdin_turn"], device=dev).clone()
+    out2 = s.heading_input(G["hdin_cur"], nt2, mpc_hds=G["hdin_hds"])
+    assert torch.equal(out2, glo_p[:, 2]) and torch.equal(nt2, nex_turn)
+    # the decay between re-plans: ten ticks without a new plan shrink the pending turn geometrically
+    for _ in range(10):
+        s.heading_input(G["hdin_cur"], nt2, mpc_hds=G["hdin_hds"])
+    assert float(nt2.abs().max()) < 1e-4     # 0.4 rad * 0.7^3 * 0.4^8

@@ -62,3 +62,11 @@ def test_model_constants_match_survey():
     assert abs(k.A[0, 0] - 1.892976) < 1e-6 and abs(k.A[0, 2] - 0.513166) < 1e-6 and abs(k.A[2, 0] - 5.034157) < 1e-6
     assert abs(k.W[0, 0] + 0.15223) < 1e-5 and abs(k.W[0, 2] + 0.17164) < 1e-5
     np.testing.assert_allclose(k.W @ k.B, np.eye(3), atol=1e-12)
+
+
+def test_heading_input_rules_match_reference_logger():
+    """Logger.tube_func / avg_hd / angle_A_minus_B (data_procs/logger_mpc.py:169-175,208-215,284-300), bit for bit."""
+    nt = _lipmodel.logger_tube(G["hdin_turn"], G["hdin_cur"])
+    assert np.array_equal(nt, G["hdin_nex_turn"])
+    assert np.array_equal(_lipmodel.avg_hd(G["hdin_cur"], nt, G["hdin_hds"]), G["hdin_pr"])
+    assert (np.abs(G["hdin_nex_turn"]) <= 0.7 * 0.4 + 1e-12).all()
