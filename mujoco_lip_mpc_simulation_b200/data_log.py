@@ -88,3 +88,64 @@ def run_from_rollout(traj, cir, elp, plans=None, status=None, dt=None):
         run.update(pred_full_end=plans, pred_feasi_end=[a for a, q in zip(plans, st) if q != 2],
                    pred_fail_end=[a for a, q in zip(plans, st) if q == 2], pred_end=[a[[0, 41]] for a in plans])
     return run
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# sup_learn/*.csv: one row per control tick of a run, written by the learning logger (data_procs/logger_iml.py:377-401) with
+# numpy.savetxt's default '%.18e' format.
+#   X_data.csv      obstacle list raveled (K x [cx, cy, r]) | CoM position (2) | CoM velocity (2) | base heading | stance foot (2)
+#                   | goal (2) | leg_ind | rest_t                                             -- all in the map frame
+#   y_mpc_data.csv  planned foot (2) | 0 | hd_input_pr + hd_input_cos | predicted position x_nex[0:2] | desired velocity (2)
+#   y_act_data.csv  the same eight columns for what the robot did (constant over a step)
+SUP_FILES = ("X_data.csv", "y_mpc_data.csv", "y_act_data.csv")
+
+
+def read_sup_learn(folder: str) -> dict:
+    """{'X': [T, 3K+11], 'y_mpc': [T, 8], 'y_act': [T, 8]} plus the named views of sup_learn_fields."""
+    import os
+    out = {}
+    for key, name in zip(("X", "y_mpc", "y_act"), SUP_FILES):
+        path = os.path.join(folder, name)
+        if os.path.exists(path):
+            out[key] = np.atleast_2d(np.loadtxt(path, delimiter=","))
+    if "X" in out:
+        out.update(sup_learn_fields(out["X"], out.get("y_mpc")))
+    return out
+
+
+def write_sup_learn(folder: str, X, y_mpc, y_act=None) -> None:
+    import os
+    os.makedirs(folder, exist_ok=True)
+    for name, a in zip(SUP_FILES, (X, y_mpc, y_act)):
+        if a is not None:
+            np.savetxt(os.path.join(folder, name), np.atleast_2d(np.asarray(a, dtype=np.float64)), delimiter=",")
+
+
+def sup_learn_fields(X, y_mpc=None) -> dict:
+    """Named columns of the feature rows (logger_iml.py:378-383) and, if given, of the MPC rows (:392-395).  The heading input of
+    the prediction is recovered as hd_input_pr = y_mpc[:, 3] - heading (hd_input_cos is the base heading; the map and robot frames
+    coincide when hd_init = 0, main_sim_mpc.py:24-25)."""
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    K = (X.shape[1] - 11) // 3
+    assert X.shape[1] == 3 * K + 11, "feature rows are 3K + 11 wide"
+    o = 3 * K
+    out = dict(obs=X[:, :o].reshape(-1, K, 3), pos=X[:, o:o + 2], vel=X[:, o + 2:o + 4], heading=X[:, o + 4], stance=X[:, o + 5:o + 7],
+               goal=X[:, o + 7:o + 9], leg_ind=X[:, o + 9].astype(np.int32), rest_t=X[:, o + 10])
+    if y_mpc is not None:
+        y = np.atleast_2d(np.asarray(y_mpc, dtype=np.float64))
+        out.update(foot=y[:, 0:2], hd_target=y[:, 3], x_nex_pos=y[:, 4:6], v_des=y[:, 6:8], hd_input_pr=y[:, 3] - out["heading"])
+    return out
+
+
+def sup_learn_rows(obs, pos, vel, heading, stance, goal, leg_ind, rest_t, foot, hd_input_pr, x_nex_pos, v_des=None):
+    """Feature and MPC rows of B ticks in the reference layout, from the inputs and outputs of DcbfSolver.tick (foot =
+    p_plan[:, 0, :2], x_nex_pos = x_next[:, :2]); obs is the un-inflated obstacle list [K, 3] of the run or [B, K, 3]."""
+    pos = np.atleast_2d(np.asarray(pos, dtype=np.float64))
+    B = pos.shape[0]
+    obs = np.asarray(obs, dtype=np.float64)
+    obs = np.broadcast_to(obs.reshape(-1, obs.shape[-2] * 3) if obs.ndim == 3 else obs.reshape(1, -1), (B, obs.shape[-2] * 3))
+    col = lambda a, w: np.broadcast_to(np.asarray(a, dtype=np.float64).reshape(-1, w), (B, w))   # noqa: E731
+    X = np.concatenate([obs, pos, col(vel, 2), col(heading, 1), col(stance, 2), col(goal, 2), col(leg_ind, 1), col(rest_t, 1)], axis=1)
+    hd = col(heading, 1) + col(hd_input_pr, 1)
+    y = np.concatenate([col(foot, 2), np.zeros((B, 1)), hd, col(x_nex_pos, 2), col(np.zeros(2) if v_des is None else v_des, 2)], axis=1)
+    return X, y

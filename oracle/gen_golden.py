@@ -328,8 +328,24 @@ def gen_rand_obs():
     print("rand_obs:", len(cir6), "circle fields and", len(mixc), "mixed fields from the reference generator;", stalled, "seeds never finished")
 
 
+def gen_sup_learn():
+    """The reference's recorded learning set sup_learn/*.csv (640 control ticks of a main_sim_mpc.py run: MPC_LIP_modi with six
+    circles, real cyipopt): features, the MPC's answers and the robot's.  Outputs of the real pipeline, not of this repository."""
+    d = os.path.join(ref_loader.REFERENCE_ROOT, "sup_learn")
+    X = np.loadtxt(os.path.join(d, "X_data.csv"), delimiter=",")
+    y = np.loadtxt(os.path.join(d, "y_mpc_data.csv"), delimiter=",")
+    a = np.loadtxt(os.path.join(d, "y_act_data.csv"), delimiter=",")
+    with open(os.path.join(d, "X_data.csv")) as f:
+        first = f.readline().strip()
+    np.savez_compressed(os.path.join(OUT, "sup_learn.npz"), X=X, y_mpc=y, y_act=a, first_line=np.array(first))
+    print("sup_learn:", X.shape, y.shape, a.shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--sup-learn-only" in sys.argv:
+        gen_sup_learn()
+        sys.exit(0)
     if "--rand-obs-only" in sys.argv:
         gen_rand_obs()
         sys.exit(0)
@@ -339,6 +355,7 @@ if __name__ == "__main__":
     gen_helpers()
     gen_data_log()
     gen_rand_obs()
+    gen_sup_learn()
     if "--helpers-only" in sys.argv:
         sys.exit(0)
     for form, seed in (("sig_step", 101), ("modi", 102), ("dd", 103)):

@@ -194,3 +194,33 @@ def test_heading_input_kernel_matches_reference_logger():
     for _ in range(10):
         s.heading_input(G["hdin_cur"], nt2, mpc_hds=G["hdin_hds"])
     assert float(nt2.abs().max()) < 1e-4     # 0.4 rad * 0.7^3 * 0.4^8
+
+
+def test_tick_on_the_recorded_learning_set():
+    """dcbf_tick on the 640 control ticks the reference recorded in sup_learn/*.csv (main_sim_mpc.py run, real cyipopt; fixture
+    tests/golden/sup_learn.npz): the LIP prediction equals the recorded x_nex[0:2] and the re-plan, cold-started, lands on the
+    recorded foot placement (the reference run warm-started and stopped after <= 30 L-BFGS iterations: statistical tolerances,
+    the same as for the oracle in tests/test_sup_learn_cpu.py)."""
+    import os
+    from mujoco_lip_mpc_simulation_b200 import data_log
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sup_learn.npz"))
+    f = data_log.sup_learn_fields(G["X"], G["y_mpc"])
+    T = len(f["pos"])
+    s = DcbfSolver("modi", device=0)
+    s.set_fields((f["obs"][0] + np.array([0.0, 0.0, 0.4]))[None])
+    glo_p = np.column_stack([f["stance"], f["hd_input_pr"]])
+    out = s.tick(f["pos"], f["vel"], f["heading"], glo_p, f["rest_t"], f["goal"], -f["leg_ind"], want_pos_det=False)
+    torch.cuda.synchronize()
+    xn = out["x_next"].cpu().numpy()
+    np.testing.assert_allclose(xn[:, :2], f["x_nex_pos"], rtol=0, atol=2e-13)      # device cosh / sinh and FMA contraction
+    st = out["plan"].status.cpu().numpy()
+    d = np.linalg.norm(out["plan"].p_plan.cpu().numpy()[:, 0, :2] - f["foot"], axis=1)
+    ok = st == 0
+    assert ok.mean() > 0.8
+    assert np.median(d[ok]) < 5e-4 and (d[ok] < 1e-3).mean() > 0.65
+    assert (d < 1e-2).mean() > 0.9 and d.max() < 0.12
+    # the learning-set rows written from the tick's own inputs and outputs have the reference layout
+    X, y = data_log.sup_learn_rows(f["obs"][0], f["pos"], f["vel"], f["heading"], f["stance"], f["goal"], f["leg_ind"], f["rest_t"],
+                                   out["plan"].p_plan.cpu().numpy()[:, 0, :2], f["hd_input_pr"], xn[:, :2], f["v_des"])
+    assert np.array_equal(X, G["X"]) and y.shape == G["y_mpc"].shape
+    np.testing.assert_allclose(y[:, 2:], G["y_mpc"][:, 2:], rtol=0, atol=2e-13)
