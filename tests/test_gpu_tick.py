@@ -2,6 +2,8 @@
 checked against the host restatements that tests/test_helpers_cpu.py pins to golden vectors of the reference classes
 (_lipmodel.flow_matrices / track_det <- MPCCBF.get_next_states / xk_track_det), and the re-plan inside the tick must be the
 very solve dcbf_solve performs on the same inputs."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -224,3 +226,62 @@ def test_tick_on_the_recorded_learning_set():
                                    out["plan"].p_plan.cpu().numpy()[:, 0, :2], f["hd_input_pr"], xn[:, :2], f["v_des"])
     assert np.array_equal(X, G["X"]) and y.shape == G["y_mpc"].shape
     np.testing.assert_allclose(y[:, 2:], G["y_mpc"][:, 2:], rtol=0, atol=2e-13)
+
+
+def test_tick_rate_closed_loop_stays_on_the_device():
+    """SURVEY.md 8(f) row 1 end to end: robots walk to the goal re-planning EIGHT times per step from a noisy state, every piece on
+    the GPU -- scenarios from dcbf_gen_fields / dcbf_gen_states, heading input from dcbf_heading_input, prediction + warm-start
+    rule + re-plan from dcbf_tick; the plant is the LIP flow about the stance foot with velocity noise (torch ops on the same
+    stream).  Nothing is copied to the host inside the loop."""
+    torch.manual_seed(3)
+    s = DcbfSolver("sig_step", device=0)
+    dev, B, F, beta, dtk = s.tdev, 512, 64, _lipmodel.BETA, 0.05
+    sc = scenarios.make_batch_device(s, B, seed=17, n_fields=F)
+    assert int((sc["attempts"] < 0).sum()) == 0
+    x0, goal, field = sc["x0"], sc["goal"], sc["field"]
+    first = s.solve(x0, goal, sc["leg"], sc["warm"], field=field)                     # the step that is about to start
+    pos, vel, hd = x0[:, 0:2].clone(), x0[:, 2:4].clone(), x0[:, 4].clone()
+    stance, nex_turn = first.p_plan[:, 0, :2].clone(), first.p_plan[:, 0, 2].clone()
+    leg_next = (-sc["leg"]).contiguous()
+    prev = first.x_plan.reshape(B, 15).clone()
+    glo_p = torch.zeros((B, 3), device=dev, dtype=torch.float64)
+    cir = sc["cir"][field.long()]                                                    # [B, K, 3] inflated by 0.4
+    d0 = torch.linalg.norm(pos - goal, dim=1)
+    done = torch.zeros(B, dtype=torch.bool, device=dev)
+    min_gap = torch.full((B,), float("inf"), device=dev, dtype=torch.float64)
+    n_ok = torch.zeros((), device=dev, dtype=torch.float64)
+    n_ticks, launches0 = 0, s.launches
+    ch, sh = math.cosh(beta * dtk), math.sinh(beta * dtk)
+    for step in range(40):
+        for j in range(8):
+            glo_p[:, :2] = stance
+            s.heading_input(hd, nex_turn, x_plan=prev, glo_p=glo_p)
+            out = s.tick(pos, vel, hd, glo_p, 0.4 - dtk * j, goal, leg_next, prev_plan=prev,
+                         mode=torch.full((B,), 1 if j == 0 else 0, dtype=torch.uint8, device=dev), field=field, want_pos_det=False)
+            plan = out["plan"]
+            prev = plan.x_plan.reshape(B, 15)
+            nex_turn = plan.p_plan[:, 0, 2].clone()
+            n_ok += (plan.status == 0).double().mean()
+            n_ticks += 1
+            # plant: LIP flow about the stance foot over one tick, velocity noise, heading follows the commanded rate
+            rel = pos - stance
+            npos = stance + ch * rel + (sh / beta) * vel
+            nvel = (sh * beta) * rel + ch * vel + 0.01 * torch.randn_like(vel)
+            live = (~done)[:, None]
+            pos, vel = torch.where(live, npos, pos), torch.where(live, nvel, vel)
+            hd = torch.where(~done, hd + glo_p[:, 2] * (dtk / 0.4), hd)
+            gap = (torch.linalg.norm(pos[:, None, :] - cir[:, :, :2], dim=2) - (cir[:, :, 2] - 0.4)).min(dim=1).values
+            min_gap = torch.minimum(min_gap, gap)
+        stance = torch.where((~done)[:, None], plan.p_plan[:, 0, :2], stance)          # touchdown on the planned foothold
+        leg_next = (-leg_next).contiguous()
+        done |= torch.linalg.norm(pos - goal, dim=1) < 0.3
+    torch.cuda.synchronize()
+    d1 = torch.linalg.norm(pos - goal, dim=1)
+    print(f"closed loop: {n_ticks} ticks x {B} robots, converged re-plans {float(n_ok) / n_ticks:.3f}, arrived {float(done.double().mean()):.3f}, "
+          f"never inside an obstacle {float((min_gap > 0.0).double().mean()):.3f}, median progress {float((d0 - d1).median()):.2f} m")
+    assert s.launches - launches0 >= 3 * n_ticks                 # heading input + prepare + solve per tick, all ours
+    assert float(n_ok) / n_ticks > 0.85                          # converged re-plans
+    assert float((min_gap > 0.0).double().mean()) > 0.97         # the body of the obstacle is never entered
+    assert float((min_gap > -0.05).double().mean()) > 0.99
+    assert float(((d1 < d0 - 2.0) | done).double().mean()) > 0.9  # walked at least 2 m towards the goal, or arrived
+    assert float(done.double().mean()) > 0.3
