@@ -306,6 +306,27 @@ def test_size_class_split_is_transparent(gpu, monkeypatch):
     assert torch.equal(res.p_plan, ref.p_plan) and torch.equal(res.x_plan, ref.x_plan)
 
 
+@pytest.mark.parametrize("form", ["sig_step", "dd"])
+def test_scheduling_order_is_transparent(gpu, monkeypatch, form):
+    """batches of 2048+ scenarios are started in the order of their predicted clearance (hard problems first, so that none of them
+    is left for the tail: sched_classify_kernel / sched_scatter_kernel); the order decides which warp solves which scenario and
+    must not change any result"""
+    B = 4096
+    sc = scenarios.make_batch(form, B, seed=43)
+    monkeypatch.setenv("DCBF_ORDER", "0")
+    ref = _solver(gpu, form, sc).solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field, last_u=sc.last_u)
+    monkeypatch.delenv("DCBF_ORDER")
+    s = _solver(gpu, form, sc)
+    l0 = s.launches
+    res = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field, last_u=sc.last_u)
+    torch.cuda.synchronize()
+    assert s.launches - l0 == 3                      # classify + scatter + solve
+    assert torch.equal(res.status, ref.status) and torch.equal(res.iters, ref.iters)
+    assert torch.equal(res.u, ref.u) and torch.equal(res.x_plan, ref.x_plan) and torch.equal(res.obj, ref.obj)
+    small = s.solve(sc.x0[:512], sc.goal[:512], sc.leg[:512], sc.warm[:512], field=sc.field[:512], last_u=None if sc.last_u is None else sc.last_u[:512])
+    assert torch.equal(small.u, ref.u[:512])          # below the threshold: natural order, same numbers
+
+
 def test_host_entry_point_with_page_locked_buffers(gpu):
     """dcbf_solve_host copies straight from / to page-locked caller buffers (no staging); same results as the staged path"""
     sc = scenarios.make_batch("sig_step", 512, seed=31)
