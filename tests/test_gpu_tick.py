@@ -172,6 +172,29 @@ def test_dd_eval_kernel_reproduces_recorded_labels():
     assert np.mean(worst[fail] < -1e-4) >= 0.95 and np.mean(worst[feasi] >= -1e-4) >= 0.9
 
 
+def test_dd_solver_reproduces_ipopt_feasibility_verdicts():
+    """dcbf_solve (dd) from the start state of the 110 recorded differential-drive re-plans: status 2 exactly where the reference's
+    Ipopt run gave up (pred_fail), as for the oracle in tests/test_data_log_cpu.py; both kernel families"""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "data_log_plans.npz"))
+    P = G["dd_plan"]
+    n = len(P)
+    d = np.diff(P, axis=1)
+    v = (d[:, :, 0] * np.cos(P[:, :3, 2]) + d[:, :, 1] * np.sin(P[:, :3, 2])) / 0.4
+    u = np.stack([v, d[:, :, 2]], axis=2).reshape(n, 6)
+    want = G["dd_label"] == 2
+    for mode in ("warp", "thread"):
+        os.environ["DCBF_KERNEL"] = mode
+        try:
+            s = DcbfSolver("dd", device=0)
+        finally:
+            del os.environ["DCBF_KERNEL"]
+        s.set_fields(G["dd_cir"] + np.array([0.0, 0.0, 0.4]), G["dd_elp"] + np.array([0.0, 0.0, 0.4, 0.4, 0.0]))
+        r = s.solve(P[:, 0], np.tile([10.0, 10.0], (n, 1)), None, u, field=G["dd_run"].astype(np.int32), last_u=u[:, :2].copy())
+        got = r.status.cpu().numpy() == 2
+        assert (got == want).mean() >= 0.98 and not (want & ~got).any(), mode
+
+
 def test_heading_input_kernel_matches_reference_logger():
     """dcbf_heading_input against Logger.tube_func / avg_hd outputs frozen from the reference (tests/golden/helpers.npz), bit for
     bit, reading the plan headings in place from an x_plan buffer and writing the third column of the next tick's glo_p."""
