@@ -314,7 +314,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "formulation": "sig_step", "n_circles": 6, "seed": SEED,
                        "l2": "flushed between timed steps (256 MiB memset)", "max_iter": int(solver.P.max_iter)},
-            "e2e": {"value": total_solves / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": total_solves / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "transfer": ("page-locked host buffers through dcbf_solve_host; the kernels load the inputs from and store the results to the "
+                                 "mapped host memory (no staging copy)" if os.environ.get("DCBF_ZEROCOPY", "1") != "0" else
+                                 "page-locked host buffers through dcbf_solve_host, cudaMemcpyAsync each way")},
             "gpu_launches": int(launches),
             "p50_solve_us": float(np.median(lat)), "p95_solve_us": float(np.percentile(lat, 95)),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",

@@ -52,6 +52,7 @@ struct dcbf_ctx {
     int *d_sched; size_t sched_cap;   // longest-expected-first order of a batch: [counts(16) | rank(B) | order(B)]
     int sched_min_batch;              // smallest batch that is ordered (env DCBF_ORDER; 0 = never)
     int sched_select;                 // order obstacle-selecting formulations too (env DCBF_ORDER_SELECT)
+    int zero_copy;                    // dcbf_solve_host reads / writes page-locked caller buffers from the kernels (env DCBF_ZEROCOPY)
 };
 
 #define CK(call)                                                                                        \
@@ -259,13 +260,16 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
         const int i_ = wp::next_problem(counter, lane);
         if (i_ >= n) break;
         const int b = order ? order[i_] : i_;
+        // the 22 input values arrive in three coalesced requests (the buffers may be mapped host memory: dcbf_solve_host)
+        sm.dz[lane] = lane < 5 ? in.x0[5 * (size_t)b + lane] : (lane < 20 ? in.warm[15 * (size_t)b + lane - 5] : (lane < 22 ? in.goal[2 * (size_t)b + lane - 20] : 0.0));
+        __syncwarp();
         if (lane == 0) {
             double x0[5], u0[15], g[2];
 #pragma unroll
-            for (int i = 0; i < 5; i++) x0[i] = in.x0[5 * (size_t)b + i];
+            for (int i = 0; i < 5; i++) x0[i] = sm.dz[i];
 #pragma unroll
-            for (int i = 0; i < 15; i++) u0[i] = in.warm[15 * (size_t)b + i];
-            g[0] = in.goal[2 * (size_t)b]; g[1] = in.goal[2 * (size_t)b + 1];
+            for (int i = 0; i < 15; i++) u0[i] = sm.dz[5 + i];
+            g[0] = sm.dz[20]; g[1] = sm.dz[21];
             stage_problem<NS>(cs_.K, sm, x0, g, u0, 0);
         } else {
             __syncwarp();
@@ -737,7 +741,8 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     ctx->refill_min_batch = rb ? atoi(rb) : -1;
     { const char *sp = getenv("DCBF_SPLIT"); ctx->split_classes = sp ? atoi(sp) : 16384; }
     { const char *sp = getenv("DCBF_ORDER"); ctx->sched_min_batch = sp ? atoi(sp) : 2048; }
-    { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }   // below ~1 problem per warp slot there is no tail to hide
+    { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }
+    { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }   // below ~1 problem per warp slot there is no tail to hide
     if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     ctx->warp_max_batch = wb ? atoi(wb) : 0x7fffffff;   // round 2: the warp kernels win at every batch size (profiles/r02_summary.md)
@@ -1068,6 +1073,23 @@ int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *go
     bool in_pinned = B >= 256, out_pinned = B >= 256;
     for (int i = 0; i < 6 && in_pinned; i++) if (ins[i].src && !is_pinned_host(ins[i].src)) in_pinned = false;
     for (int i = 0; i < 8 && out_pinned; i++) if (outs[i].dst && !is_pinned_host(outs[i].dst)) out_pinned = false;
+    // Page-locked buffers on both sides and a warp kernel (coalesced per-problem reads and writes): no copies at all, the kernels
+    // load the inputs from and store the results to the mapped host buffers while they run (measured: profiles/r02_summary.md).
+    if (in_pinned && out_pinned && ctx->zero_copy && use_warp_kernel(ctx, B)) {
+        const void *dptr[14];
+        bool mapped = true;
+        for (int i = 0; i < 6 && mapped; i++) { void *d = nullptr; if (ins[i].src && cudaHostGetDevicePointer(&d, (void *)ins[i].src, 0) != cudaSuccess) mapped = false; dptr[i] = d; }
+        for (int i = 0; i < 8 && mapped; i++) { void *d = nullptr; if (outs[i].dst && cudaHostGetDevicePointer(&d, outs[i].dst, 0) != cudaSuccess) mapped = false; dptr[6 + i] = d; }
+        if (mapped) {
+            rc = dcbf_solve(ctx, B, (const double *)dptr[0], (const double *)dptr[1], (const int32_t *)dptr[4], (const int32_t *)dptr[5], (const double *)dptr[2],
+                            (const double *)dptr[3], (double *)dptr[6], (double *)dptr[7], (double *)dptr[8], (int32_t *)dptr[11], (int32_t *)dptr[12],
+                            (double *)dptr[9], (double *)dptr[10], (uint8_t *)dptr[13], ctx->stream);
+            if (rc != DCBF_OK) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));
+            return DCBF_OK;
+        }
+        (void)cudaGetLastError();
+    }
     if (in_pinned) {
         for (int i = 0; i < 6; i++)
             if (ins[i].src) CK(cudaMemcpyAsync(dp + ins[i].off, ins[i].src, ins[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
