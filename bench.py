@@ -47,7 +47,7 @@ def f_iter(n: int, m: int, m_nl: int, m_b: int, kc: int, ke: int, form: str) -> 
 
 
 F_ITER_SIG_K6 = f_iter(9, 30, 27, 0, 6, 0, "sig_step")   # = 8455
-NCU_DRAM_BYTES_PER_LAUNCH = 1.43e6   # measured once per change with ncu (profiles/r02_summary.md); not re-measured at run time
+NCU_DRAM_BYTES_PER_LAUNCH = 0.697e6  # measured once per change with ncu (profiles/r02_summary.md); not re-measured at run time
 
 
 def io_bytes_per_solve(kc: int) -> int:
