@@ -562,8 +562,9 @@ __global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
 
 // one problem per warp for batches that cannot fill the GPU with one problem per thread (and for single solves)
 static bool use_warp_kernel(const dcbf_ctx *ctx, int B) {
-    // DD: the warp kernel wins up to ~32 k scenarios (3x at 4096), the per-thread kernel beyond (profiles/r02_summary.md)
-    if (ctx->P.formulation == DCBF_DD && ctx->kernel_mode == 0) return B <= 32768;
+    // DD: with the start order the warp kernel wins wherever the order is applied (3x at 4096, 14.6 vs 18.4 ms at 65536, 56.7 vs 57.9 ms
+    // at 262144); without it the per-thread kernel is ahead from ~32 k scenarios on (profiles/r02_summary.md)
+    if (ctx->P.formulation == DCBF_DD && ctx->kernel_mode == 0) return B <= (ctx->sched_min_batch > 0 ? DCBF_SCHED_MAX_BATCH : 32768);
     if (ctx->kernel_mode == 1) return false;
     if (ctx->kernel_mode == 2) return true;
     return B <= ctx->warp_max_batch;
