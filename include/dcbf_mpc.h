@@ -120,8 +120,10 @@ int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, cons
                  const int32_t *field, double *x_final, int32_t *steps_done, int32_t *n_infeasible,
                  int32_t *total_iters, double *traj, void *stream);
 
-/* dcbf_solve for host buffers: copies inputs to the device, solves, copies results back and synchronises.
- * Obstacle fields still come from dcbf_set_fields_host / dcbf_set_fields. */
+/* dcbf_solve for host buffers; returns when the results are in the caller's buffers.  Pageable buffers are staged through one
+ * pinned block (one copy each way).  If every buffer is page-locked (cudaHostAlloc / cudaHostRegister) and the batch runs on a
+ * warp kernel, nothing is copied: the kernels read the inputs from and write the results to the mapped host memory directly
+ * (environment DCBF_ZEROCOPY=0 restores cudaMemcpyAsync).  Obstacle fields still come from dcbf_set_fields_host / dcbf_set_fields. */
 int dcbf_set_fields_host(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir_host, int32_t Ke, const double *elp_host);
 int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg,
                     const int32_t *field, const double *warm, const double *last_u, double *u, double *x_plan,
