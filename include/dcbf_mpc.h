@@ -15,6 +15,8 @@
  *   dcbf_solve           <- MPCCBF.solveMPCCBF + the plan re-roll of gen_control_test / gen_dd_control
  *                           (MPC_LIP_sig_step.py:89-111,184-278; MPC_LIP_modi.py:90-115,197-301,325-338;
  *                            MPC_DD_sig_step.py:70-99,123-193) i.e. the cyipopt.Problem(...).solve(u0) call
+ *   dcbf_setup_info      <- MPCCBF.select_obs (MPC_LIP_modi.py:325-338) and the goal shift inside solveMPCCBF
+ *                           (MPC_LIP_sig_step.py:229-253, MPC_LIP_modi.py:249-271), as the solve applies them
  *   dcbf_rollout         <- the plan -> apply -> re-plan loop of MPC_LIP_sig_step.py:565-575
  *   dcbf_solve_host      <- same as dcbf_solve for callers that hold host (numpy) buffers
  *   dcbf_alip_foot       <- the closed-form ALIP foot placement behind the DD re-plan (Logger.ALIP_gen_foot_input,
@@ -50,7 +52,7 @@
 extern "C" {
 #endif
 
-#define DCBF_ABI_VERSION 2
+#define DCBF_ABI_VERSION 3
 #define DCBF_MAX_OBS 16 /* circles and ellipses each, per field */
 
 enum dcbf_formulation { DCBF_SIG_STEP = 0, DCBF_MODI = 1, DCBF_DD = 2 };
@@ -110,6 +112,15 @@ int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, co
 int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
                const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
                int32_t *iters, double *obj, double *viol, uint8_t *close2goal, void *stream);
+
+/* The per-scenario problem setup that precedes every solve, made visible (device pointers): obstacle selection
+ * (MPCCBF.select_obs, MPC_LIP_modi.py:325-338: keep an obstacle if dist^2 - r^2 <= detect_sq, r = max(a, b) for an ellipse)
+ * and the detour goal (MPC_LIP_sig_step.py:229-253; MPC_LIP_modi.py:249-271 searches the selected circles only).
+ * Outputs (any may be NULL): mask[B] -- bit j set = obstacle j of the scenario's field is a row of its NLP (circles 0..Kc-1,
+ * then ellipses Kc..Kc+Ke-1; all ones without select_obs), count[B] = number of selected obstacles, goal_eff[B][2] = the goal the
+ * NLP is solved with.  It runs the same setup code as dcbf_solve (of the kernel family DCBF_KERNEL selects). */
+int dcbf_setup_info(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *field, uint32_t *mask,
+                    int32_t *count, double *goal_eff, void *stream);
 
 /* K3: closed loop of `steps` re-plans per scenario without leaving the GPU (LIP formulations).  Each step:
  * solve, apply the first foot placement exactly (x <- x_plan[0]), flip the stance leg, warm start from the shifted

@@ -59,6 +59,7 @@ class DcbfSolver:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.tdev = torch.device("cuda", self.device)
         self._ctx = C.c_void_p()
+        # the C ABI restores the caller's current device on exit of every entry point (dcbf_kernels.cu: struct Call)
         rc = self.lib.dcbf_create(C.byref(self.P), self.device, C.byref(self._ctx))
         if rc != 0:
             raise RuntimeError(f"dcbf_create failed ({rc})")
@@ -140,6 +141,10 @@ class DcbfSolver:
         if leg is not None and leg.shape[0] != B:
             leg = leg.expand(B).contiguous()
         field = None if field is None else self._dev(field, torch.int32).reshape(-1)
+        if field is not None and field.shape[0] != B:
+            raise ValueError(f"field has {field.shape[0]} entries for a batch of {B} scenarios")
+        # field VALUES are checked on the device (an index outside [0, F) makes that scenario return status -13); a host-side
+        # min/max would synchronise the stream on every call
         last_u = None if last_u is None else self._dev(last_u, torch.float64).reshape(B, 2)
         return B, x0, goal, leg, field, last_u
 
@@ -186,7 +191,20 @@ class DcbfSolver:
         self._check(rc, "dcbf_eval")
         return dict(f=f, grad=grad, c=c, jac=jac, cl=cl, cu=cu, hess=hess)
 
+    def setup_info(self, x0, goal, field=None):
+        """Obstacle selection and detour goal of every scenario, as the solve kernels apply them (dcbf_setup_info).
+        Returns dict(mask[B] int64 bit field: circles 0..Kc-1, ellipses Kc.., count[B], goal_eff[B,2])."""
+        B, x0, goal, _, field, _ = self._inputs(x0, goal, None, field, None)
+        mask = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        count = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        ge = torch.empty((B, 2), dtype=torch.float64, device=self.tdev)
+        rc = self.lib.dcbf_setup_info(self._ctx, B, _ptr(x0), _ptr(goal), _ptr(field), _ptr(mask), _ptr(count), _ptr(ge), self._stream())
+        self._check(rc, "dcbf_setup_info")
+        return dict(mask=mask.to(torch.int64) & 0xFFFFFFFF, count=count, goal_eff=ge)
+
     def rollout(self, steps, x0, goal, leg, field=None, want_traj=True):
+        if self.dd:
+            raise ValueError("the closed-loop rollout belongs to the LIP formulations")
         B, x0, goal, leg, field, _ = self._inputs(x0, goal, leg, field, None)
         kw = dict(device=self.tdev)
         xf = torch.empty((B, 5), dtype=torch.float64, **kw)
@@ -276,6 +294,8 @@ class DcbfSolver:
             base, stride, step = src.data_ptr(), 3, 1
         if glo_p is not None:
             assert isinstance(glo_p, torch.Tensor) and glo_p.is_cuda and glo_p.is_contiguous() and glo_p.shape == (B, 3)
+            assert glo_p.dtype == torch.float64 and glo_p.device == self.tdev, "glo_p must be an FP64 tensor on the solver's device"
+            assert nex_turn.device == self.tdev
             out, optr, ostride = glo_p[:, 2], glo_p.data_ptr() + 2 * 8, 3
         else:
             out = torch.empty((B,), device=self.tdev, dtype=torch.float64)
@@ -337,7 +357,9 @@ class DcbfSolver:
         B = x0.shape[0]
         goal = f64(np.broadcast_to(f64(goal).reshape(-1, 2), (B, 2)))
         leg = None if leg is None else np.ascontiguousarray(np.broadcast_to(np.asarray(leg, dtype=np.int32).reshape(-1), (B,)))
-        field = None if field is None else np.ascontiguousarray(field, dtype=np.int32)
+        field = None if field is None else np.ascontiguousarray(field, dtype=np.int32).reshape(-1)
+        if field is not None and field.shape[0] != B:
+            raise ValueError(f"field has {field.shape[0]} entries for a batch of {B} scenarios")
         warm = f64(warm).reshape(B, self.nu)
         last_u = None if last_u is None else f64(last_u).reshape(B, 2)
         if out is None:

@@ -30,24 +30,28 @@ struct dcbf_ctx {
     int device;
     int F, Kc, Ke;
     double *cir_rec, *elp_rec;   // prepared fields (device)
+    size_t cir_cap, elp_cap;     // their capacities in records (dcbf_set_fields reallocates only to grow)
     int64_t launches;
     char err[256];
     // staging for the host-buffer entry points
     void *h_pin; size_t h_pin_bytes;
     void *d_buf; size_t d_buf_bytes;
-    double *d_cir_raw, *d_elp_raw; size_t raw_bytes;
+    double *d_cir_raw, *d_elp_raw; size_t cir_raw_bytes, elp_raw_bytes;
+    // stream order between entry points: every call records ev_done on its stream when it has enqueued its work, and a call on
+    // a DIFFERENT stream first waits for it (prepared fields and the shared scratch -- counters, start order, size classes --
+    // are then never read or reused before the previous call's kernels are through).  One context must still not be driven
+    // from two host threads at once.
+    cudaEvent_t ev_done; cudaStream_t last_stream; bool have_done;
     cudaStream_t stream;
     int sm_count;
     int kernel_mode;   // 0 auto, 1 per-thread, 2 warp-cooperative (env DCBF_KERNEL=thread|warp)
     int warp_max_batch;
     wp::WarpTables *d_tab;   // constant tables of the warp kernels (dcbf_warp.cuh)
-    int *d_counter;          // work counter of the persistent (refill) kernels
+    int *d_counter;          // work counters of the persistent warp kernels (one per concurrently running launch)
     double *d_tick; size_t tick_cap;   // scratch of dcbf_tick: [x_next | warm | x_plan | p_plan] when the caller passes NULL
     double *d_flow;                    // cosh / sinh table of pos_det_kernel (2 x 41)
     int *d_order; size_t order_cap;   // size-class split of obstacle-selecting formulations: [counts(2) | small list | large list]
     cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
-    int refill_ctas_lip, refill_ctas_dd;   // resident CTAs of the refill kernels on this device
-    int refill_min_batch;
     int split_classes;   // smallest batch that is split by size class (env DCBF_SPLIT; 0 = never)
     int *d_sched; size_t sched_cap;   // longest-expected-first order of a batch: [counts(16) | rank(B) | order(B)]
     int sched_min_batch;              // smallest batch that is ordered (env DCBF_ORDER; 0 = never)
@@ -64,6 +68,25 @@ struct dcbf_ctx {
         }                                                                                               \
     } while (0)
 
+// Scope of one entry point: switches to the context's device and restores the caller's current device on exit (a library must
+// not change the thread's device under torch), and keeps the entry points ordered across streams (see dcbf_ctx::ev_done).
+struct Call {
+    dcbf_ctx *ctx; cudaStream_t st; int prev; bool ok;
+    Call(dcbf_ctx *c, cudaStream_t s) : ctx(c), st(s), prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        if (prev != c->device && cudaSetDevice(c->device) != cudaSuccess) return;
+        if (c->have_done && c->last_stream != s && cudaStreamWaitEvent(s, c->ev_done, 0) != cudaSuccess) return;
+        ok = true;
+    }
+    ~Call() {
+        if (ok && cudaEventRecord(ctx->ev_done, st) == cudaSuccess) { ctx->last_stream = st; ctx->have_done = true; }
+        if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    }
+};
+#define ENTER(stream_)                                                                                   \
+    Call call_(ctx, (cudaStream_t)(stream_));                                                            \
+    if (!call_.ok) { snprintf(ctx->err, sizeof(ctx->err), "%s: cannot switch to device %d / order the stream", __func__, ctx->device); return DCBF_ERR_CUDA; }
+
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void prep_fields_kernel(int F, int Kc, const double *__restrict__ cir, int Ke, const double *__restrict__ elp,
                                    double *__restrict__ cir_rec, double *__restrict__ elp_rec) {
@@ -77,34 +100,6 @@ __global__ void __launch_bounds__(DCBF_BLOCK) solve_lip_kernel(dcbf_params P, Co
 }
 __global__ void __launch_bounds__(DCBF_BLOCK) solve_dd_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out) {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) solve_dd_lane(P, K, in, out, b);
-}
-// persistent variants: every lane pulls its next problem from an atomic counter the moment its current one is done, so the
-// lanes of a warp stay busy although iteration counts differ (feasible ~14, infeasible ~21, max ~40)
-__global__ void __launch_bounds__(DCBF_BLOCK) solve_lip_refill_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out, int *counter) {
-    LipModel<DCBF_KT> M;
-    IpmState<9> S;
-    int b = -1;
-    for (;;) {
-        if (b < 0) {
-            b = atomicAdd(counter, 1);
-            if (b >= B) break;
-            lip_lane_begin(P, K, in, b, M, S);
-        }
-        if (ipm_iterate(K, P, M, S)) { lip_lane_finish(P, M, S, b, out); b = -1; }
-    }
-}
-__global__ void __launch_bounds__(DCBF_BLOCK) solve_dd_refill_kernel(dcbf_params P, Consts K, int B, BatchIn in, SolveOut out, int *counter) {
-    DdModel<DCBF_KT> M;
-    IpmState<6> S;
-    int b = -1;
-    for (;;) {
-        if (b < 0) {
-            b = atomicAdd(counter, 1);
-            if (b >= B) break;
-            dd_lane_begin(P, in, b, M, S);
-        }
-        if (ipm_iterate(K, P, M, S)) { dd_lane_finish(P, K, M, S, b, out); b = -1; }
-    }
 }
 __global__ void __launch_bounds__(DCBF_BLOCK) eval_lip_kernel(dcbf_params P, Consts K, int B, BatchIn in, EvalPtrs ev) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,7 +150,8 @@ __global__ void __launch_bounds__(256) sched_classify_kernel(dcbf_params P, int 
             const double *x = in.x0 + 5 * (size_t)b;
             px = x[0]; py = x[1]; vx = x[2]; vy = x[3];
         }
-        const int fld = in.field ? in.field[b] : 0;
+        bool bad;
+        const int fld = batch_field(in, b, bad);
         const double *cr = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC, *er = in.elp_rec + (size_t)fld * in.Ke * DCBF_ELP_REC;
         double key = 1e30;
         int nsel = 0;
@@ -196,7 +192,8 @@ __global__ void classify_lip_kernel(dcbf_params P, int B, BatchIn in, int small_
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double px = in.x0[5 * (size_t)b], py = in.x0[5 * (size_t)b + 1];
-    const int fld = in.field ? in.field[b] : 0;
+    bool bad;
+    const int fld = batch_field(in, b, bad);
     const double *cir = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC;
     const double *elp = in.elp_rec + (size_t)fld * in.Ke * DCBF_ELP_REC;
     int ks = 0;
@@ -406,6 +403,39 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
     if (W > 1) { while (wp::cta_tick(0) > 0) {} }
 }
 
+// Problem setup of every scenario exactly as the solve kernels perform it, made visible: obstacle selection (MPCCBF.select_obs,
+// MPC_LIP_modi.py:325-338) and the detour goal (MPC_LIP_sig_step.py:229-253; MPC_LIP_modi.py:249-271 over the selected circles).
+// Bit j of mask[b] = obstacle j of the scenario's field is a row of its NLP (circles 0..Kc-1, then ellipses Kc..Kc+Ke-1).
+template <class M>
+__global__ void __launch_bounds__(32) setup_info_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in,
+                                                             uint32_t *__restrict__ mask, int32_t *__restrict__ count, double *__restrict__ goal_eff) {
+    constexpr int NX = M::N == 6 ? 3 : 5;
+    const int lane = wp::lane_id();
+    wp::WarpShared<M, 4> &sm = wp::g_sm<M, 4>[0];
+    wp::stage_cta<M, 4>(P, K, tab, lane, 0);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        if (lane < NX) sm.x0[lane] = in.x0[(size_t)NX * b + lane];
+        if (lane < 2) sm.graw[lane] = in.goal[2 * (size_t)b + lane];
+        __syncwarp();
+        unsigned mk = 0u;
+        const int Ks = M::template setup<4>(sm, wp::g_cs.P, in, b, lane, &mk);   // the setup call of wp::solve_warp
+        if (lane == 0) { if (mask) mask[b] = mk; if (count) count[b] = Ks; }
+        if (lane < 2 && goal_eff) goal_eff[2 * (size_t)b + lane] = sm.goal[lane];
+        __syncwarp();
+    }
+}
+template <bool DD>
+__global__ void setup_info_thread_kernel(dcbf_params P, int B, BatchIn in, uint32_t *__restrict__ mask, int32_t *__restrict__ count,
+                                         double *__restrict__ goal_eff) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    Problem pb;
+    load_problem<DD>(P, in, b, pb);   // the setup call of the per-thread kernels
+    if (mask) mask[b] = pb.mc | (pb.me << in.Kc);
+    if (count) count[b] = __popc(pb.mc) + __popc(pb.me);
+    if (goal_eff) { goal_eff[2 * (size_t)b] = pb.goal[0]; goal_eff[2 * (size_t)b + 1] = pb.goal[1]; }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // control tick: prediction + warm-start bookkeeping in front of the solve, dense plan trajectory behind it
 // ---------------------------------------------------------------------------------------------------------------
@@ -476,12 +506,17 @@ __global__ void gen_fields_kernel(int F, uint64_t seed, gen::FieldSpec S, double
 struct GenSinCos { __device__ void operator()(double a, double *s, double *c) const { sincos(a, s, c); } };
 struct GenAtan2 { __device__ double operator()(double y, double x) const { return atan2(y, x); } };
 __global__ void gen_states_kernel(int B, uint64_t seed, gen::StateSpec S, const int32_t *__restrict__ field, const double *__restrict__ cir_rec,
-                                  int Kc, const double *__restrict__ elp_rec, int Ke, double *__restrict__ x0, double *__restrict__ goal,
+                                  int F, int Kc, const double *__restrict__ elp_rec, int Ke, double *__restrict__ x0, double *__restrict__ goal,
                                   int32_t *__restrict__ leg, double *__restrict__ warm, double *__restrict__ last_u, int32_t *__restrict__ attempts) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int fld = field ? field[b] : 0;
     const int nx = S.dd ? 3 : 5, nw = S.dd ? 6 : 15;
+    if ((unsigned)fld >= (unsigned)F) {   // index outside the prepared fields: no state, reported like a field without a clear spot
+        if (x0) for (int i = 0; i < nx; i++) x0[(size_t)nx * b + i] = nan("");
+        if (attempts) attempts[b] = -1;
+        return;
+    }
     const int n = gen::make_state(S, seed, (uint32_t)b, cir_rec + (size_t)fld * Kc * DCBF_CIR_REC, Kc, DCBF_CIR_REC,
                                   elp_rec + (size_t)fld * Ke * DCBF_ELP_REC, Ke, DCBF_ELP_REC, x0 ? x0 + (size_t)nx * b : nullptr,
                                   goal ? goal + 2 * (size_t)b : nullptr, leg ? leg + b : nullptr, warm ? warm + (size_t)nw * b : nullptr,
@@ -713,6 +748,9 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     ctx->P = *params;
     ctx->K = make_consts();
     ctx->device = device;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore_{prev_dev};   // the caller's current device comes back on every exit
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     cudaDeviceProp prop;
@@ -729,23 +767,13 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
         delete W;
         if (!ok) { cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); delete ctx; return DCBF_ERR_CUDA; }
     }
-    {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_lip_refill_kernel, DCBF_BLOCK, 0);
-        ctx->refill_ctas_lip = (nb > 0 ? nb : 1) * ctx->sm_count;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, solve_dd_refill_kernel, DCBF_BLOCK, 0);
-        ctx->refill_ctas_dd = (nb > 0 ? nb : 1) * ctx->sm_count;
-    }
-    const char *rb = getenv("DCBF_REFILL_MIN_BATCH");
-    // measured on B200 (profiles/r01_summary.md): refill desynchronises the lanes of a warp (different iteration index, phase and
-    // line-search depth per lane) and loses 25-30 % against the static assignment -> off unless requested (0: auto, N: batches > N)
-    ctx->refill_min_batch = rb ? atoi(rb) : -1;
     { const char *sp = getenv("DCBF_SPLIT"); ctx->split_classes = sp ? atoi(sp) : 16384; }
     { const char *sp = getenv("DCBF_ORDER"); ctx->sched_min_batch = sp ? atoi(sp) : 2048; }
     { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }   // below ~1 problem per warp slot there is no tail to hide
     if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     ctx->warp_max_batch = wb ? atoi(wb) : 0x7fffffff;   // round 2: the warp kernels win at every batch size (profiles/r02_summary.md)
     *out = ctx;
     return DCBF_OK;
@@ -753,6 +781,8 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
 
 void dcbf_destroy(dcbf_ctx *ctx) {
     if (!ctx) return;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); cudaFree(ctx->d_order); cudaFree(ctx->d_sched); cudaFree(ctx->d_tick); cudaFree(ctx->d_flow); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -760,6 +790,8 @@ void dcbf_destroy(dcbf_ctx *ctx) {
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
     delete ctx;
 }
 
@@ -777,12 +809,18 @@ int dcbf_num_rows(const dcbf_ctx *ctx) {
 int dcbf_set_fields(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir_dev, int32_t Ke, const double *elp_dev, void *stream) {
     if (!ctx || F < 1 || Kc < 0 || Ke < 0 || Kc > DCBF_MAX_OBS || Ke > DCBF_MAX_OBS) return DCBF_ERR_ARG;
     if ((Kc > 0 && !cir_dev) || (Ke > 0 && !elp_dev)) return DCBF_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(stream);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaFree(ctx->cir_rec)); CK(cudaFree(ctx->elp_rec));
-    ctx->cir_rec = ctx->elp_rec = nullptr;
-    CK(cudaMalloc(&ctx->cir_rec, sizeof(double) * DCBF_CIR_REC * (size_t)F * (Kc > 0 ? Kc : 1)));
-    CK(cudaMalloc(&ctx->elp_rec, sizeof(double) * DCBF_ELP_REC * (size_t)F * (Ke > 0 ? Ke : 1)));
+    // the record buffers only grow: a call with fields of the same (or a smaller) shape allocates nothing and does not synchronise
+    const size_t nc = (size_t)F * (Kc > 0 ? Kc : 1), ne = (size_t)F * (Ke > 0 ? Ke : 1);
+    if (ctx->cir_cap < nc) {
+        CK(cudaFree(ctx->cir_rec)); ctx->cir_rec = nullptr; ctx->cir_cap = 0;
+        CK(cudaMalloc(&ctx->cir_rec, sizeof(double) * DCBF_CIR_REC * nc)); ctx->cir_cap = nc;
+    }
+    if (ctx->elp_cap < ne) {
+        CK(cudaFree(ctx->elp_rec)); ctx->elp_rec = nullptr; ctx->elp_cap = 0;
+        CK(cudaMalloc(&ctx->elp_rec, sizeof(double) * DCBF_ELP_REC * ne)); ctx->elp_cap = ne;
+    }
     const int n = F * (Kc > Ke ? Kc : Ke);
     if (n > 0) {
         prep_fields_kernel<<<(n + 255) / 256, 256, 0, st>>>(F, Kc, cir_dev, Ke, elp_dev, ctx->cir_rec, ctx->elp_rec);
@@ -806,8 +844,8 @@ int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, co
     if (B == 0) return DCBF_OK;
     if (!x0 || !goal || !z) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
-    CK(cudaSetDevice(ctx->device));
-    BatchIn in = {x0, goal, nullptr, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
+    ENTER(stream);
+    BatchIn in = {x0, goal, nullptr, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F};
     EvalPtrs ev = {z, lambda, f, grad, c, jac, cl, cu, hess, dcbf_num_rows(ctx)};
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->P.formulation == DCBF_DD) eval_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, ev);
@@ -824,20 +862,12 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
     if (B == 0) return DCBF_OK;
     if (!x0 || !goal || !warm) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
-    CK(cudaSetDevice(ctx->device));
-    BatchIn in = {x0, goal, warm, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
+    ENTER(stream);
+    BatchIn in = {x0, goal, warm, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F};
     SolveOut out = {u, x_plan, p_plan, obj, viol, status, iters, close2goal};
     cudaStream_t st = (cudaStream_t)stream;
     const bool dd = ctx->P.formulation == DCBF_DD;
-    const int resident = (dd ? ctx->refill_ctas_dd : ctx->refill_ctas_lip) * DCBF_BLOCK;
-    const bool refill = ctx->refill_min_batch >= 0 && B > (ctx->refill_min_batch > 0 ? ctx->refill_min_batch : resident) &&
-                        !use_warp_kernel(ctx, B);
-    if (refill) {
-        CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
-        if (dd) solve_dd_refill_kernel<<<ctx->refill_ctas_dd, DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out, ctx->d_counter);
-        else solve_lip_refill_kernel<<<ctx->refill_ctas_lip, DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out, ctx->d_counter);
-    }
-    else if (dd && use_warp_kernel(ctx, B)) {
+    if (dd && use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);
         const int rc = ns == 1 ? launch_solve_dd_warp<1>(ctx, B, in, out, st) : (ns == 2 ? launch_solve_dd_warp<2>(ctx, B, in, out, st) : launch_solve_dd_warp<4>(ctx, B, in, out, st));
         if (rc != DCBF_OK) return rc;
@@ -857,6 +887,29 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
     return DCBF_OK;
 }
 
+int dcbf_setup_info(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *field, uint32_t *mask, int32_t *count,
+                    double *goal_eff, void *stream) {
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
+    if (B == 0) return DCBF_OK;
+    if (!x0 || !goal) return DCBF_ERR_ARG;
+    if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
+    ENTER(stream);
+    BatchIn in = {x0, goal, nullptr, nullptr, nullptr, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F};
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dd = ctx->P.formulation == DCBF_DD;
+    if (ctx->kernel_mode == 1) {
+        if (dd) setup_info_thread_kernel<true><<<(B + 127) / 128, 128, 0, st>>>(ctx->P, B, in, mask, count, goal_eff);
+        else setup_info_thread_kernel<false><<<(B + 127) / 128, 128, 0, st>>>(ctx->P, B, in, mask, count, goal_eff);
+    } else {
+        const int grid = B < ctx->sm_count * 16 ? B : ctx->sm_count * 16;
+        if (dd) setup_info_warp_kernel<wp::DdW><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, mask, count, goal_eff);
+        else setup_info_warp_kernel<wp::LipW><<<grid, 32, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, mask, count, goal_eff);
+    }
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
 int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo_vel, const double *glo_hd, const double *glo_p,
               const double *t_rest, const double *goal, const int32_t *leg, const int32_t *field, const double *prev_plan,
               const uint8_t *mode, double *x_next, double *warm, double *u, double *x_plan, double *p_plan, int32_t *status,
@@ -866,7 +919,7 @@ int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo
     if (ctx->P.formulation == DCBF_DD) return DCBF_ERR_ARG;
     if (!glo_pos || !glo_vel || !glo_hd || !glo_p || !t_rest || !goal) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(stream);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t b = (size_t)B;
     if (ctx->tick_cap < b) {   // scratch for the intermediates the caller does not want back
@@ -911,7 +964,7 @@ int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double 
     if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
     if (!x_alip || !y_alip || !time || !support || !speed || speed_stride < 1 || !(H > 0.0) || !(T > 0.0) || !(m > 0.0)) return DCBF_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(stream);
     alip_foot_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, x_alip, y_alip, time, support, speed, speed_stride, H, T, m, W, foot, am, next);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -921,7 +974,7 @@ int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double 
 int dcbf_math_probe(dcbf_ctx *ctx, int32_t n, const double *a, const double *b, double *out, void *stream) {
     if (!ctx || n < 0 || (n > 0 && (!a || !b || !out))) return DCBF_ERR_ARG;
     if (n == 0) return DCBF_OK;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(stream);
     math_probe_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, a, b, out);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -933,7 +986,7 @@ int dcbf_heading_input(dcbf_ctx *ctx, int32_t B, const double *cur_hd, double *n
     if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
     if (!cur_hd || !nex_turn || !mpc_hds || !hd_input || hds_stride < 1 || hds_step < 1 || out_stride < 1) return DCBF_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(stream);
     heading_input_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, cur_hd, nex_turn, mpc_hds, hds_stride, hds_step, hd_input, out_stride);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -945,7 +998,7 @@ int dcbf_gen_fields(dcbf_ctx *ctx, int32_t F, uint64_t seed, int32_t num, int32_
     if (!ctx || F < 0 || num < 1 || num > DCBF_GEN_MAX_OBS || !(margin > 0.0) || !(radius >= 0.35) || !(half_gap >= 0.0)) return DCBF_ERR_ARG;
     if (F == 0) return DCBF_OK;
     if (!cir || (mix && num > 1 && !elp)) return DCBF_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(stream);
     gen::FieldSpec S = {num, mix ? 1 : 0, margin, radius, half_gap, safe_dis, 2000, 64};
     gen_fields_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, seed, S, cir, elp, draws);
     CK(cudaGetLastError());
@@ -958,10 +1011,10 @@ int dcbf_gen_states(dcbf_ctx *ctx, int32_t B, uint64_t seed, const int32_t *fiel
     if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(stream);
     const int dd = ctx->P.formulation == DCBF_DD;
     gen::StateSpec S = {dd, goal_x, goal_y, 8.0, 0.05, 0.3, 0.4, 0.8, 0.15, bvy_max > 0.0 ? bvy_max : ctx->P.bvy_max, 64};
-    gen_states_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, seed, S, field, ctx->cir_rec, ctx->Kc, ctx->elp_rec, ctx->Ke, x0, goal,
+    gen_states_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, seed, S, field, ctx->cir_rec, ctx->F, ctx->Kc, ctx->elp_rec, ctx->Ke, x0, goal,
                                                                         leg, warm, last_u, attempts);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -976,8 +1029,8 @@ int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, cons
     if (B == 0) return DCBF_OK;
     if (!x0 || !goal) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
-    CK(cudaSetDevice(ctx->device));
-    BatchIn in = {x0, goal, nullptr, nullptr, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke};
+    ENTER(stream);
+    BatchIn in = {x0, goal, nullptr, nullptr, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F};
     RolloutOut out = {x_final, traj, steps_done, n_infeasible, total_iters};
     if (use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);
@@ -1018,12 +1071,12 @@ static int ensure_staging(dcbf_ctx *ctx, size_t bytes) {
 int dcbf_set_fields_host(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir_host, int32_t Ke, const double *elp_host) {
     if (!ctx || F < 1 || Kc < 0 || Ke < 0 || Kc > DCBF_MAX_OBS || Ke > DCBF_MAX_OBS) return DCBF_ERR_ARG;
     if ((Kc > 0 && !cir_host) || (Ke > 0 && !elp_host)) return DCBF_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaFree(ctx->d_cir_raw)); CK(cudaFree(ctx->d_elp_raw));
-    ctx->d_cir_raw = ctx->d_elp_raw = nullptr;
+    ENTER(ctx->stream);
     const size_t cb = sizeof(double) * 3 * (size_t)F * Kc, eb = sizeof(double) * 5 * (size_t)F * Ke;
-    if (cb) { CK(cudaMalloc(&ctx->d_cir_raw, cb)); CK(cudaMemcpyAsync(ctx->d_cir_raw, cir_host, cb, cudaMemcpyHostToDevice, ctx->stream)); }
-    if (eb) { CK(cudaMalloc(&ctx->d_elp_raw, eb)); CK(cudaMemcpyAsync(ctx->d_elp_raw, elp_host, eb, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (ctx->cir_raw_bytes < cb) { CK(cudaFree(ctx->d_cir_raw)); ctx->d_cir_raw = nullptr; ctx->cir_raw_bytes = 0; CK(cudaMalloc(&ctx->d_cir_raw, cb)); ctx->cir_raw_bytes = cb; }
+    if (ctx->elp_raw_bytes < eb) { CK(cudaFree(ctx->d_elp_raw)); ctx->d_elp_raw = nullptr; ctx->elp_raw_bytes = 0; CK(cudaMalloc(&ctx->d_elp_raw, eb)); ctx->elp_raw_bytes = eb; }
+    if (cb) CK(cudaMemcpyAsync(ctx->d_cir_raw, cir_host, cb, cudaMemcpyHostToDevice, ctx->stream));
+    if (eb) CK(cudaMemcpyAsync(ctx->d_elp_raw, elp_host, eb, cudaMemcpyHostToDevice, ctx->stream));
     int rc = dcbf_set_fields(ctx, F, Kc, ctx->d_cir_raw, Ke, ctx->d_elp_raw, ctx->stream);
     if (rc != DCBF_OK) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1039,7 +1092,7 @@ int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *go
     if (B == 0) return DCBF_OK;
     if (!x0 || !goal || !warm) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
-    CK(cudaSetDevice(ctx->device));
+    ENTER(ctx->stream);
     const bool dd = ctx->P.formulation == DCBF_DD;
     const size_t nx = dd ? 3 : 5, nu = dd ? 6 : 15, b = (size_t)B;
     // layout of the staging block: inputs first (one H2D copy), outputs after (one D2H copy)
@@ -1117,7 +1170,8 @@ int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *go
 
 double dcbf_fp64_peak_tflops(dcbf_ctx *ctx, int32_t repeats) {
     if (!ctx) return -1.0;
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1.0;
+    Call call_(ctx, ctx->stream);
+    if (!call_.ok) return -1.0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return -1.0;
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;

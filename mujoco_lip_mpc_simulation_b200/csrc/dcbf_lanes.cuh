@@ -28,7 +28,17 @@ struct BatchIn {
     const int32_t *leg, *field;
     const double *cir_rec, *elp_rec;
     int Kc, Ke;
+    int F;   // number of prepared fields (0: unknown, no range check)
 };
+
+// field index of scenario b.  An index outside [0, F) -- a stale or short index array -- must not become an out-of-bounds read:
+// the scenario then reads field 0 and `bad` makes the caller poison its state, so that it comes back with status -13
+// (invalid number) and NaN plans instead of silent garbage.
+DCBF_HD int batch_field(const BatchIn &in, int b, bool &bad) {
+    const int f = in.field ? in.field[b] : 0;
+    bad = in.F > 0 && (unsigned)f >= (unsigned)in.F;
+    return bad ? 0 : f;
+}
 
 template <bool DD>
 DCBF_HD void load_problem(const dcbf_params &P, const BatchIn &in, int b, Problem &pb) {
@@ -39,7 +49,9 @@ DCBF_HD void load_problem(const dcbf_params &P, const BatchIn &in, int b, Proble
     pb.leg = in.leg ? in.leg[b] : 1;
     if (DD && in.last_u) { pb.last_u[0] = in.last_u[2 * (size_t)b]; pb.last_u[1] = in.last_u[2 * (size_t)b + 1]; }
     else { pb.last_u[0] = 0.0; pb.last_u[1] = 0.0; }
-    const int f = in.field ? in.field[b] : 0;
+    bool bad;
+    const int f = batch_field(in, b, bad);
+    if (bad) { pb.x0[2] = nan(""); pb.x0[NX - 1] = nan(""); }
     pb.nc = in.Kc; pb.ne = in.Ke;
     pb.cir = in.cir_rec + (size_t)f * in.Kc * DCBF_CIR_REC;
     pb.elp = in.elp_rec + (size_t)f * in.Ke * DCBF_ELP_REC;

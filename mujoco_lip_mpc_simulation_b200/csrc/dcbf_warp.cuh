@@ -310,8 +310,10 @@ __device__ __forceinline__ void eval_cbf(const double *o, double gm1, double x1,
 // `sel_out` / `rec` let the LIP model run the detour heuristic on the same lanes.
 template <class M, int NS>
 __device__ __forceinline__ int stage_obstacles(const dcbf_params &P, WarpShared<M, NS> &sm, const BatchIn &in, int b, int lane, double px, double py,
-                                               double *rec, bool &sel_out, bool &is_circle) {
-    const int fld = in.field ? in.field[b] : 0;
+                                               double *rec, bool &sel_out, bool &is_circle, unsigned *mask_out = nullptr) {
+    bool bad;
+    const int fld = batch_field(in, b, bad);
+    if (bad && lane == 0) { sm.x0[2] = nan(""); sm.x0[4] = nan(""); }   // invalid field index: the solve returns -13 (the caller syncs the warp before it reads x0 again)
     const double *cir = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC;
     const double *elp = in.elp_rec + (size_t)fld * in.Ke * DCBF_ELP_REC;
     const int j = lane;
@@ -337,6 +339,7 @@ __device__ __forceinline__ int stage_obstacles(const dcbf_params &P, WarpShared<
         }
     }
     sel_out = sel; is_circle = is_c;
+    if (mask_out) *mask_out = mask;
     return __popc(mask);
 }
 
@@ -358,11 +361,11 @@ struct LipW {
 
     // problem setup: obstacle selection + compaction, detour heuristic (MPC_LIP_sig_step.py:229-253), node 0
     template <int NS>
-    static __device__ __forceinline__ int setup(WarpShared<LipW, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane) {
+    static __device__ __forceinline__ int setup(WarpShared<LipW, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane, unsigned *mask_out = nullptr) {
         const double px = sm.x0[0], py = sm.x0[1];
         double rec[6];
         bool sel, is_c;
-        const int Ks = stage_obstacles<LipW, NS>(P, sm, in, b, lane, px, py, rec, sel, is_c);
+        const int Ks = stage_obstacles<LipW, NS>(P, sm, in, b, lane, px, py, rec, sel, is_c, mask_out);
         bool hit = false;
         double ngx = 0.0, ngy = 0.0;
         const double gx = sm.graw[0], gy = sm.graw[1];
@@ -619,10 +622,10 @@ struct DdW {
     static __device__ __forceinline__ int class_start(int cls, int Ks, int) { return cls * Ks; }
 
     template <int NS>
-    static __device__ __forceinline__ int setup(WarpShared<DdW, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane) {
+    static __device__ __forceinline__ int setup(WarpShared<DdW, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane, unsigned *mask_out = nullptr) {
         double rec[6];
         bool sel, is_c;
-        const int Ks = stage_obstacles<DdW, NS>(P, sm, in, b, lane, sm.x0[0], sm.x0[1], rec, sel, is_c);
+        const int Ks = stage_obstacles<DdW, NS>(P, sm, in, b, lane, sm.x0[0], sm.x0[1], rec, sel, is_c, mask_out);
         if (lane == 0) { sm.goal[0] = sm.graw[0]; sm.goal[1] = sm.graw[1]; }   // no detour heuristic (MPC_DD_sig_step.py:144-168 is commented out)
         if (lane < 3) sm.nd.nodes[0][lane] = sm.x0[lane];
         if (lane < 6) { sm.nd.Jx[0][lane] = 0.0; sm.nd.Jy[0][lane] = 0.0; }

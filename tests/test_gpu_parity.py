@@ -45,18 +45,29 @@ def _agreement(form, res, ref, B):
     return same_class, both, dp, rel
 
 
+def _distinct_optima(res, ref, both, dp, rel):
+    """jointly converged pairs whose plans differ AND which the data prove to be two local optima of the non-convex NLP:
+    both points are feasible to 1e-6 and their objectives differ (north_star: "any mismatch explained as a distinct local
+    optimum, with the fraction reported")."""
+    return both & (dp > POS_TOL) & (rel > OBJ_TOL) & (res.viol.cpu().numpy() <= 1e-6) & (ref["viol"] <= 1e-6)
+
+
 @pytest.mark.parametrize("form", ["sig_step", "modi", "dd"])
 def test_eval_kernel_matches_reference_callbacks(gpu, form):
     """K1 against golden vectors from the reference's own LIP_Prob classes (mapped to the reduced space)."""
     g = np.load(os.path.join(G, f"callbacks_{form}.npz"), allow_pickle=True)
     n_case = len(g["xk"])
     U = lip_np.p_map()
+    ran = 0
     for b in range(n_case):
-        if form == "modi" and not (g["sel_c"][b].all() and g["sel_e"][b].all()):
-            continue   # the recorded rows depend on the selection; dcbf_eval emits every row
-        elp = g["elp"][b] if len(g["elp"][b]) else None
+        # the reference builds its rows from the SELECTED obstacles (MPC_LIP_modi.py:325-338; all of them for the other two
+        # formulations); dcbf_eval emits a row per obstacle of the field, so the field handed over is the selection
+        cir = g["cir"][b][g["sel_c"][b].astype(bool)]
+        elp = g["elp"][b][g["sel_e"][b].astype(bool)] if len(g["elp"][b]) else np.zeros((0, 5))
         s = gpu(form, device=0)
-        s.set_fields(g["cir"][b], elp)
+        s.set_fields(cir if len(cir) else None, elp if len(elp) else None)
+        assert s.m == len(g["c"][b])
+        ran += 1
         if form == "dd":
             z = g["u"][b]
         else:
@@ -71,6 +82,66 @@ def test_eval_kernel_matches_reference_callbacks(gpu, form):
         np.testing.assert_allclose(J, Jref, rtol=0, atol=1e-11)
         np.testing.assert_array_equal(r["cl"][0].cpu().numpy(), np.asarray(g["cl"][b], float))
         np.testing.assert_array_equal(r["cu"][0].cpu().numpy(), np.asarray(g["cu"][b], float))
+    assert ran == n_case and ran >= 20
+
+
+@pytest.mark.parametrize("mode", ["warp", "thread"])
+def test_obstacle_selection_and_detour_goal_match_reference(gpu, monkeypatch, mode):
+    """select_obs (MPC_LIP_modi.py:325-338) and the goal shift over the selected circles (:249-271) exactly as the solve kernels
+    apply them (dcbf_setup_info runs their setup code), against the masks / effective goals recorded from the reference classes;
+    sig_step: every obstacle is a row and the goal shift searches all circles (MPC_LIP_sig_step.py:229-253)."""
+    monkeypatch.setenv("DCBF_KERNEL", mode)
+    for form in ("modi", "sig_step", "dd"):
+        g = np.load(os.path.join(G, f"callbacks_{form}.npz"), allow_pickle=True)
+        n_sel = n_shift = 0
+        for b in range(len(g["xk"])):
+            cir, elp = g["cir"][b], g["elp"][b]
+            s = gpu(form, device=0)
+            s.set_fields(cir if len(cir) else None, elp if len(elp) else None)
+            r = s.setup_info(g["xk"][b][None, :s.nx], g["goal"][b][None])
+            want = sum(int(v) << j for j, v in enumerate(list(g["sel_c"][b]) + list(g["sel_e"][b])))
+            assert int(r["mask"][0]) == want, (form, b)
+            assert int(r["count"][0]) == int(g["sel_c"][b].sum() + g["sel_e"][b].sum())
+            np.testing.assert_allclose(r["goal_eff"][0].cpu().numpy(), g["goal_eff"][b], rtol=0, atol=1e-12)
+            n_sel += int(want != (1 << (len(cir) + len(elp))) - 1)
+            n_shift += int(np.abs(g["goal_eff"][b] - g["goal"][b]).max() > 1e-9)
+        if form == "modi":
+            assert n_sel >= 20      # the fixture exercises the selection: nearly every case drops an obstacle
+        if form != "dd":
+            assert n_shift >= 1     # ... and the detour
+    # a batch: the mask is the definition, evaluated in numpy on the same fields
+    sc = scenarios.make_batch("modi", 4096, seed=5)
+    s = _solver(gpu, "modi", sc)
+    r = s.setup_info(sc.x0, sc.goal, field=sc.field)
+    px, py = sc.x0[:, 0:1], sc.x0[:, 1:2]
+    c, e = sc.cir[sc.field], sc.elp[sc.field]
+    sel_c = (px - c[:, :, 0]) ** 2 + (py - c[:, :, 1]) ** 2 - c[:, :, 2] ** 2 <= 16.0
+    sel_e = (px - e[:, :, 0]) ** 2 + (py - e[:, :, 1]) ** 2 - np.maximum(e[:, :, 2], e[:, :, 3]) ** 2 <= 16.0
+    bits = np.concatenate([sel_c, sel_e], axis=1)
+    want = (bits * (1 << np.arange(bits.shape[1]))[None]).sum(axis=1)
+    mask = r["mask"].cpu().numpy()
+    # a scenario whose distance sits within rounding of the threshold may differ (d^2 - r^2 is formed from r^2 prepared on the device)
+    assert np.mean(mask == want) >= 0.9999
+    assert np.array_equal(r["count"].cpu().numpy(), np.array([bin(int(v)).count("1") for v in mask]))
+
+
+def test_invalid_field_index_is_reported_not_dereferenced(gpu):
+    """a stale / out-of-range field index must not become an out-of-bounds read: that scenario returns status -13"""
+    sc = scenarios.make_batch("sig_step", 512, seed=3, n_fields=8)
+    s = _solver(gpu, "sig_step", sc)
+    fld = sc.field.copy()
+    fld[7] = 8          # one past the last field
+    fld[100] = -1
+    fld[300] = 1 << 30
+    res = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=fld)
+    ref = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
+    st = res.status.cpu().numpy()
+    assert list(st[[7, 100, 300]]) == [-13, -13, -13]
+    keep = np.ones(512, bool); keep[[7, 100, 300]] = False
+    assert np.array_equal(st[keep], ref.status.cpu().numpy()[keep])
+    assert torch.equal(res.u[torch.as_tensor(keep)], ref.u[torch.as_tensor(keep)])
+    with pytest.raises(ValueError):
+        s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field[:100])
 
 
 @pytest.mark.parametrize("form", ["sig_step", "modi", "dd"])
@@ -109,25 +180,37 @@ def test_solve_matches_golden(gpu, form):
     res = s.solve(g["x0"], g["goal"], g["leg"], g["warm"], field=np.arange(n, dtype=np.int32), last_u=g["last_u"])
     ref = dict(status=g["status"], u=g["u"], p_plan=g["p_plan"], f=g["f"])
     same_class, both, dp, rel = _agreement(form, res, ref, n)
-    assert same_class.mean() >= 0.98
-    assert np.mean(dp[both] <= POS_TOL) >= 0.98 and np.mean(rel[both] <= OBJ_TOL) >= 0.98
+    # the fixture holds a few hundred problems: one mismatch is 0.3-0.5 %, so the bound here is "at most one", the 99.9 % bound
+    # of the north_star is asserted on the full-size batches below
+    print(f"{form}: {n} golden problems, class mismatches {(~same_class).sum()}, plan mismatches {(dp[both] > POS_TOL).sum()}")
+    assert (~same_class).sum() <= 1
+    assert (dp[both] > POS_TOL).sum() <= 1 and (rel[both] > OBJ_TOL).sum() <= 1
 
 
-@pytest.mark.parametrize("form,B,seed", [("sig_step", 4096, 0), ("modi", 2048, 1), ("dd", 2048, 2)])
+@pytest.mark.parametrize("form,B,seed", [("sig_step", 4096, 0), ("modi", 65536, 1), ("dd", 65536, 2)])
 def test_solve_matches_oracle_on_bench_distribution(gpu, form, B, seed):
-    """config 2 at its full size (4096) and slices of configs 3/4, against the C oracle on the same seeded inputs."""
+    """configs 2, 3 and 4 at their FULL sizes (4096 / 65536 / 65536) against the C oracle on the same seeded inputs, with the
+    north_star's numbers: the same feasible / infeasible class on >= 99.9 %, plans within 1e-4 and objectives within 1e-6
+    relative on >= 99.9 % of the jointly converged solves once the pairs this test PROVES to be two distinct local optima
+    (both feasible to 1e-6, objectives differ) are set aside; their fraction is printed and bounded."""
     sc = scenarios.make_batch(form, B, seed=seed)
-    s = _solver(gpu, form, sc, max_iter=300)
+    s = _solver(gpu, form, sc)
     res = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field, last_u=sc.last_u)
-    P = c_oracle.params(form, max_iter=300)
+    P = c_oracle.params(form, max_iter=200)
     ref = c_oracle.solve_batch(P, sc.x0, sc.goal, sc.leg, sc.cir, sc.elp if sc.elp.shape[1] else None, sc.warm,
                                field=sc.field, last_u=sc.last_u, threads=os.cpu_count() or 4)
     same_class, both, dp, rel = _agreement(form, res, ref, B)
-    print(f"{form}: class agreement {same_class.mean():.5f}, solution agreement {np.mean(dp[both] <= POS_TOL):.5f}, "
-          f"objective agreement {np.mean(rel[both] <= OBJ_TOL):.5f}, converged both {both.sum()}/{B}")
-    assert same_class.mean() >= 0.995
-    assert np.mean(dp[both] <= POS_TOL) >= 0.995
-    assert np.mean(rel[both] <= OBJ_TOL) >= 0.995
+    distinct = _distinct_optima(res, ref, both, dp, rel)
+    rest = both & ~distinct
+    print(f"{form} B={B}: class agreement {same_class.mean():.5f}; jointly converged {both.sum()}; distinct local optima "
+          f"{distinct.sum()} ({distinct.sum() / max(1, both.sum()):.5f}); plans within 1e-4 {np.mean(dp[both] <= POS_TOL):.5f} raw, "
+          f"{np.mean(dp[rest] <= POS_TOL):.5f} without them; objectives within 1e-6 {np.mean(rel[both] <= OBJ_TOL):.5f} raw, "
+          f"{np.mean(rel[rest] <= OBJ_TOL):.5f} without them")
+    assert same_class.mean() >= 0.999
+    assert both.mean() >= 0.5
+    assert distinct.sum() <= 0.003 * both.sum()
+    assert np.mean(dp[rest] <= POS_TOL) >= 0.999
+    assert np.mean(rel[rest] <= OBJ_TOL) >= 0.999
 
 
 @pytest.mark.parametrize("mode", ["thread", "warp"])
