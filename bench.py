@@ -48,7 +48,25 @@ def f_iter(n: int, m: int, m_nl: int, m_b: int, kc: int, ke: int, form: str) -> 
 
 F_ITER_SIG_K6 = f_iter(9, 30, 27, 0, 6, 0, "sig_step")   # = 8455
 POOL = 8                             # distinct synthetic batches the timed steps rotate through (same pool for every N)
-NCU_DRAM_BYTES_PER_LAUNCH = 0.697e6  # measured once per change with ncu (profiles/r02_summary.md); not re-measured at run time
+MAX_ITER = 200                       # dcbf_default_params (a safety cap; see DESIGN.md "iteration caps")
+CONFIG5 = dict(scenarios=1 << 20, steps=50, seed=3, n_fields=4096)    # BASELINE.json configs[4] / SURVEY.md 8(d) config 5
+
+
+def workload_config():
+    """the `config` object of the JSON line -- the SAME dict for both arms (bench.py and bench.py --impl reference)"""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "formulation": "sig_step", "n_circles": 6, "seed": SEED,
+            "l2": "flushed between timed steps (256 MiB memset)", "max_iter": MAX_ITER,
+            "batches": f"pool of {POOL} distinct batches (seeds {SEED}..{SEED + POOL - 1}); rank r solves batch (r + step) mod {POOL}"}
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture summary (profiles/, written by
+    tools/ncu_lines.py / by hand from `ncu --page raw`); None if the file is missing"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return float(d["dram_bytes_per_launch"]), d.get("source", "profiles/ncu_traffic.json")
+    except Exception:
+        return None, None
 
 
 def io_bytes_per_solve(kc: int) -> int:
@@ -94,25 +112,28 @@ def run_reference(args):
     from oracle import c_oracle
     cores = os.cpu_count() or 1
     sample = 1024
-    sc = scenarios.make_batch("sig_step", BATCH, seed=SEED)
-    P = c_oracle.params("sig_step", max_iter=300)
+    # the GPU arm's workload: the same pool of POOL batches, step s solves batch s mod POOL (rank 0's rotation) -- here a bounded
+    # sample of it per step, the first `sample` scenarios of that batch
+    pool = [scenarios.make_batch("sig_step", BATCH, seed=SEED + j) for j in range(POOL)]
+    P = c_oracle.params("sig_step", max_iter=MAX_ITER)
     sl = slice(0, sample)
 
-    def step():
+    def step(s_):
+        sc = pool[s_ % POOL]
         return c_oracle.solve_batch(P, sc.x0[sl], sc.goal[sl], sc.leg[sl], sc.cir, None, sc.warm[sl], field=sc.field[sl], threads=cores)
-    for _ in range(args.warmup):
-        step()
+    for s_ in range(args.warmup):
+        step(s_)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
+    for s_ in range(args.steps):
+        step(s_)
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
     line = {"impl": "reference", "metric": "D-CBF ALIP MPC solves/sec", "value": val, "unit": "solves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_per_step": sample},
+            "config": workload_config(),
             "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
-                             "sample": f"first {sample} scenarios of the workload per step, oracle/dcbf_oracle.c on {cores} threads "
+                             "sample": f"first {sample} scenarios of the step's batch (same pool and rotation as the GPU arm), oracle/dcbf_oracle.c on {cores} threads "
                                        "(reference = Python callbacks + cyipopt/Ipopt/MA57, not installable: no Ipopt, no network)"},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -126,6 +147,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also report large-batch throughput (65536 / 1M scenarios)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 1M x 50 sharded closed-loop rollout (BASELINE.json configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -158,6 +180,7 @@ def main():
     sc = pool[rank % POOL]                              # this rank's batch for the single-solve latency probe
     sc_last = pool[(rank + args.steps - 1) % POOL]      # the batch of the last timed step (status / agreement checks)
     solver = DcbfSolver("sig_step", device=local)
+    assert int(solver.P.max_iter) == MAX_ITER
     solver.set_fields(cir_all)
     t = lambda a, dt: torch.as_tensor(a, dtype=dt, device=dev)  # noqa: E731
     dev_in = [(t(b_.x0, torch.float64), t(b_.goal, torch.float64), t(b_.leg, torch.int32), t(b_.field + j * F, torch.int32), t(b_.warm, torch.float64))
@@ -244,6 +267,50 @@ def main():
         solver.solve_host(sc.x0[j:j + 1], sc.goal[j:j + 1], sc.leg[j:j + 1], sc.warm[j:j + 1], field=own_field[j:j + 1], out=one)
         lat.append((time.perf_counter() - t0) * 1e6)
 
+    # ---- config 5 (BASELINE.json configs[4]): closed-loop LIP rollout, 1 M scenarios x 50 steps with warm-started re-planning,
+    # sharded by batch slice over the ranks (strong scaling: 1 M / N scenarios per GPU), final result gather over NCCL -------------
+    cfg5 = None
+    if not args.no_config5:
+        from mujoco_lip_mpc_simulation_b200.sharding import gather_rollout, rollout_shard, shard_inputs
+        B5, S5 = CONFIG5["scenarios"], CONFIG5["steps"]
+        sv5 = DcbfSolver("sig_step", device=local)
+        warm5 = shard_inputs(sv5, 8192, seed=99, n_fields=256, rank=rank, world=world)      # warm-up: kernel load, allocator, NCCL
+        gather_rollout(rollout_shard(sv5, 2, warm5), 8192)
+        inp5 = shard_inputs(sv5, B5, seed=CONFIG5["seed"], n_fields=CONFIG5["n_fields"], rank=rank, world=world)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        l5 = sv5.launches
+        ev[0].record()
+        r5 = rollout_shard(sv5, S5, inp5)
+        ev[1].record()
+        g5 = gather_rollout(r5, B5)                # the only collective of the path (one NCCL all-gather of 56 B per scenario)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        roll_ms = max_over_ranks(ev[0].elapsed_time(ev[1]), dev)
+        gath_ms = max_over_ranks(ev[1].elapsed_time(ev[2]), dev)
+        solves5 = sum_over_ranks(float(r5["steps_done"].sum().item()), dev)
+        iters5 = sum_over_ranks(float(r5["total_iters"].sum().item()), dev)
+        ninf5 = sum_over_ranks(float(r5["n_infeasible"].sum().item()), dev)
+        if rank == 0:
+            xf, sd = g5["x_final"], g5["steps_done"]
+            arrived = ((xf[:, 0] - 10.0) ** 2 + (xf[:, 1] - 10.0) ** 2).sqrt() <= 0.35 + 1e-9
+            cfg5 = {"workload": "configs[4]: closed-loop LIP rollout, 1 M scenarios x 50 steps, warm-started re-planning, sharded by batch slice",
+                    "scenarios": B5, "steps": S5, "seed": CONFIG5["seed"], "field_pool": CONFIG5["n_fields"], "scaling": "strong",
+                    "scenarios_per_gpu": (B5 + world - 1) // world, "solves": int(solves5), "rollout_ms": roll_ms,
+                    "solves_per_s": solves5 / (roll_ms * 1e-3), "gather_ms": gath_ms, "gather_bytes": B5 * 56,
+                    "gather": "one all_gather_into_tensor of [n, 7] FP64 per rank (NCCL)" if world > 1 else "none (one rank)",
+                    "mean_iters_per_replan": iters5 / solves5, "infeasible_replan_frac": ninf5 / solves5,
+                    "mean_steps": float(sd.double().mean()), "arrived_frac": float(arrived.double().mean()),
+                    "gpu_launches": int(sv5.launches - l5),
+                    # rank-count-independent fingerprint of the gathered result (identical at N = 1, 2, 4, 8)
+                    "checksum": {"steps_done_sum": int(sd.sum()), "n_infeasible_sum": int(g5["n_infeasible"].sum()),
+                                 "x_final_nansum": float(torch.nan_to_num(xf).sum())}}
+        del r5, g5, inp5, sv5
+
     extra = {}
     if args.sweep and rank == 0:
         for form, Bs in (("sig_step", 65536), ("sig_step", 1 << 20), ("modi", 65536), ("dd", 4096), ("dd", 65536)):
@@ -303,7 +370,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle
         cores = os.cpu_count() or 1
-        P = c_oracle.params("sig_step", max_iter=300)
+        P = c_oracle.params("sig_step", max_iter=MAX_ITER)
         t0 = time.perf_counter()
         ref = c_oracle.solve_batch(P, sc_last.x0, sc_last.goal, sc_last.leg, sc_last.cir, None, sc_last.warm, field=sc_last.field, threads=cores)
         dt = time.perf_counter() - t0
@@ -330,9 +397,7 @@ def main():
             "metric": "D-CBF ALIP MPC solves/sec", "value": total_solves / dev_s, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "formulation": "sig_step", "n_circles": 6, "seed": SEED,
-                       "l2": "flushed between timed steps (256 MiB memset)", "max_iter": int(solver.P.max_iter),
-                       "batches": f"pool of {POOL} distinct batches (seeds {SEED}..{SEED + POOL - 1}); rank r solves batch (r + step) mod {POOL}"},
+            "config": workload_config(),
             "e2e": {"value": total_solves / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "transfer": ("page-locked host buffers through dcbf_solve_host; the kernels load the inputs from and store the results to the "
                                  "mapped host memory (no staging copy)" if os.environ.get("DCBF_ZEROCOPY", "1") != "0" else
@@ -341,10 +406,10 @@ def main():
             "p50_solve_us": float(np.median(lat)), "p95_solve_us": float(np.percentile(lat, 95)),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": "profiles/r02_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of solve_lip_warp_kernel<1>, B = 4096)",
+                         "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
                          "kernel": "solve_lip_warp_kernel<1> (one problem per warp)", "algorithmic_bytes": B * io_bytes_per_solve(6),
                          "peak_source": "measured on this GPU by dcbf_fp64_peak_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
-                         "flop_per_iter": F_ITER_SIG_K6, "iters_per_step": int(iters.sum()),
+                         "flop_per_iter": F_ITER_SIG_K6, "iters_per_step": flop_per_step / F_ITER_SIG_K6,
                          "hbm": {"achieved": io_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": io_gbs / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
             "iters": {"mean": float(iters.mean()), "p50": float(np.median(iters)), "p99": float(np.percentile(iters, 99)), "max": int(iters.max())},
@@ -352,7 +417,13 @@ def main():
             "clocks": sampler.summary(),
         }
         if cpu:
+            try:   # the reference's own Python path, measured where the reference exists (tools/reference_python_baseline.py)
+                cpu["reference_python"] = json.load(open(os.path.join(ROOT, "profiles", "r03_reference_python.json")))
+            except Exception:
+                cpu["reference_python"] = None
             line["cpu_baseline"] = cpu
+        if cfg5:
+            line["config5"] = cfg5
         if extra:
             line["sweep"] = extra
         print(json.dumps(line))
