@@ -297,7 +297,7 @@ def main():
         ninf5 = sum_over_ranks(float(r5["n_infeasible"].sum().item()), dev)
         if rank == 0:
             xf, sd = g5["x_final"], g5["steps_done"]
-            arrived = ((xf[:, 0] - 10.0) ** 2 + (xf[:, 1] - 10.0) ** 2).sqrt() <= 0.35 + 1e-9
+            arrived = sd < S5          # stopped early: close_2_goal of MPC_LIP_sig_step.py:110-111 (a planned step within 0.35 m of the goal)
             cfg5 = {"workload": "configs[4]: closed-loop LIP rollout, 1 M scenarios x 50 steps, warm-started re-planning, sharded by batch slice",
                     "scenarios": B5, "steps": S5, "seed": CONFIG5["seed"], "field_pool": CONFIG5["n_fields"], "scaling": "strong",
                     "scenarios_per_gpu": (B5 + world - 1) // world, "solves": int(solves5), "rollout_ms": roll_ms,
