@@ -94,6 +94,9 @@ DCBF_CE int THI(int l) { return 6 + l; }
 #ifndef DCBF_MU_MAX
 #define DCBF_MU_MAX 0.1
 #endif
+#ifndef DCBF_SIGMA_MIN
+#define DCBF_SIGMA_MIN 0.0
+#endif
 #ifndef DCBF_ADAPT_FIRST
 #define DCBF_ADAPT_FIRST 0
 #endif
@@ -1358,7 +1361,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
                 const double err = dinf / sd + A.theta + A.csum / (sc * nzd);
                 const double xi = A.cmin / avg;
                 const double q = dmin(0.05 * (1.0 - xi) / xi, 2.0);
-                const double mu_loqo = dmax(mu_min, dmin(0.1 * q * q * q * avg, DCBF_MU_MAX));
+                const double mu_loqo = dmax(mu_min, dmin(dmax(0.1 * q * q * q, DCBF_SIGMA_MIN) * avg, DCBF_MU_MAX));
                 if (S.free_mode) {
                     double refmax = 0.0;
                     for (int i = 0; i < S.nref; i++) refmax = dmax(refmax, S.kref[i]);

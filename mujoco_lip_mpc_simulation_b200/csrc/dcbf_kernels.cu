@@ -57,6 +57,7 @@ struct dcbf_ctx {
     int sched_min_batch;              // smallest batch that is ordered (env DCBF_ORDER; 0 = never)
     int sched_select;                 // order obstacle-selecting formulations too (env DCBF_ORDER_SELECT)
     int zero_copy;                    // dcbf_solve_host reads / writes page-locked caller buffers from the kernels (env DCBF_ZEROCOPY)
+    int dd_generic;                   // differential drive: keep the generic two-slot kernel (env DCBF_DD_GENERIC=1; A/B comparisons and tests)
 };
 
 #define CK(call)                                                                                        \
@@ -302,13 +303,13 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
 }
 
 // differential-drive formulation, one problem per warp (wp::DdW): same driver, 6 variables, node Jacobians per iterate
-template <int NS>
-__global__ void __launch_bounds__(32 * wp::Wpc<wp::DdW, NS>::v, 12 / wp::Wpc<wp::DdW, NS>::v) solve_dd_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out, const int *__restrict__ order, int *counter) {
-    constexpr int W = wp::Wpc<wp::DdW, NS>::v;
+template <class M, int NS>
+__global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, 12 / wp::Wpc<M, NS>::v) solve_dd_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out, const int *__restrict__ order, int *counter) {
+    constexpr int W = wp::Wpc<M, NS>::v;
     const int lane = wp::lane_id(), wid = W > 1 ? wp::warp_in_cta() : 0;
-    wp::WarpShared<wp::DdW, NS> &sm = wp::g_sm<wp::DdW, NS>[wid];
+    wp::WarpShared<M, NS> &sm = wp::g_sm<M, NS>[wid];
     const wp::CtaShared &cs_ = wp::g_cs;
-    wp::stage_cta<wp::DdW, NS>(P, K, tab, lane, wid);
+    wp::stage_cta<M, NS>(P, K, tab, lane, wid);
     for (;;) {
         const int i_ = wp::next_problem(counter, lane);
         if (i_ >= B) break;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::DdW, NS>::v, 12 / wp::Wpc<wp:
         if (lane >= 16 && lane < 22) sm.zc[lane - 16] = in.warm[6 * (size_t)b + lane - 16];
         __syncwarp();
         wp::WState S;
-        wp::solve_warp<wp::DdW, NS>(in, b, lane, wid, 1, S);
+        wp::solve_warp<M, NS>(in, b, lane, wid, 1, S);
         // ---- outputs: plan re-roll of gen_dd_control (MPC_DD_sig_step.py:83-99) = the staged nodes of the final iterate ------
         if (lane < 9 && out.x_plan) out.x_plan[9 * (size_t)b + lane] = sm.nd.nodes[lane / 3 + 1][lane % 3];
         if (lane < 6 && out.u) out.u[6 * (size_t)b + lane] = sm.zc[lane];
@@ -651,15 +652,15 @@ static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const Solv
     return DCBF_OK;
 }
 
-template <int NS>
+template <class M, int NS>
 static int launch_solve_dd_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
     const int *order = nullptr;
     const int rc = schedule_order(ctx, B, in, st, &order);
     if (rc != DCBF_OK) return rc;
     int *counter = ctx->d_counter + 1;
     CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    const int grid = warp_grid<wp::DdW, NS>(ctx, B, 12 / wp::Wpc<wp::DdW, NS>::v);
-    solve_dd_warp_kernel<NS><<<grid, 32 * wp::Wpc<wp::DdW, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, counter);
+    const int grid = warp_grid<M, NS>(ctx, B, 12 / wp::Wpc<M, NS>::v);
+    solve_dd_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, counter);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -770,7 +771,8 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     { const char *sp = getenv("DCBF_SPLIT"); ctx->split_classes = sp ? atoi(sp) : 16384; }
     { const char *sp = getenv("DCBF_ORDER"); ctx->sched_min_batch = sp ? atoi(sp) : 2048; }
     { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }
-    { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }   // below ~1 problem per warp slot there is no tail to hide
+    { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }
+    { const char *sp = getenv("DCBF_DD_GENERIC"); ctx->dd_generic = sp ? atoi(sp) : 0; }   // below ~1 problem per warp slot there is no tail to hide
     if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
@@ -869,7 +871,11 @@ int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, c
     const bool dd = ctx->P.formulation == DCBF_DD;
     if (dd && use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);
-        const int rc = ns == 1 ? launch_solve_dd_warp<1>(ctx, B, in, out, st) : (ns == 2 ? launch_solve_dd_warp<2>(ctx, B, in, out, st) : launch_solve_dd_warp<4>(ctx, B, in, out, st));
+        // two slots and at most ten obstacles (3 K <= 32): the D-CBF rows fill slot 0, the twelve linear rows get slot 1 (wp::DdL)
+        const bool lin2 = ns == 2 && 3 * (ctx->Kc + ctx->Ke) <= 32 && !ctx->dd_generic;
+        const int rc = ns == 1 ? launch_solve_dd_warp<wp::DdW, 1>(ctx, B, in, out, st)
+                     : lin2    ? launch_solve_dd_warp<wp::DdL, 2>(ctx, B, in, out, st)
+                     : ns == 2 ? launch_solve_dd_warp<wp::DdW, 2>(ctx, B, in, out, st) : launch_solve_dd_warp<wp::DdW, 4>(ctx, B, in, out, st);
         if (rc != DCBF_OK) return rc;
     }
     else if (dd) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);

@@ -262,6 +262,9 @@ DCBF_HD void rollout_lip_lane(const dcbf_params &P, const Consts &K, const Batch
     for (int st = 0; st < steps; st++) {
         setup_problem(P, M.pb);                                          // goal shift / selection at the new state
         ipm_init(P, S);
+#ifdef DCBF_MU_WARM
+        if (st > 0) S.mu = DCBF_MU_WARM;
+#endif
         lip_z_from_u(K, M.pb.x0, u0, S.z);
         while (!ipm_iterate(K, P, M, S)) {}
         tot += S.iters;

@@ -33,12 +33,12 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int NSRC = 27;     // node quantities feeding the Lagrangian Hessian: 3 nodes x 8 entries, 3 leg multipliers
 constexpr int NHT = 6;       // terms per matrix entry in the Hessian table
 // flat layout of the assembled system: q1 q2 q3 (27) | pad | K (45, packed rows 0..8) | right-hand side (= packed row 9) | tail.
-// The tail lets all 32 lanes store "their" right-hand-side component without a lane test (only 0..8 are meaningful).
+// Slot N of the right-hand side is a dump: all 32 lanes store "their" component without a lane test (index min(lane, N)).
 constexpr int KQ_Q = 0;
 constexpr int KQ_K = 28;
 constexpr int KQ_RHS = KQ_K + 45;
-constexpr int KQ_LEN = KQ_RHS + 32;
-constexpr int LF_LEN = 56 + 32;   // factor rows 0..9, then one dump slot per lane for the branch-free stores
+constexpr int KQ_LEN = KQ_RHS + 12;   // right-hand side (N entries) + one dump slot (index N) for the lanes beyond N
+constexpr int LF_LEN = 56 + 8;    // factor rows 0..9, then eight dump slots for the branch-free stores (lane & 7)
 
 // Host-built constant tables, one copy per context in device memory (build_warp_tables()).
 struct WarpTables {
@@ -48,6 +48,8 @@ struct WarpTables {
     double cab[10][6];        // (cA[3], cB[3]) per row class: CBF step 0..2, velocity rows step 0..2, leg step 0..2, turn
     int desc_dd[64];          // DD: 2 rounds x 32 lanes, same packing (21 matrix entries + 18 vector entries)
     double sm_dd[24];         // DD: constant Hessian pattern of the control-smoothness cost (per unit 2 w_t)
+    int desc_lin[64];         // DD, linear rows in their own slot (DdL): closed-form contribution of the four linear rows of a step to the
+                              // lane's entry: flags (bits 0..4, see DdWT::lin_term) | source row << 8 | first column << 16
 };
 
 // variable order (fx0, fy0, fx1, fy1, fx2, fy2, t0, t1, t2): step of a variable
@@ -146,6 +148,26 @@ inline bool build_warp_tables(const Consts &k, WarpTables &W) {
         }
         if (n != 39) return false;
         for (int t = 0; t < 64; t++) W.desc_dd[t] = t < 39 ? (ent[t].rowP | ent[t].rowQ << 8 | ent[t].cls << 16 | ent[t].out << 20) : -1;
+        // linear rows of step i (fen+: v + s w, fen-: v - s w, bound v, bound w) sit in columns 32 + 4 i .. 32 + 4 i + 3 of the staged
+        // weights; with x_j the weight of row j:  (v, v): x1 + x2 + x3,  (w, v): s (x1 - x2),  (w, w): s^2 (x1 + x2) + x4  -- matrix entries
+        // take sigma (staged row 2 N), the vector entries of variable v_i / w_i take  x1 + x2 + x3  /  s (x1 - x2) + x4  of their weight row
+        for (int t = 0; t < 64; t++) {
+            int flags = 0, src = 0, col = 32;
+            if (t < 39) {
+                if (ent[t].rowP < 12) {       // matrix entry (a, b)
+                    const int a = ent[t].rowP - 6, b = ent[t].rowQ;
+                    if ((a >> 1) == (b >> 1)) {
+                        flags = (a & 1) == 0 ? (1 | 4) : ((b & 1) == 0 ? 2 : (16 | 8));
+                        src = 12; col = 32 + 4 * (a >> 1);
+                    }
+                } else {                      // vector entry: weight row 13 + v, variable a
+                    const int a = ent[t].rowQ;
+                    flags = (a & 1) == 0 ? (1 | 4) : (2 | 8);
+                    src = ent[t].rowP; col = 32 + 4 * (a >> 1);
+                }
+            }
+            W.desc_lin[t] = flags | src << 8 | col << 16;
+        }
         // t sum_i |u_i - u_{i-1}|^2  (MPC_DD_sig_step.py:351-369): Hessian 2 t * [[2,-1,0],[-1,2,-1],[0,-1,1]] on v and on w
         for (int e = 0; e < 24; e++) W.sm_dd[e] = 0.0;
         static const double D3[3][3] = {{2, -1, 0}, {-1, 2, -1}, {0, -1, 1}};
@@ -180,6 +202,7 @@ struct DdNodeData {
     double Q[4][3], Cc[4][2];    // sum of y * Q_r and y * grad h over the rows that touch node k
     double cvw[3], cww[3];   // curvature coefficients of the positions (see dd_add_second() in dcbf_core.cuh)
     double last_u[2];
+    double sm_dd[24];        // constant Hessian pattern of the control-smoothness cost (copy of WarpTables::sm_dd)
 };
 
 template <class M, int NS>
@@ -188,11 +211,12 @@ struct alignas(16) WarpShared {
     static constexpr int RP = 32 * NS + 2;   // padded row length: class starts / ends are rounded to even rows
     static constexpr int NST = 2 * N + 4;
     double ST[NST][RP];      // staged rows, transposed: [0, N) gradient, [N, 2N) sigma * gradient, then sigma, w1, binv, y
-    double HQ[32 * NS][M::NHQ];   // y * (second-order / first-order row coefficients) of the D-CBF rows
+    double HQ[M::LIN2 ? 32 : 32 * NS][M::NHQ];   // y * (second-order / first-order row coefficients) of the D-CBF rows
     double obs[KsMax<NS>::v][6];  // selected obstacles: cx, cy, a', b', c', rhs
     double KQ[KQ_LEN];       // assembled system (see KQ_*)
     double Lf[LF_LEN];       // Cholesky factor (packed rows 0..N-1), the forward-substituted right-hand side (row N), dump slots
-    double dz[32], zc[32], zt[32];   // N meaningful entries each; all lanes store
+    double dz[32];           // N meaningful entries; all lanes store (also the staging buffer of the problem's 22 input values)
+    double zc[16], zt[16];   // N meaningful entries; lanes >= N store lane N-1's value into slot N-1 (index ln)
     double x0[5], goal[2], graw[2];
     // row state (slack, multipliers, step) of the kernels with more than one row per lane: the slot loop stays rolled there
     // (half the code, a third fewer registers); the single-slot kernel keeps it in registers
@@ -210,7 +234,6 @@ struct CtaShared {
     double cab[10][6];
     double hc[NHT][48];          // copy of the Hessian table (global loads in the assembly loop cost a long-scoreboard stall each)
     unsigned char hs[NHT][48];
-    double sm_dd[24];
     const WarpTables *tab;
 };
 
@@ -226,9 +249,12 @@ struct CtaShared {
 #define DCBF_WPC_DD(NS) ((NS) == 2 ? 2 : 1)
 #endif
 struct LipW;
-struct DdW;
+template <bool LIN> struct DdWT;
+using DdW = DdWT<false>;   // differential drive, generic row slots
+using DdL = DdWT<true>;    // differential drive, at most 10 obstacles: D-CBF rows in slot 0, the twelve linear rows in slot 1
 template <class M, int NS> struct Wpc { static constexpr int v = DCBF_WPC_LIP(NS); };
 template <int NS> struct Wpc<DdW, NS> { static constexpr int v = DCBF_WPC_DD(NS); };
+template <int NS> struct Wpc<DdL, NS> { static constexpr int v = 1; };
 
 // per-problem scratch (one per warp) and the constants are static shared-memory objects, so every function sees them as
 // shared-space symbols (no generic pointers through the out-of-line calls)
@@ -352,6 +378,7 @@ struct LipW {
     static constexpr int NROUND = 3;
     static constexpr bool HAS_CURV = false;
     static constexpr bool ROLL2 = false;   // two-slot kernel: unrolled slot loop, row state in registers (measured faster for modi)
+    static constexpr bool LIN2 = false;
     using NodeData = LipNodeData;
     enum { RT_NONE = 0, RT_CBF, RT_VBX, RT_VBY, RT_LEG, RT_DTH, RT_FENP, RT_FENM };
 
@@ -608,12 +635,15 @@ struct LipW {
 // ===============================================================================================================
 // DD model (MPC_DD_sig_step.py): z = (v0, w0, v1, w1, v2, w2), x+ = x + dt v cos th, y+ = y + dt v sin th, th+ = th + w
 // ===============================================================================================================
-struct DdW {
+template <bool LIN>
+struct DdWT {
+    using Self = DdWT<LIN>;
     static constexpr int N = 6;
     static constexpr int NHQ = 7;   // y * (2a', b', 2c', h1x, h1y, h0x, h0y)
     static constexpr int NROUND = 2;
     static constexpr bool HAS_CURV = true;
-    static constexpr bool ROLL2 = true;    // two-slot kernel: rolled slot loop, row state in shared memory (measured faster for DD)
+    static constexpr bool ROLL2 = !LIN;    // generic two-slot kernel: rolled slot loop, row state in shared memory (measured faster for DD)
+    static constexpr bool LIN2 = LIN;      // slot 1 holds the linear rows only (unrolled slots, closed-form contributions, 32-column dot products)
     using NodeData = DdNodeData;
     enum { RT_NONE = 0, RT_CBF, RT_FENP, RT_FENM, RT_BV, RT_BW };
 
@@ -622,16 +652,16 @@ struct DdW {
     static __device__ __forceinline__ int class_start(int cls, int Ks, int) { return cls * Ks; }
 
     template <int NS>
-    static __device__ __forceinline__ int setup(WarpShared<DdW, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane, unsigned *mask_out = nullptr) {
+    static __device__ __forceinline__ int setup(WarpShared<Self, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane, unsigned *mask_out = nullptr) {
         double rec[6];
         bool sel, is_c;
-        const int Ks = stage_obstacles<DdW, NS>(P, sm, in, b, lane, sm.x0[0], sm.x0[1], rec, sel, is_c, mask_out);
+        const int Ks = stage_obstacles<Self, NS>(P, sm, in, b, lane, sm.x0[0], sm.x0[1], rec, sel, is_c, mask_out);
         if (lane == 0) { sm.goal[0] = sm.graw[0]; sm.goal[1] = sm.graw[1]; }   // no detour heuristic (MPC_DD_sig_step.py:144-168 is commented out)
         if (lane < 3) sm.nd.nodes[0][lane] = sm.x0[lane];
         if (lane < 6) { sm.nd.Jx[0][lane] = 0.0; sm.nd.Jy[0][lane] = 0.0; }
         {   // the columns of linear and of unused rows keep their zeros for the whole solve (see stage_row)
             double *st = &sm.ST[0][0];
-            for (int t = lane; t < WarpShared<DdW, NS>::NST * WarpShared<DdW, NS>::RP; t += 32) st[t] = 0.0;
+            for (int t = lane; t < WarpShared<Self, NS>::NST * WarpShared<Self, NS>::RP; t += 32) st[t] = 0.0;
         }
         __syncwarp();
         return Ks;
@@ -644,10 +674,31 @@ struct DdW {
     static __device__ __forceinline__ RowDesc row_desc(int r, int Ks, int, int m) {
         RowDesc d;
         d.type = RT_NONE; d.step = 0; d.obs = 0; d.cls = 0;
+        if (LIN) {   // D-CBF rows 0 .. 3 Ks - 1 (Ks <= 10) in slot 0, linear row w of step i at 32 + 4 i + w
+            if (r < 32) { if (r < 3 * Ks) { d.type = RT_CBF; d.step = r / Ks; d.obs = r - d.step * Ks; } }
+            else if (r < 44) { const int w = r - 32; d.step = w >> 2; d.type = RT_FENP + (w & 3); }
+            return d;
+        }
         if (r >= m) return d;
         if (r < 3 * Ks) { d.type = RT_CBF; d.step = r / Ks; d.obs = r - d.step * Ks; }
         else { const int w = r - 3 * Ks; d.step = w >> 2; d.type = RT_FENP + (w & 3); }
         return d;
+    }
+    // a linear row (value of the linear form cv * z_v + cw * z_w of its step; the direction pass calls it on dz)
+    static __device__ __forceinline__ double eval_lin(const dcbf_params &P, const RowDesc &rd, const double *z) {
+        const int i = rd.step;
+        const double cv = (rd.type == RT_BW || rd.type == RT_NONE) ? 0.0 : 1.0;
+        const double cw = rd.type == RT_FENP ? P.s_turn : (rd.type == RT_FENM ? -P.s_turn : (rd.type == RT_BW ? 1.0 : 0.0));
+        return cv * z[2 * i] + cw * z[2 * i + 1];
+    }
+    // closed-form contribution of the linear rows to the lane's entry of the assembled system (descriptor: WarpTables::desc_lin)
+    template <int NS>
+    static __device__ __forceinline__ double lin_term(const WarpShared<Self, NS> &sm, const dcbf_params &P, int dl) {
+        constexpr int RP = WarpShared<Self, NS>::RP;
+        const double *px = &sm.ST[0][0] + ((dl >> 8) & 0xff) * RP + (dl >> 16);
+        const double2 xa = *reinterpret_cast<const double2 *>(px), xb = *reinterpret_cast<const double2 *>(px + 2);
+        const double s1 = xa.x + xa.y, s2 = xa.x - xa.y, st = P.s_turn;
+        return ((dl & 1) ? s1 : 0.0) + ((dl & 2) ? st * s2 : 0.0) + ((dl & 4) ? xb.x : 0.0) + ((dl & 8) ? xb.y : 0.0) + ((dl & 16) ? st * st * s1 : 0.0);
     }
     // MPC_DD_sig_step.py:127-141 (variable bounds as rows; split form of the coupling row)
     static __device__ __forceinline__ RowBnd row_bounds(const dcbf_params &P, const RowDesc &rd, int) {
@@ -661,7 +712,7 @@ struct DdW {
     }
 
     template <int NS, bool GRAD>
-    static __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<DdW, NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
+    static __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<Self, NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
         e.c = 0.0;
         if (GRAD) { e.p0 = e.p1 = e.q0 = e.q1 = e.t_all = e.t_own = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0; }
         const int i = rd.step;
@@ -679,8 +730,8 @@ struct DdW {
     // D-CBF rows: chain rule through the node Jacobians.  Linear rows: the gradient is (t_all, t_own) on (v_i, w_i); the other
     // entries of their columns were zeroed once per problem (setup) and nobody else writes them.
     template <int NS>
-    static __device__ __forceinline__ void stage_row(WarpShared<DdW, NS> &sm, const CtaShared &, const RowDesc &rd, const RowEval &e, double sig, double y, int r) {
-        constexpr int RP = WarpShared<DdW, NS>::RP;
+    static __device__ __forceinline__ void stage_row(WarpShared<Self, NS> &sm, const CtaShared &, const RowDesc &rd, const RowEval &e, double sig, double y, int r) {
+        constexpr int RP = WarpShared<Self, NS>::RP;
         const int i = rd.step, kn = i + 1;
         double *col = &sm.ST[0][r];
         if (rd.type == RT_CBF) {
@@ -701,7 +752,7 @@ struct DdW {
     // headings and their sines / cosines (lanes 0..2 = th_0..2), then nodes 1..3 with their Jacobians and objective terms
     template <int NS>
     static __device__ __noinline__ void nodes(const double *z, int lane, int wid, double sf, bool want_hess) {
-        WarpShared<DdW, NS> &sm = g_sm<DdW, NS>[wid];
+        WarpShared<Self, NS> &sm = g_sm<Self, NS>[wid];
         const dcbf_params &P = g_cs.P;
         const double dt = g_cs.K.dt;
         if (lane < 3) {
@@ -755,11 +806,11 @@ struct DdW {
     }
 
     template <int NS>
-    static __device__ __forceinline__ double objective(const WarpShared<DdW, NS> &sm) {
+    static __device__ __forceinline__ double objective(const WarpShared<Self, NS> &sm) {
         return sm.nd.nobj[0][0] + sm.nd.nobj[1][0] + sm.nd.nobj[2][0] + sm.nd.nobj[3][0];
     }
     template <int NS>
-    static __device__ __forceinline__ double grad(const WarpShared<DdW, NS> &sm, const CtaShared &, int lane, int ln) {
+    static __device__ __forceinline__ double grad(const WarpShared<Self, NS> &sm, const CtaShared &, int lane, int ln) {
         const int a = ln < 6 ? ln : 5;
         double g = sm.nd.gsm[a];
 #pragma unroll
@@ -770,7 +821,7 @@ struct DdW {
         return lane < 6 ? g : 0.0;
     }
     template <int NS>
-    static __device__ __forceinline__ void rescale_objective_hessian(WarpShared<DdW, NS> &sm, int lane, double sf) {
+    static __device__ __forceinline__ void rescale_objective_hessian(WarpShared<Self, NS> &sm, int lane, double sf) {
         if (lane < 3) {
 #pragma unroll
             for (int c = 4; c < 10; c++) sm.nd.nobj[lane + 1][c] *= sf;
@@ -780,7 +831,7 @@ struct DdW {
     // per-node second-order sources: Q_k = sum y Q_r (+ objective), C_k = sum y grad h (+ sf * objective gradient), and the
     // curvature coefficients of the positions (dd_add_second() in dcbf_core.cuh)
     template <int NS>
-    static __device__ __forceinline__ void hess_sources(WarpShared<DdW, NS> &sm, const dcbf_params &P, int lane, int Ks, int ms) {
+    static __device__ __forceinline__ void hess_sources(WarpShared<Self, NS> &sm, const dcbf_params &P, int lane, int Ks, int ms) {
         const double gm1 = P.gamma - 1.0;
         const int lp = lane - 16;
         if ((unsigned)lp < 15u) {   // lanes 16..30: node kn = lp / 5 + 1, component c = lp % 5  (qxx, qxy, qyy, cx, cy)
@@ -798,7 +849,7 @@ struct DdW {
         }
     }
     template <int NS>
-    static __device__ __forceinline__ void hess_curvature(WarpShared<DdW, NS> &sm, int lane, double sf, const double *z) {
+    static __device__ __forceinline__ void hess_curvature(WarpShared<Self, NS> &sm, int lane, double sf, const double *z) {
         if (lane >= 1 && lane < 3) {   // l = 1, 2
             const int l = lane;
             const double dt = g_cs.K.dt;
@@ -812,11 +863,11 @@ struct DdW {
     // Lagrangian Hessian of matrix entry e = tri(a, b), a >= b
     static __host__ __device__ constexpr int round_terms(int) { return 1; }
     template <int NS>
-    static __device__ __forceinline__ double hess_entry(const WarpShared<DdW, NS> &sm, const CtaShared &cs_, int e, double sf, int) {
+    static __device__ __forceinline__ double hess_entry(const WarpShared<Self, NS> &sm, const CtaShared &cs_, int e, double sf, int) {
         int a = 0;
         while ((a + 1) * (a + 2) / 2 <= e) a++;
         const int b = e - a * (a + 1) / 2;
-        double acc = 2.0 * cs_.P.w_t * sf * cs_.sm_dd[e];
+        double acc = 2.0 * cs_.P.w_t * sf * sm.nd.sm_dd[e];
 #pragma unroll
         for (int kn = 1; kn <= 3; kn++) {
             const double jxa = sm.nd.Jx[kn][a], jya = sm.nd.Jy[kn][a], jxb = sm.nd.Jx[kn][b], jyb = sm.nd.Jy[kn][b];
@@ -902,6 +953,8 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
     // kernels: descriptor and bounds are recomputed per slot (a few integer instructions) and the state sits in sm.RS.
     constexpr bool ROLLED = Sh::ROLLED;
     constexpr int NREG = ROLLED ? 1 : NS, UNR = ROLLED ? 1 : NS;
+    constexpr int DOTC = M::LIN2 ? 32 : 32 * NS;   // columns the dot products sweep (LIN2: the linear rows of slot 1 enter in closed form)
+    static_assert(!M::LIN2 || (NS == 2 && !ROLLED), "the linear-row slot belongs to the unrolled two-slot kernel");
     RowDesc rdA[NREG];
     RowBnd rbA[NREG];
     double rsA[NREG], rzlA[NREG], rzuA[NREG], rdsA[NREG], relA[NREG], reuA[NREG];
@@ -921,6 +974,9 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
     int dsc[M::NROUND];
 #pragma unroll
     for (int t = 0; t < M::NROUND; t++) dsc[t] = __ldg(M::desc(cs_.tab) + 32 * t + lane);
+    int dlin[M::NROUND];
+#pragma unroll
+    for (int t = 0; t < M::NROUND; t++) dlin[t] = M::LIN2 ? __ldg(cs_.tab->desc_lin + 32 * t + lane) : 0;
     const int ln = lane < N ? lane : N - 1;   // clamped lane: keeps the per-variable sections branch-free
     const int rowbase = lane < N + 1 ? lane * (lane + 1) / 2 : 0;
     // ---- solver state ------------------------------------------------------------------------------------------------
@@ -956,7 +1012,10 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         for (int s = 0; s < NS; s++) {
             DCBF_ROW_BEGIN
             RowEval e;
-            M::template eval_row<NS, true>(P, sm, rd, sm.zc, e);
+            bool lin = false;   // slot 1 of a LIN2 model: linear rows only (s is a constant after unrolling)
+            if constexpr (M::LIN2) lin = s == 1;
+            if (lin) { if constexpr (M::LIN2) e.c = M::eval_lin(P, rd, sm.zc); }
+            else M::template eval_row<NS, true>(P, sm, rd, sm.zc, e);
             double sig = 0.0, w1 = 0.0, binv = 0.0, y = 0.0;
             double t_rc = 0.0, t_cmin = 1e300, t_cmax = 0.0, t_z = 0.0, t_log = 0.0, t_v2 = 0.0, t_v = 0.0;
             if (rd.type != 0) {
@@ -1009,7 +1068,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 }
             }
             // stage the transposed row (rows beyond m stage zeros so that the dot products need no guards)
-            M::template stage_row<NS>(sm, cs_, rd, e, sig, y, r);
+            if (!lin) M::template stage_row<NS>(sm, cs_, rd, e, sig, y, r);   // linear rows: only the four weights below are staged
             {
                 double *col = &sm.ST[2 * N][r];
                 col[0] = sig; col[RP] = w1; col[2 * RP] = binv; col[3 * RP] = y;
@@ -1043,13 +1102,14 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 // fewer FMAs but twice the instructions -- remainder ladders, divergence bookkeeping, address decoding per block.
                 double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
-                for (int r = 0; r < 32 * NS; r += 4) {
+                for (int r = 0; r < DOTC; r += 4) {
                     const double2 u = *reinterpret_cast<const double2 *>(pp + r), v = *reinterpret_cast<const double2 *>(pq + r);
                     const double2 u2 = *reinterpret_cast<const double2 *>(pp + r + 2), v2 = *reinterpret_cast<const double2 *>(pq + r + 2);
                     acc0 = fma(u.x, v.x, acc0); acc1 = fma(u.y, v.y, acc1);
                     acc2 = fma(u2.x, v2.x, acc2); acc3 = fma(u2.y, v2.y, acc3);
                 }
                 double acc = (acc0 + acc1) + (acc2 + acc3);
+                if constexpr (M::LIN2) acc += M::template lin_term<NS>(sm, P, dlin[t]);
                 if (M::round_terms(t) > 0 && eo >= KQ_K) acc += M::template hess_entry<NS>(sm, cs_, eo - KQ_K, sf_eff, M::round_terms(t));   // Lagrangian Hessian
                 sm.KQ[eo] = acc;
             }
@@ -1106,7 +1166,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             if (S.iters >= P.max_iter) { S.status = -1; break; }
             rhs_a = -q[ln];
         }
-        sm.KQ[KQ_RHS_ + lane] = rhs_a;   // packed row N of the system (lanes >= N write the tail)
+        sm.KQ[KQ_RHS_ + (lane < N ? lane : N)] = rhs_a;   // packed row N of the system (lanes >= N write the dump slot)
         __syncwarp();
         // ---- restoration: Levenberg-Marquardt trials reuse the assembled K while lambda is escalated ---------------------------
         // ---- main phase: one factorisation with inertia correction by delta ----------------------------------------------------
@@ -1131,7 +1191,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                     if (!(d > 1e-14)) { ok = false; break; }
                     const double rinv = frsqrt(d);
                     Lrow[j] = lane == j ? rinv : s_ * rinv;   // diagonal stored as its reciprocal
-                    sm.Lf[act ? rowbase + j : 56 + lane] = Lrow[j];
+                    sm.Lf[act ? rowbase + j : 56 + (lane & 7)] = Lrow[j];
                     __syncwarp();
                 }
                 if (ok || resto) break;
@@ -1159,7 +1219,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             __syncwarp();
             if (!resto) break;
             // Levenberg-Marquardt trial at full step (violation only)
-            sm.zt[lane] = sm.zc[ln] + sm.dz[ln];
+            sm.zt[ln] = sm.zc[ln] + sm.dz[ln];
             __syncwarp();
             M::template nodes<NS>(sm.zt, lane, wid, 0.0, false);
             v2t = 0.0; vmt = 0.0;
@@ -1169,7 +1229,10 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 if (rd.type == 0) continue;
                 const RowBnd bb = ROLLED ? M::row_bounds(P, rd, leg) : rbA[ROLLED ? 0 : s];
                 RowEval e;
-                M::template eval_row<NS, false>(P, sm, rd, sm.zt, e);
+                bool lin = false;
+                if constexpr (M::LIN2) lin = s == 1;
+                if (lin) { if constexpr (M::LIN2) e.c = M::eval_lin(P, rd, sm.zt); }
+                else M::template eval_row<NS, false>(P, sm, rd, sm.zt, e);
                 double v = 0.0;
                 if (bb.has_lo && e.c < bb.lo) v = e.c - bb.lo;
                 if (bb.has_hi && e.c > bb.hi) v = e.c - bb.hi;
@@ -1187,7 +1250,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         if (resto) {
             if (lm_accept) {
                 const double dn = wmax(lane < N ? fabs(sm.dz[ln]) : 0.0);
-                sm.zc[lane] = sm.zt[lane];
+                sm.zc[ln] = sm.zt[ln];
                 S.iters++;
                 S.lm_lambda = fmax(S.lm_lambda * 0.2, 1e-12);
                 const double v2c = sm.cold[C_ST_V2];
@@ -1209,8 +1272,13 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 DCBF_ROW_BEGIN
                 if (rd.type == 0) continue;
                 double jd = 0.0;
+                bool lin = false;
+                if constexpr (M::LIN2) lin = s == 1;
+                if (lin) { if constexpr (M::LIN2) jd = M::eval_lin(P, rd, sm.dz); }
+                else {
 #pragma unroll
-                for (int a = 0; a < N; a++) jd = fma(sm.ST[a][r], sm.dz[a], jd);
+                    for (int a = 0; a < N; a++) jd = fma(sm.ST[a][r], sm.dz[a], jd);
+                }
                 const double d = jd + rds_;
                 rds_ = d;
                 // both sides in straight-line code (see the full pass); rel_ / reu_ hold the reciprocal gaps on entry
@@ -1239,7 +1307,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         double alpha = amax;
         int accepted = 0;
         for (int ls = 0; ls < DCBF_LS_MAX; ls++, alpha *= 0.5) {
-            sm.zt[lane] = fma(alpha, sm.dz[ln], sm.zc[ln]);
+            sm.zt[ln] = fma(alpha, sm.dz[ln], sm.zc[ln]);
             __syncwarp();
             M::template nodes<NS>(sm.zt, lane, wid, S.sf, true);
             const double ft = M::template objective<NS>(sm);
@@ -1252,7 +1320,10 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 const RowBnd bb = ROLLED ? M::row_bounds(P, rd, leg) : rbA[ROLLED ? 0 : s];
                 const double rs_ = ROLLED ? sm.RS[0][ROLLED ? r : 0] : rsA[ROLLED ? 0 : s], rds_ = ROLLED ? sm.RS[ROLLED ? 3 : 0][ROLLED ? r : 0] : rdsA[ROLLED ? 0 : s];
                 RowEval e;
-                M::template eval_row<NS, false>(P, sm, rd, sm.zt, e);
+                bool lin = false;
+                if constexpr (M::LIN2) lin = s == 1;
+                if (lin) { if constexpr (M::LIN2) e.c = M::eval_lin(P, rd, sm.zt); }
+                else M::template eval_row<NS, false>(P, sm, rd, sm.zt, e);
                 const double stv = rs_ + alpha * rds_;
                 th_t += fabs(e.c - stv);
                 const double gl = bb.has_lo ? stv - relax_lo(bb.lo) : 1.0, gh = bb.has_hi ? relax_hi(bb.hi) - stv : 1.0;
@@ -1289,7 +1360,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             S.iters++;
             continue;
         }
-        sm.zc[lane] = sm.zt[lane];
+        sm.zc[ln] = sm.zt[ln];
         __syncwarp();
         S.alpha = alpha; S.alpha_z = az; S.pending = true;
         nodes_valid = true; carry_ok = true;   // the accepted trial staged the nodes (with Hessian terms) and the barrier sum of the new point
@@ -1321,7 +1392,7 @@ __device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K,
     for (int t = t0; t < NHT * 48; t += 32 * W) (&g_cs.hc[0][0])[t] = __ldg(&tab->hc[0][0] + t);
     for (int t = t0; t < NHT * 48 / 4; t += 32 * W)
         reinterpret_cast<unsigned *>(&g_cs.hs[0][0])[t] = __ldg(reinterpret_cast<const unsigned *>(&tab->hs[0][0]) + t);
-    if (t0 < 24) g_cs.sm_dd[t0] = __ldg(&tab->sm_dd[t0]);
+    if constexpr (M::N == 6) { if (lane < 24) sm.nd.sm_dd[lane] = __ldg(&tab->sm_dd[lane]); }
     for (int t = lane; t < 2 * WarpShared<M, NS>::NST; t += 32) sm.ST[t >> 1][32 * NS + (t & 1)] = 0.0;
     __syncthreads();
 }
