@@ -71,12 +71,15 @@ typedef struct dcbf_params {
     int32_t goal_shift;  /* 1: 15-degree detour heuristic (MPC_LIP_sig_step.py:229-253) */
     int32_t has_fen;     /* 1: speed/turn coupling row s*|dtheta| + v (MPC_LIP_modi.py:493) */
     int32_t close_any;   /* 1: close_2_goal if any step is inside close_radius (sig_step), 0: first step only */
-    int32_t reserved0, reserved1;
+    int32_t tiny_count;  /* this many accepted steps in a row shorter than tiny_alpha, with rows still violated, send the iterate to the
+                            restoration phase (the fraction-to-boundary rule is pinning it: typical for infeasible problems) */
+    int32_t reserved1;
     double w_p, w_q, w_r, w_t;                                        /* cost weights p, q, r, t */
     double gamma, s_turn;                                             /* D-CBF decay, turn coupling */
     double bvx_min, bvx_max, bvy_min, bvy_max, leg_sq, ang_max;       /* row bounds */
     double detect_sq, close_radius;
     double tol, constr_viol_tol, mu_init;                             /* Ipopt: tol, constr_viol_tol, mu_init */
+    double tiny_alpha;                                                /* see tiny_count */
 } dcbf_params;
 
 typedef struct dcbf_ctx dcbf_ctx;

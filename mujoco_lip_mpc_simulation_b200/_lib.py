@@ -21,12 +21,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3",
 class DcbfParams(C.Structure):
     """ctypes mirror of `dcbf_params` (include/dcbf_mpc.h)."""
     _fields_ = [("formulation", C.c_int32), ("max_iter", C.c_int32), ("select_obs", C.c_int32), ("goal_shift", C.c_int32),
-                ("has_fen", C.c_int32), ("close_any", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+                ("has_fen", C.c_int32), ("close_any", C.c_int32), ("tiny_count", C.c_int32), ("reserved1", C.c_int32),
                 ("w_p", C.c_double), ("w_q", C.c_double), ("w_r", C.c_double), ("w_t", C.c_double),
                 ("gamma", C.c_double), ("s_turn", C.c_double),
                 ("bvx_min", C.c_double), ("bvx_max", C.c_double), ("bvy_min", C.c_double), ("bvy_max", C.c_double),
                 ("leg_sq", C.c_double), ("ang_max", C.c_double), ("detect_sq", C.c_double), ("close_radius", C.c_double),
-                ("tol", C.c_double), ("constr_viol_tol", C.c_double), ("mu_init", C.c_double)]
+                ("tol", C.c_double), ("constr_viol_tol", C.c_double), ("mu_init", C.c_double), ("tiny_alpha", C.c_double)]
 
 
 # every symbol include/dcbf_mpc.h declares

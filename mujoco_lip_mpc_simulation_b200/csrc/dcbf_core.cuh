@@ -1404,7 +1404,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             S.acc_cnt = 0;
         }
         if (S.iters >= P.max_iter) { S.status = -1; S.done = true; return true; }
-        if (S.tiny >= 3) {
+        if (S.tiny >= P.tiny_count) {
             // three consecutive accepted steps shorter than 1e-2 while the rows are still violated: the fraction-to-boundary
             // rule is pinning the iterate (typical for infeasible problems) -> go to restoration now instead of crawling
             S.tiny = 0;
@@ -1535,7 +1535,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
     DCBF_UNROLL
     for (int i = 0; i < N; i++) S.z[i] = fma(alpha, S.dz[i], S.z[i]);
     S.alpha = alpha; S.alpha_z = D.az; S.pending = true;
-    if (alpha < 1e-2 && A.vmax > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
+    if (alpha < P.tiny_alpha && A.vmax > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
     S.iters++;
     return false;
 }

@@ -725,6 +725,11 @@ int dcbf_default_params(int formulation, dcbf_params *P) {
     // MPC_DD_sig_step.py:183).  Those caps are not comparable with exact-Hessian Newton iterations; the default here
     // is a safety cap only (DESIGN.md "iteration caps").
     P->max_iter = 200;
+    // Early hand-over to the restoration phase.  LIP formulations: three accepted steps below 1e-2.  Differential drive, where 46 % of
+    // the config-4 scenarios are infeasible and crawl for ~10 such steps first: two below 5e-2 (mean iterations 14.8 -> 12.8 on
+    // config 4, class agreement with the oracle 99.97 %; the same setting costs the modi formulation 0.06 points, so it keeps 1e-2 / 3).
+    P->tiny_alpha = formulation == DCBF_DD ? 5e-2 : 1e-2;
+    P->tiny_count = formulation == DCBF_DD ? 2 : 3;
     if (formulation == DCBF_SIG_STEP) {
         P->w_p = 2.0; P->w_r = 15.0; P->gamma = 0.4; P->s_turn = 0.014 * 180.0 / PI; P->bvy_max = 0.3;
         P->goal_shift = 1; P->close_radius = 0.35; P->close_any = 1;

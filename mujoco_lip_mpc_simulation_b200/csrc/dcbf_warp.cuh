@@ -600,7 +600,7 @@ struct LipW {
     // this assembly round has (round 0 holds the entries among the variables of step 0: up to 6; round 1: 2; round 2 has vector
     // entries only) -- build_warp_tables() verifies the bound
     template <int NS>
-    static __device__ __forceinline__ double hess_entry(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int e, double sf, int terms) {
+    static __device__ __forceinline__ double hess_entry(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int e, double sf, int terms, int) {
         double acc = 0.0;
 #pragma unroll
         for (int h = 0; h < NHT; h++) if (h < terms) acc = fma(cs_.hc[h][e], sm.nd.NHf[cs_.hs[h][e]], acc);   // `terms` is a constant after unrolling
@@ -839,10 +839,21 @@ struct DdWT {
             // rows of step kn - 1 see node kn as their far end (Q_r, h1); rows of step kn see it as their near end (gm1 Q_r, h0)
             double acc = 0.0;
             const int cf = c, cn = c < 3 ? c : c + 2;   // HQ slots: far end 0..2 / 3..4, near end 0..2 (x gm1) / 5..6
-            for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * Ks + j][cf];
-            if (kn < 3) {
-                const double sc = c < 3 ? gm1 : 1.0;   // q0 / q1 already carry gm1
-                for (int j = 0; j < Ks; j++) acc = fma(sc, sm.HQ[kn * Ks + j][cn], acc);
+            if (LIN) {   // at most ten D-CBF rows per step: fixed trip count, rows beyond Ks masked (no loop bookkeeping)
+                const double sc = kn < 3 ? (c < 3 ? gm1 : 1.0) : 0.0;
+                const int r0 = (kn - 1) * Ks, r1 = kn < 3 ? kn * Ks : r0;
+#pragma unroll
+                for (int j = 0; j < 10; j++) {
+                    const int jj = j < Ks ? j : 0;
+                    const double a0 = sm.HQ[r0 + jj][cf], a1 = sm.HQ[r1 + jj][cn];
+                    acc += j < Ks ? fma(sc, a1, a0) : 0.0;
+                }
+            } else {
+                for (int j = 0; j < Ks; j++) acc += sm.HQ[(kn - 1) * Ks + j][cf];
+                if (kn < 3) {
+                    const double sc = c < 3 ? gm1 : 1.0;   // q0 / q1 already carry gm1
+                    for (int j = 0; j < Ks; j++) acc = fma(sc, sm.HQ[kn * Ks + j][cn], acc);
+                }
             }
             if (c < 3) sm.nd.Q[kn][c] = acc + sm.nd.nobj[kn][4 + c];
             else sm.nd.Cc[kn][c - 3] = acc;   // the objective part is added by the lanes below (needs sf)
@@ -863,10 +874,8 @@ struct DdWT {
     // Lagrangian Hessian of matrix entry e = tri(a, b), a >= b
     static __host__ __device__ constexpr int round_terms(int) { return 1; }
     template <int NS>
-    static __device__ __forceinline__ double hess_entry(const WarpShared<Self, NS> &sm, const CtaShared &cs_, int e, double sf, int) {
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= e) a++;
-        const int b = e - a * (a + 1) / 2;
+    static __device__ __forceinline__ double hess_entry(const WarpShared<Self, NS> &sm, const CtaShared &cs_, int e, double sf, int, int ab) {
+        const int a = ab & 0xff, b = ab >> 8;   // the entry's variables (a >= b), decoded from the descriptor once per problem
         double acc = 2.0 * cs_.P.w_t * sf * sm.nd.sm_dd[e];
 #pragma unroll
         for (int kn = 1; kn <= 3; kn++) {
@@ -974,6 +983,9 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
     int dsc[M::NROUND];
 #pragma unroll
     for (int t = 0; t < M::NROUND; t++) dsc[t] = __ldg(M::desc(cs_.tab) + 32 * t + lane);
+    int hab[M::NROUND];   // matrix entries: the pair of variables (a | b << 8) of the lane's entry (operand rows N + a and b)
+#pragma unroll
+    for (int t = 0; t < M::NROUND; t++) hab[t] = dsc[t] >= 0 ? (((dsc[t] & 0xff) - N) & 0xff) | (((dsc[t] >> 8) & 0xff) << 8) : 0;
     int dlin[M::NROUND];
 #pragma unroll
     for (int t = 0; t < M::NROUND; t++) dlin[t] = M::LIN2 ? __ldg(cs_.tab->desc_lin + 32 * t + lane) : 0;
@@ -1008,6 +1020,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         // ---- rows: evaluate, update row state, stage gradients and weights; statistics stay in registers ----------------------
         Stat8 st8;
         st8.s0 = st8.s1 = st8.s2 = st8.s3 = 0.0; st8.m0 = 0.0; st8.m1 = 1e300; st8.m2 = 0.0; st8.m3 = 0.0;
+        double gap_prod = 1.0;   // unrolled slots: product of the lane's gaps (each in (0, ~1e2]), one logarithm after the loop
 #pragma unroll UNR
         for (int s = 0; s < NS; s++) {
             DCBF_ROW_BEGIN
@@ -1061,7 +1074,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                     t_z = rzl_ + rzu_;
                     const double lp = gl * gh;
                     rel_ = il; reu_ = ih;
-                    if (!carry_ok) t_log = dlog(lp);
+                    if (!carry_ok) { if (ROLLED || NS == 1) t_log = dlog(lp); else gap_prod *= lp; }
                     rds_ = rc;
                     t_rc = fabs(rc);
                     w1 = sig * rc;
@@ -1077,6 +1090,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             st8.m0 = fmax(st8.m0, t_rc); st8.m1 = fmin(st8.m1, t_cmin); st8.m2 = fmax(st8.m2, t_cmax); st8.m3 = fmax(st8.m3, t_v);
             DCBF_ROW_END
         }
+        if (!ROLLED && NS > 1 && !resto && !carry_ok) st8.s2 = dlog(gap_prod);
         __syncwarp();   // the row branches reconverge here, before the shuffles
         reduce8_inline(st8, lane);
         const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? carry_log : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
@@ -1110,7 +1124,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 }
                 double acc = (acc0 + acc1) + (acc2 + acc3);
                 if constexpr (M::LIN2) acc += M::template lin_term<NS>(sm, P, dlin[t]);
-                if (M::round_terms(t) > 0 && eo >= KQ_K) acc += M::template hess_entry<NS>(sm, cs_, eo - KQ_K, sf_eff, M::round_terms(t));   // Lagrangian Hessian
+                if (M::round_terms(t) > 0 && eo >= KQ_K) acc += M::template hess_entry<NS>(sm, cs_, eo - KQ_K, sf_eff, M::round_terms(t), hab[t]);   // Lagrangian Hessian
                 sm.KQ[eo] = acc;
             }
         }
@@ -1143,7 +1157,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             if (E0 <= tol) { S.status = 0; break; }
             if (E0 <= 1e-6 && st_vmax <= P.constr_viol_tol) { if (++S.acc_cnt >= 15) { S.status = 1; break; } } else S.acc_cnt = 0;
             if (S.iters >= P.max_iter) { S.status = -1; break; }
-            if (S.tiny >= 3) {   // pinned by the fraction-to-boundary rule while still infeasible: restoration now (see ipm_iterate())
+            if (S.tiny >= P.tiny_count) {   // pinned by the fraction-to-boundary rule while still infeasible: restoration now (see ipm_iterate())
                 S.tiny = 0;
                 const int slot = S.nf < DCBF_FILT ? S.nf : (S.iters % DCBF_FILT);
                 if (lane == 0) { sm.filt_th[slot] = (1.0 - 1e-5) * st_theta; sm.filt_ph[slot] = (S.sf * fobj - S.mu * st_logsum) - 1e-5 * st_theta; }
@@ -1311,7 +1325,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             __syncwarp();
             M::template nodes<NS>(sm.zt, lane, wid, S.sf, true);
             const double ft = M::template objective<NS>(sm);
-            double th_t = 0.0, lg_t = 0.0;
+            double th_t = 0.0, lg_t = 0.0, gp_t = 1.0;
             bool okv = true;
 #pragma unroll UNR
             for (int s = 0; s < NS; s++) {
@@ -1328,8 +1342,9 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 th_t += fabs(e.c - stv);
                 const double gl = bb.has_lo ? stv - relax_lo(bb.lo) : 1.0, gh = bb.has_hi ? relax_hi(bb.hi) - stv : 1.0;
                 okv = okv && gl > 0.0 && gh > 0.0;
-                lg_t += dlog(gl * gh);
+                if (ROLLED || NS == 1) lg_t += dlog(gl * gh); else gp_t *= gl * gh;
             }
+            if (!ROLLED && NS > 1) lg_t = dlog(gp_t);   // (a trial with a non-positive gap is rejected by okv below, whatever this is)
             __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -1364,7 +1379,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         __syncwarp();
         S.alpha = alpha; S.alpha_z = az; S.pending = true;
         nodes_valid = true; carry_ok = true;   // the accepted trial staged the nodes (with Hessian terms) and the barrier sum of the new point
-        if (alpha < 1e-2 && sm.cold[C_ST_VMAX] > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
+        if (alpha < P.tiny_alpha && sm.cold[C_ST_VMAX] > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
         S.iters++;
     }
     // every exit leaves the loop right after a full pass (or before any trial), so the node data are the rollout of the final iterate
