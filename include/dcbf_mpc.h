@@ -22,6 +22,8 @@
  *   dcbf_alip_foot       <- the closed-form ALIP foot placement behind the DD re-plan (Logger.ALIP_gen_foot_input,
  *                           data_procs/logger_dd.py:356-363 -> ALIP.AMprediction / computeSw2CoM / computeStepping /
  *                           regulate_lateral_step / getTimedState, ALIP_plan/planner.py:188-261,346-370)
+ *   dcbf_veldes_foot     <- MPCCBF.alip_des_vel + MPCCBF.cal_foot_with_veldes (MPC_LIP_sig_step.py:168-181), the velocity-tracking
+ *                           foothold Logger.cal_foot_input places between re-plans (data_procs/logger.py:380-418)
  *   dcbf_heading_input   <- Logger.tube_func + Logger.avg_hd, the heading-rate input of that prediction
  *                           (data_procs/logger_mpc.py:208-215,278-300)
  *   dcbf_gen_fields /    <- rand_obs.gen_ran_obs_list (rand_obs.py:31-81) and the start state of the __main__ loop
@@ -170,6 +172,16 @@ int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo
 int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double *y_alip, const double *time, const int32_t *support,
                    const double *speed, int32_t speed_stride, double H, double T, double m, double W, double *foot, double *am,
                    double *next, void *stream);
+
+/* Velocity-tracking foot placement used between re-plans (LIP formulations; MPCCBF.alip_des_vel and MPCCBF.cal_foot_with_veldes,
+ * MPC_LIP_sig_step.py:168-181, called by Logger.cal_foot_input, data_procs/logger.py:380-418).  Per scenario:
+ *   vel_des = (sigma vx_max dt / 2, 0.5 (-0.5 leg step_gap) beta sinh(beta dt) / (cosh(beta dt) + 1)), sigma = beta coth(beta dt / 2)
+ *             -- or vel_des_in[B][2] when that is not NULL (then leg may be NULL);
+ *   foot    = B_vel^-1 (vel_des - (A x_state)[2:4]): the foothold after which the LIP step ends with velocity vel_des.
+ * x_state[B][5] (may be NULL if foot is NULL), leg[B] = leg_ind (+1 / -1), step_gap = 0.3 in the reference (MPC_LIP_sig_step.py:41).
+ * Outputs (any may be NULL): vel_des_out[B][2], foot[B][2]. */
+int dcbf_veldes_foot(dcbf_ctx *ctx, int32_t B, const double *x_state, const int32_t *leg, const double *vel_des_in, double vx_max,
+                     double step_gap, double *vel_des_out, double *foot, void *stream);
 
 /* Heading input of the LIP prediction, the per-tick tail of Logger.update_n_record (data_procs/logger_mpc.py:278-281):
  *   nex_turn <- tube_func(nex_turn, cur_hd)      the last plan's turn, scaled by 0.4 inside the +-0.15 rad tube and 0.7 outside

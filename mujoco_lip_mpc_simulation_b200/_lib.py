@@ -33,7 +33,7 @@ class DcbfParams(C.Structure):
 EXPORTS = ["dcbf_abi_version", "dcbf_default_params", "dcbf_create", "dcbf_destroy", "dcbf_last_error",
            "dcbf_set_fields", "dcbf_num_rows", "dcbf_num_vars", "dcbf_eval", "dcbf_solve", "dcbf_rollout",
            "dcbf_set_fields_host", "dcbf_solve_host", "dcbf_launch_count", "dcbf_fp64_peak_tflops", "dcbf_tick", "dcbf_alip_foot", "dcbf_math_probe",
-           "dcbf_gen_fields", "dcbf_gen_states", "dcbf_heading_input", "dcbf_setup_info"]
+           "dcbf_gen_fields", "dcbf_gen_states", "dcbf_heading_input", "dcbf_setup_info", "dcbf_veldes_foot"]
 
 
 def needs_build() -> bool:
@@ -94,6 +94,7 @@ def load():
     lib.dcbf_gen_states.argtypes = [vp, C.c_int32, C.c_uint64, vp] + [C.c_double] * 3 + [dp, dp, vp, dp, dp, vp, vp]
     lib.dcbf_heading_input.argtypes = [vp, C.c_int32, dp, dp, dp, C.c_int32, C.c_int32, dp, C.c_int32, vp]
     lib.dcbf_setup_info.argtypes = [vp, C.c_int32] + [dp] * 6 + [vp]
+    lib.dcbf_veldes_foot.argtypes = [vp, C.c_int32, dp, dp, dp, C.c_double, C.c_double, dp, dp, vp]
     lib.dcbf_launch_count.argtypes = [vp]
     lib.dcbf_launch_count.restype = C.c_int64
     lib.dcbf_fp64_peak_tflops.argtypes = [vp, C.c_int32]

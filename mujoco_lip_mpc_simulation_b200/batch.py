@@ -279,6 +279,24 @@ class DcbfSolver:
         self._check(rc, "dcbf_alip_foot")
         return dict(foot=foot, am=am, next=nxt)
 
+    def veldes_foot(self, x_state=None, leg=None, vel_des=None, vx_max=0.6, step_gap=0.3):
+        """MPCCBF.alip_des_vel + MPCCBF.cal_foot_with_veldes for B scenarios on the device (dcbf_veldes_foot): the desired
+        end-of-step velocity for walking speed vx_max with stance sign leg (or vel_des as given) and the foothold that reaches it
+        from x_state [B,5].  Returns dict(vel_des[B,2], foot[B,2] | None)."""
+        assert not self.dd, "the velocity-tracking foothold belongs to the LIP formulations"
+        xs = None if x_state is None else self._dev(x_state, torch.float64).reshape(-1, 5)
+        lg = None if leg is None else self._dev(leg, torch.int32).reshape(-1)
+        vd = None if vel_des is None else self._dev(vel_des, torch.float64).reshape(-1, 2)
+        B = next(t.shape[0] for t in (xs, vd, lg) if t is not None)
+        if lg is not None and lg.shape[0] != B:
+            lg = lg.expand(B).contiguous()
+        out_v = torch.empty((B, 2), dtype=torch.float64, device=self.tdev)
+        foot = None if xs is None else torch.empty((B, 2), dtype=torch.float64, device=self.tdev)
+        rc = self.lib.dcbf_veldes_foot(self._ctx, B, _ptr(xs), _ptr(lg), _ptr(vd), float(vx_max), float(step_gap), _ptr(out_v), _ptr(foot),
+                                       self._stream())
+        self._check(rc, "dcbf_veldes_foot")
+        return dict(vel_des=out_v, foot=foot)
+
     def heading_input(self, cur_hd, nex_turn, x_plan=None, mpc_hds=None, glo_p=None):
         """Logger.tube_func + Logger.avg_hd for B scenarios (dcbf_heading_input).  nex_turn [B] (device tensor) is updated in
         place.  The plan headings come from x_plan [B,3,5] (a dcbf_tick / solve output, read in place) or mpc_hds [B,3]; the

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
         const int i_ = wp::next_problem(counter, lane);
         if (i_ >= n) break;
         const int b = order ? order[i_] : i_;
+        DCBF_ASSERT(b >= 0 && b < B);
         // the 22 input values arrive in three coalesced requests (the buffers may be mapped host memory: dcbf_solve_host)
         sm.dz[lane] = lane < 5 ? in.x0[5 * (size_t)b + lane] : (lane < 20 ? in.warm[15 * (size_t)b + lane - 5] : (lane < 22 ? in.goal[2 * (size_t)b + lane - 20] : 0.0));
         __syncwarp();
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, 12 / wp::Wpc<M, NS>::v
         const int i_ = wp::next_problem(counter, lane);
         if (i_ >= B) break;
         const int b = order ? order[i_] : i_;
+        DCBF_ASSERT(b >= 0 && b < B);
         if (lane < 3) sm.x0[lane] = in.x0[3 * (size_t)b + lane];
         if (lane >= 8 && lane < 10) { sm.graw[lane - 8] = in.goal[2 * (size_t)b + lane - 8]; sm.nd.last_u[lane - 8] = in.last_u ? in.last_u[2 * (size_t)b + lane - 8] : 0.0; }
         if (lane >= 16 && lane < 22) sm.zc[lane - 16] = in.warm[6 * (size_t)b + lane - 16];
@@ -581,6 +583,31 @@ __global__ void alip_foot_kernel(int B, const double *__restrict__ xa, const dou
     if (next) {   // getTimedState over the rest of the step
         next[4 * (size_t)b + 0] = ch * px + sh / mhl * Ly; next[4 * (size_t)b + 1] = mhl * sh * px + ch * Ly;
         next[4 * (size_t)b + 2] = ch * py - sh / mhl * Lx; next[4 * (size_t)b + 3] = -mhl * sh * py + ch * Lx;
+    }
+}
+
+// Velocity-tracking foot placement between re-plans (MPCCBF.alip_des_vel + MPCCBF.cal_foot_with_veldes, MPC_LIP_sig_step.py:168-181;
+// caller Logger.cal_foot_input, data_procs/logger.py:380-418), one thread per scenario:
+//   v_des  = (sigma vx_max dt / 2,  0.5 (-0.5 leg step_gap) beta sinh(beta dt) / (cosh(beta dt) + 1))        unless given
+//   foot   = B_vel^-1 (v_des - (A x)[2:4]),  B_vel = -beta sinh(beta dt) I   (the foothold that makes the next step end at v_des)
+__global__ void veldes_foot_kernel(int B, Consts K, double sigma, double step_gap, double vx_max, const double *__restrict__ x_state,
+                                   const int32_t *__restrict__ leg, const double *__restrict__ vel_des_in, double *__restrict__ vel_des_out,
+                                   double *__restrict__ foot) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double vd0, vd1;
+    if (vel_des_in) { vd0 = vel_des_in[2 * (size_t)b]; vd1 = vel_des_in[2 * (size_t)b + 1]; }
+    else {
+        const double bt = sqrt(K.bS / K.Sb);   // beta: bS = beta sinh(beta dt), Sb = sinh(beta dt) / beta
+        vd0 = sigma * vx_max * K.dt / 2.0;
+        vd1 = 0.5 * (-0.5 * (double)(leg ? leg[b] : 1) * step_gap) * (bt * sinh(bt * K.dt)) / (cosh(bt * K.dt) + 1.0);
+    }
+    if (vel_des_out) { vel_des_out[2 * (size_t)b] = vd0; vel_des_out[2 * (size_t)b + 1] = vd1; }
+    if (foot && x_state) {
+        const double *x = x_state + 5 * (size_t)b;
+        const double ax2 = K.bS * x[0] + K.C * x[2], ax3 = K.bS * x[1] + K.C * x[3];     // (A x)[2:4]
+        foot[2 * (size_t)b] = (vd0 - ax2) / (-K.bS);
+        foot[2 * (size_t)b + 1] = (vd1 - ax3) / (-K.bS);
     }
 }
 
@@ -977,6 +1004,19 @@ int dcbf_alip_foot(dcbf_ctx *ctx, int32_t B, const double *x_alip, const double 
     if (!x_alip || !y_alip || !time || !support || !speed || speed_stride < 1 || !(H > 0.0) || !(T > 0.0) || !(m > 0.0)) return DCBF_ERR_ARG;
     ENTER(stream);
     alip_foot_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, x_alip, y_alip, time, support, speed, speed_stride, H, T, m, W, foot, am, next);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return DCBF_OK;
+}
+
+int dcbf_veldes_foot(dcbf_ctx *ctx, int32_t B, const double *x_state, const int32_t *leg, const double *vel_des_in, double vx_max,
+                     double step_gap, double *vel_des_out, double *foot, void *stream) {
+    if (!ctx || B < 0) return DCBF_ERR_ARG;
+    if (B == 0) return DCBF_OK;
+    if (ctx->P.formulation == DCBF_DD || (foot && !x_state) || (!vel_des_in && !leg)) return DCBF_ERR_ARG;
+    ENTER(stream);
+    const double beta = sqrt(9.81 / 1.0), sigma = beta / tanh(ctx->K.dt * beta / 2.0);   // MPC_LIP_sig_step.py:44 (beta coth(beta dt / 2))
+    veldes_foot_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, ctx->K, sigma, step_gap, vx_max, x_state, leg, vel_des_in, vel_des_out, foot);
     CK(cudaGetLastError());
     ctx->launches++;
     return DCBF_OK;

@@ -179,6 +179,16 @@ inline bool build_warp_tables(const Consts &k, WarpTables &W) {
 
 #if defined(__CUDACC__)
 
+// Bounds-checked build (-DDCBF_BOUNDS=1, tools/sanitize_probe.py): every data-dependent index into the per-problem scratch is
+// asserted on the device (a violated assert traps the kernel and the entry point returns a CUDA error).  compute-sanitizer is
+// closed on the GPU pool (profiles/r03_sanitizer_refused.log), so this build is the memory check of the warp kernels.
+#if DCBF_BOUNDS
+#include <assert.h>
+#define DCBF_ASSERT(c) assert(c)
+#else
+#define DCBF_ASSERT(c) ((void)0)
+#endif
+
 template <int NS> struct KsMax { static constexpr int v = NS == 1 ? 6 : (NS == 2 ? 17 : 2 * DCBF_MAX_OBS); };
 
 // slots of WarpShared::cold.  Every lane stores the same value and nobody reads before the next __syncwarp(); none of these is
@@ -254,7 +264,10 @@ using DdW = DdWT<false>;   // differential drive, generic row slots
 using DdL = DdWT<true>;    // differential drive, at most 10 obstacles: D-CBF rows in slot 0, the twelve linear rows in slot 1
 template <class M, int NS> struct Wpc { static constexpr int v = DCBF_WPC_LIP(NS); };
 template <int NS> struct Wpc<DdW, NS> { static constexpr int v = DCBF_WPC_DD(NS); };
-template <int NS> struct Wpc<DdL, NS> { static constexpr int v = 1; };
+#ifndef DCBF_WPC_DDL
+#define DCBF_WPC_DDL 1
+#endif
+template <int NS> struct Wpc<DdL, NS> { static constexpr int v = DCBF_WPC_DDL; };
 
 // per-problem scratch (one per warp) and the constants are static shared-memory objects, so every function sees them as
 // shared-space symbols (no generic pointers through the out-of-line calls)
@@ -359,6 +372,7 @@ __device__ __forceinline__ int stage_obstacles(const dcbf_params &P, WarpShared<
     const unsigned mask = __ballot_sync(FULL, sel);
     if (sel) {
         const int pos = __popc(mask & ((1u << lane) - 1u));
+        DCBF_ASSERT(pos >= 0 && (size_t)fld * in.Kc + in.Kc <= (size_t)(in.F > 0 ? in.F : 1 << 30) * in.Kc);
         if (pos < KsMax<NS>::v) {
 #pragma unroll
             for (int c = 0; c < 6; c++) sm.obs[pos][c] = rec[c];
@@ -466,6 +480,7 @@ struct LipW {
         const int i = rd.step, kn = i + 1;
         const double (*nodes)[5] = sm.nd.nodes;
         if (rd.type == RT_CBF) {
+            DCBF_ASSERT(rd.obs >= 0 && rd.obs < KsMax<NS>::v && i >= 0 && i < 3);
             eval_cbf<GRAD>(sm.obs[rd.obs], P.gamma - 1.0, nodes[kn][0], nodes[kn][1], nodes[i][0], nodes[i][1], e);
         } else if (rd.type != RT_NONE) {
             // every other row is  al * v_bx + be * v_by + ga * turn_i + de * |pos_i - foot_i|^2  with coefficients of the row type
@@ -500,6 +515,7 @@ struct LipW {
             col[(2 * l) * RP] = gxv; col[(2 * l + 1) * RP] = gyv; col[(6 + l) * RP] = gtv;
             col[(9 + 2 * l) * RP] = sig * gxv; col[(9 + 2 * l + 1) * RP] = sig * gyv; col[(9 + 6 + l) * RP] = sig * gtv;
         }
+        DCBF_ASSERT(r >= 0 && r < (int)(sizeof(sm.HQ) / sizeof(sm.HQ[0])));
         sm.HQ[r][0] = y * e.hq0; sm.HQ[r][1] = y * e.hq1; sm.HQ[r][2] = y * e.hq2;
     }
 
@@ -603,7 +619,7 @@ struct LipW {
     static __device__ __forceinline__ double hess_entry(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int e, double sf, int terms, int) {
         double acc = 0.0;
 #pragma unroll
-        for (int h = 0; h < NHT; h++) if (h < terms) acc = fma(cs_.hc[h][e], sm.nd.NHf[cs_.hs[h][e]], acc);   // `terms` is a constant after unrolling
+        for (int h = 0; h < NHT; h++) if (h < terms) { DCBF_ASSERT(e >= 0 && e < 48 && cs_.hs[h][e] <= NSRC); acc = fma(cs_.hc[h][e], sm.nd.NHf[cs_.hs[h][e]], acc); }   // `terms` is a constant after unrolling
         return acc;
     }
     static __host__ __device__ constexpr int round_terms(int t) { return t == 0 ? 6 : (t == 1 ? 2 : 0); }
@@ -695,6 +711,7 @@ struct DdWT {
     template <int NS>
     static __device__ __forceinline__ double lin_term(const WarpShared<Self, NS> &sm, const dcbf_params &P, int dl) {
         constexpr int RP = WarpShared<Self, NS>::RP;
+        DCBF_ASSERT((((dl >> 8) & 0xff) < (WarpShared<Self, NS>::NST) && (dl >> 16) + 3 < RP && ((dl >> 16) & 1) == 0));
         const double *px = &sm.ST[0][0] + ((dl >> 8) & 0xff) * RP + (dl >> 16);
         const double2 xa = *reinterpret_cast<const double2 *>(px), xb = *reinterpret_cast<const double2 *>(px + 2);
         const double s1 = xa.x + xa.y, s2 = xa.x - xa.y, st = P.s_turn;
@@ -717,6 +734,7 @@ struct DdWT {
         if (GRAD) { e.p0 = e.p1 = e.q0 = e.q1 = e.t_all = e.t_own = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0; }
         const int i = rd.step;
         if (rd.type == RT_CBF) {
+            DCBF_ASSERT(rd.obs >= 0 && rd.obs < KsMax<NS>::v && i >= 0 && i < 3);
             eval_cbf<GRAD>(sm.obs[rd.obs], P.gamma - 1.0, sm.nd.nodes[i + 1][0], sm.nd.nodes[i + 1][1], sm.nd.nodes[i][0], sm.nd.nodes[i][1], e);
         } else if (rd.type != RT_NONE) {
             const double v = z[2 * i], w = z[2 * i + 1];
@@ -741,6 +759,7 @@ struct DdWT {
                 const double g = fma(e.p0, jx1[a], fma(e.p1, jy1[a], fma(e.q0, jx0[a], e.q1 * jy0[a])));
                 col[a * RP] = g; col[(6 + a) * RP] = sig * g;
             }
+            DCBF_ASSERT(r >= 0 && r < (int)(sizeof(sm.HQ) / sizeof(sm.HQ[0])));
             double *h = sm.HQ[r];
             h[0] = y * e.hq0; h[1] = y * e.hq1; h[2] = y * e.hq2; h[3] = y * e.p0; h[4] = y * e.p1; h[5] = y * e.q0; h[6] = y * e.q1;
         } else if (rd.type != RT_NONE) {
@@ -845,6 +864,7 @@ struct DdWT {
 #pragma unroll
                 for (int j = 0; j < 10; j++) {
                     const int jj = j < Ks ? j : 0;
+                    DCBF_ASSERT(r0 + jj >= 0 && r1 + jj < 32 && cf < NHQ && cn < NHQ);
                     const double a0 = sm.HQ[r0 + jj][cf], a1 = sm.HQ[r1 + jj][cn];
                     acc += j < Ks ? fma(sc, a1, a0) : 0.0;
                 }
@@ -1083,6 +1103,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             // stage the transposed row (rows beyond m stage zeros so that the dot products need no guards)
             if (!lin) M::template stage_row<NS>(sm, cs_, rd, e, sig, y, r);   // linear rows: only the four weights below are staged
             {
+                DCBF_ASSERT(r >= 0 && r < 32 * NS && Ks >= 0 && Ks <= KsMax<NS>::v && m <= 32 * NS + (M::LIN2 ? 32 : 0));
                 double *col = &sm.ST[2 * N][r];
                 col[0] = sig; col[RP] = w1; col[2 * RP] = binv; col[3 * RP] = y;
             }
@@ -1111,6 +1132,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             if (d >= 0) {
                 const double *pp = stf + (d & 0xff) * RP, *pq = stf + ((d >> 8) & 0xff) * RP;
                 const int eo = d >> 20;
+                DCBF_ASSERT((d & 0xff) < Sh::NST && ((d >> 8) & 0xff) < Sh::NST && eo >= 0 && eo < KQ_RHS_);
                 // Fixed trip count over the whole padded row range (rows beyond m and rows of earlier steps hold zeros): the loop
                 // unrolls completely.  A per-lane start row (rows of steps before the entry's class cannot contribute) executed
                 // fewer FMAs but twice the instructions -- remainder ladders, divergence bookkeeping, address decoding per block.

@@ -308,3 +308,25 @@ def test_tick_rate_closed_loop_stays_on_the_device():
     assert float((min_gap > -0.05).double().mean()) > 0.99
     assert float(((d1 < d0 - 2.0) | done).double().mean()) > 0.9  # walked at least 2 m towards the goal, or arrived
     assert float(done.double().mean()) > 0.3
+
+
+def test_veldes_foot_kernel_matches_reference_helpers():
+    """dcbf_veldes_foot = MPCCBF.alip_des_vel + MPCCBF.cal_foot_with_veldes (MPC_LIP_sig_step.py:168-181) against the values the
+    reference's own methods returned (tests/golden/helpers.npz), and against the host mirror on a batch"""
+    import os
+    H = np.load(os.path.join(os.path.dirname(__file__), "golden", "helpers.npz"))
+    s = DcbfSolver("sig_step", device=0)
+    a = s.veldes_foot(leg=[1], vx_max=0.7)["vel_des"].cpu().numpy()[0]
+    b = s.veldes_foot(leg=[-1], vx_max=0.5)["vel_des"].cpu().numpy()[0]
+    np.testing.assert_allclose([a, b], H["alip_des_vel"], rtol=0, atol=1e-14)
+    r = s.veldes_foot(x_state=H["cfv_in"][None, :5], vel_des=H["cfv_in"][None, 5:])
+    np.testing.assert_allclose(r["foot"].cpu().numpy()[0], H["cfv_out"], rtol=0, atol=1e-13)
+    from mujoco_lip_mpc_simulation_b200.MPC_LIP_sig_step import MPCCBF
+    rng = np.random.default_rng(3)
+    xs = rng.normal(size=(257, 5)); leg = rng.choice([-1, 1], size=257).astype(np.int32)
+    r = s.veldes_foot(x_state=xs, leg=leg, vx_max=0.6)
+    pl = MPCCBF([[10.0, 10.0]], [[1, 1, 0.5]], [[1, 1, 0.9]], [-0.5, 10.5])
+    for i in (0, 1, 100, 256):
+        vd = pl.alip_des_vel(0.6, int(leg[i]))
+        np.testing.assert_allclose(r["vel_des"][i].cpu().numpy(), vd, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(r["foot"][i].cpu().numpy(), pl.cal_foot_with_veldes(xs[i], vd), rtol=0, atol=1e-12)
