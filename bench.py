@@ -380,8 +380,27 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        extra["tick_modi_65536"] = {"ticks_per_s": 65536 / (best * 1e-3), "ms": best, "pos_det_bytes": int(tk["pos_det"].numel() * 8)}
-        del tk
+        extra["tick_modi_65536"] = {"ticks_per_s": 65536 / (best * 1e-3), "ms": best, "pos_det_bytes": int(tk["pos_det"].numel() * 8),
+                                    "mean_iters": float(tk["plan"].iters.float().mean())}
+        # the tick-rate workload of the reference (main_sim_mpc.py:85-88: 40 re-plans per step): the next tick, 10 ms later, from a state
+        # 5 mm / 2 cm/s away, warm-started from the plan above verbatim (mode 0 -> first barrier parameter mu_warm)
+        gen = torch.Generator(device=dev); gen.manual_seed(5)
+        pos2 = targs[0] + 0.005 * torch.randn(targs[0].shape, generator=gen, device=dev, dtype=torch.float64)
+        vel2 = targs[1] + 0.02 * torch.randn(targs[1].shape, generator=gen, device=dev, dtype=torch.float64)
+        prev, md0 = tk["plan"].x_plan.reshape(65536, 15).clone(), torch.zeros(65536, dtype=torch.uint8, device=dev)
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            e0.record()
+            tw = sv.tick(pos2, vel2, targs[2], targs[3], targs[4], t(s3.goal, torch.float64), t(s3.leg, torch.int32), prev_plan=prev, mode=md0,
+                         field=t(s3.field, torch.int32))
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        extra["tick_warm_modi_65536"] = {"ticks_per_s": 65536 / (best * 1e-3), "ms": best, "mean_iters": float(tw["plan"].iters.float().mean()),
+                                         "mu_warm": float(sv.P.mu_warm)}
+        del tk, tw
         # config 5 shape, one GPU's share at 8 GPUs: closed-loop rollout, 131072 scenarios x 50 steps, no host round trips
         s5 = scenarios.make_batch("sig_step", 131072, seed=SEED + 3)
         sv = DcbfSolver("sig_step", device=local)

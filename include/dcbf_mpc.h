@@ -82,6 +82,9 @@ typedef struct dcbf_params {
     double detect_sq, close_radius;
     double tol, constr_viol_tol, mu_init;                             /* Ipopt: tol, constr_viol_tol, mu_init */
     double tiny_alpha;                                                /* see tiny_count */
+    double mu_warm;   /* first barrier parameter of a re-plan warm-started from the previous plan verbatim (dcbf_tick mode 0) */
+    double mu_shift;  /* ... from the shifted plan [x_2, x_3, x_3] (dcbf_tick mode 1, dcbf_rollout after the first step), whose third
+                         step still violates the velocity rows; a cold start uses mu_init */
 } dcbf_params;
 
 typedef struct dcbf_ctx dcbf_ctx;

@@ -88,27 +88,6 @@ DCBF_CE int THI(int l) { return 6 + l; }
 #ifndef DCBF_KAPPA_EPS
 #define DCBF_KAPPA_EPS 10.0          /* Ipopt barrier_tol_factor */
 #endif
-#ifndef DCBF_ADAPTIVE_MU
-#define DCBF_ADAPTIVE_MU 0
-#endif
-#ifndef DCBF_MU_MAX
-#define DCBF_MU_MAX 0.1
-#endif
-#ifndef DCBF_SIGMA_MIN
-#define DCBF_SIGMA_MIN 0.0
-#endif
-#ifndef DCBF_ADAPT_FIRST
-#define DCBF_ADAPT_FIRST 0
-#endif
-#ifndef DCBF_MU_BASED_INIT
-#define DCBF_MU_BASED_INIT 0
-#endif
-#ifndef DCBF_ZINIT_MAX
-#define DCBF_ZINIT_MAX 1e3
-#endif
-#ifndef DCBF_ZINIT_MIN
-#define DCBF_ZINIT_MIN 1e-6
-#endif
 #ifndef DCBF_RESTO_WINDOW
 #define DCBF_RESTO_WINDOW 1e-2       /* restoration: relative decrease of the squared violation over three steps */
 #endif
@@ -182,11 +161,6 @@ struct IpmState {
     int nf, iters, acc_cnt, status;
     int phase, nstall, tiny, nresto;
     bool pending, reinit, first, done;
-#if DCBF_ADAPTIVE_MU
-    double kref[4];        // KKT errors of the last accepted free-mode iterates (adaptive barrier rule)
-    int nref;
-    bool free_mode;
-#endif
 };
 
 // accumulators of one full pass
@@ -198,7 +172,6 @@ struct Acc {
     double theta, pinf;       // sum |c - s|, max |c - s|
     double cmin, cmax;        // extremes of gap*z (complementarity)
     double zsum;              // sum of bound multipliers
-    double csum;              // sum of gap*z
     double logsum, logprod;   // sum log(gaps) = logsum + log(logprod)
     double v2, vmax;          // violation of the original bounds
     int nz, nrows, logcnt;
@@ -210,7 +183,7 @@ DCBF_HD void acc_reset(Acc<N> &A) {
     for (int i = 0; i < N * (N + 1) / 2; i++) A.K[i] = 0.0;
     DCBF_UNROLL
     for (int i = 0; i < N; i++) { A.q1[i] = 0.0; A.q2[i] = 0.0; A.q3[i] = 0.0; A.grad[i] = 0.0; }
-    A.f = 0.0; A.theta = 0.0; A.pinf = 0.0; A.cmin = 1e300; A.cmax = 0.0; A.zsum = 0.0; A.csum = 0.0;
+    A.f = 0.0; A.theta = 0.0; A.pinf = 0.0; A.cmin = 1e300; A.cmax = 0.0; A.zsum = 0.0;
     A.logsum = 0.0; A.logprod = 1.0; A.v2 = 0.0; A.vmax = 0.0; A.nz = 0; A.nrows = 0; A.logcnt = 0;
 }
 
@@ -265,13 +238,8 @@ DCBF_HD RowW row_full(const RowCtl &ctl, Acc<N> &A, LogAcc &LA, double c, double
             sv = dmin(sv, hr - 1e-2 * dmax(1.0, fabs(hr)));
         }
         s = sv;
-#if DCBF_MU_BASED_INIT
-        if (LO) zl = dmin(DCBF_ZINIT_MAX, dmax(DCBF_ZINIT_MIN, ctl.mu / (s - lr)));
-        if (HI) zu = dmin(DCBF_ZINIT_MAX, dmax(DCBF_ZINIT_MIN, ctl.mu / (hr - s)));
-#else
         if (LO) zl = 1.0;
         if (HI) zu = 1.0;
-#endif
     } else if (ctl.pending) {
         s += ctl.alpha * ds;
         if (LO) {
@@ -293,7 +261,7 @@ DCBF_HD RowW row_full(const RowCtl &ctl, Acc<N> &A, LogAcc &LA, double c, double
         const double gap = s - lr, inv = 1.0 / gap;
         sig += zl * inv; binv += inv; y -= zl;
         const double cz = gap * zl;
-        A.cmin = dmin(A.cmin, cz); A.cmax = dmax(A.cmax, cz); A.zsum += zl; A.csum += cz; A.nz++;
+        A.cmin = dmin(A.cmin, cz); A.cmax = dmax(A.cmax, cz); A.zsum += zl; A.nz++;
         log_push(LA, gap);
         el = inv;
     }
@@ -301,7 +269,7 @@ DCBF_HD RowW row_full(const RowCtl &ctl, Acc<N> &A, LogAcc &LA, double c, double
         const double gap = hr - s, inv = 1.0 / gap;
         sig += zu * inv; binv -= inv; y += zu;
         const double cz = gap * zu;
-        A.cmin = dmin(A.cmin, cz); A.cmax = dmax(A.cmax, cz); A.zsum += zu; A.csum += cz; A.nz++;
+        A.cmin = dmin(A.cmin, cz); A.cmax = dmax(A.cmax, cz); A.zsum += zu; A.nz++;
         log_push(LA, gap);
         eu = inv;
     }
@@ -1301,9 +1269,6 @@ DCBF_HD void ipm_init(const dcbf_params &P, IpmState<N> &S) {
     S.resto_target = 0.0; S.resto_entry = 0.0; S.theta_max = 1e300; S.theta_min = 0.0; S.nf = 0; S.iters = 0; S.acc_cnt = 0;
     S.status = -1; S.nstall = 0; S.tiny = 0; S.nresto = 0; S.v2_h1 = 0.0; S.v2_h2 = 0.0; S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; S.done = false;
     S.obj = 0.0; S.viol = 0.0;
-#if DCBF_ADAPTIVE_MU
-    S.nref = 0; S.free_mode = true;
-#endif
 }
 
 template <int N>
@@ -1346,44 +1311,6 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
         const double sd = dmax(100.0, 2.0 * A.zsum / (double)(A.nrows + A.nz)) * 0.01;
         const double sc = dmax(100.0, A.zsum / (double)(A.nz > 0 ? A.nz : 1)) * 0.01;
         double E0;
-#if DCBF_ADAPTIVE_MU
-        {
-            // Adaptive barrier parameter (Nocedal, Waechter & Waltz 2009; Ipopt mu_strategy adaptive with the LOQO oracle): in free
-            // mode mu follows the current complementarity every iteration, mu = sigma * avg with the centrality-driven
-            // sigma = 0.1 min(0.05 (1 - xi) / xi, 2)^3, xi = min / avg of the complementarity products, as long as the KKT error
-            // keeps decreasing against the last four accepted iterates; otherwise the monotone rule takes over (mu fixed at 0.8 avg
-            // until its barrier problem is solved to kappa_eps mu) and hands back afterwards.
-            const double nzd = (double)(A.nz > 0 ? A.nz : 1);
-            const double avg = A.csum / nzd;
-            E0 = dmax(dmax(dinf / sd, A.pinf), A.cmax / sc);
-            if (E0 > tol) {
-                const double mu_min = tol * 0.1;
-                const double err = dinf / sd + A.theta + A.csum / (sc * nzd);
-                const double xi = A.cmin / avg;
-                const double q = dmin(0.05 * (1.0 - xi) / xi, 2.0);
-                const double mu_loqo = dmax(mu_min, dmin(dmax(0.1 * q * q * q, DCBF_SIGMA_MIN) * avg, DCBF_MU_MAX));
-                if (S.free_mode) {
-                    double refmax = 0.0;
-                    for (int i = 0; i < S.nref; i++) refmax = dmax(refmax, S.kref[i]);
-                    const bool sufficient = S.nref < 4 || err <= 0.9999 * refmax;
-                    if (sufficient) {
-                        S.kref[S.iters & 3] = err; if (S.nref < 4) S.nref++;
-                        if (S.iters > 0 || DCBF_ADAPT_FIRST) { S.mu = mu_loqo; S.nf = 0; }
-                    } else {
-                        S.free_mode = false;
-                        S.mu = dmax(mu_min, dmin(0.8 * avg, DCBF_MU_MAX)); S.nf = 0;
-                    }
-                } else {
-                    const double compm = dmax(fabs(A.cmax - S.mu), fabs(A.cmin - S.mu));
-                    const double Emu = dmax(dmax(dinf / sd, A.pinf), compm / sc);
-                    if (Emu <= DCBF_KAPPA_EPS * S.mu) {
-                        S.free_mode = true; S.nref = 1; S.kref[0] = err;
-                        S.mu = dmin(mu_loqo, dmax(mu_min, dmin(DCBF_KAPPA_MU * S.mu, DCBF_MU_POW(S.mu)))); S.nf = 0;
-                    }
-                }
-            }
-        }
-#else
         for (;;) {
             const double compm = dmax(fabs(A.cmax - S.mu), fabs(A.cmin - S.mu));
             E0 = dmax(dmax(dinf / sd, A.pinf), A.cmax / sc);
@@ -1396,7 +1323,6 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             }
             break;
         }
-#endif
         if (E0 <= tol) { S.status = 0; S.done = true; return true; }
         if (E0 <= 1e-6 && A.vmax <= P.constr_viol_tol) {
             if (++S.acc_cnt >= 15) { S.status = 1; S.done = true; return true; }

@@ -274,8 +274,9 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
             __syncwarp();
         }
         const int leg = in.leg ? in.leg[b] : 1;
+        const int md = in.mode ? in.mode[b] : 2;   // 0: warm start = previous plan verbatim, 1: shifted plan, 2: cold start
         wp::WState S;
-        wp::solve_warp<wp::LipW, NS>(in, b, lane, wid, leg, S);
+        wp::solve_warp<wp::LipW, NS>(in, b, lane, wid, leg, S, md == 0 ? cs_.P.mu_warm : (md == 1 ? cs_.P.mu_shift : cs_.P.mu_init));
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
         if (lane < 15) {
             const double v = sm.nd.nodes[lane / 5 + 1][lane % 5];
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, 12 / wp::Wpc<M, NS>::v
         if (lane >= 16 && lane < 22) sm.zc[lane - 16] = in.warm[6 * (size_t)b + lane - 16];
         __syncwarp();
         wp::WState S;
-        wp::solve_warp<M, NS>(in, b, lane, wid, 1, S);
+        wp::solve_warp<M, NS>(in, b, lane, wid, 1, S, cs_.P.mu_init);
         // ---- outputs: plan re-roll of gen_dd_control (MPC_DD_sig_step.py:83-99) = the staged nodes of the final iterate ------
         if (lane < 9 && out.x_plan) out.x_plan[9 * (size_t)b + lane] = sm.nd.nodes[lane / 3 + 1][lane % 3];
         if (lane < 6 && out.u) out.u[6 * (size_t)b + lane] = sm.zc[lane];
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
         int done = 0, ninf = 0, tot = 0;
         for (int st = 0; st < steps; st++) {
             wp::WState S;
-            wp::solve_warp<wp::LipW, NS>(in, b, lane, wid, leg, S);
+            wp::solve_warp<wp::LipW, NS>(in, b, lane, wid, leg, S, st == 0 ? cs_.P.mu_init : cs_.P.mu_shift);
             tot += S.iters;
             if (S.status == 2) ninf++;
             const bool close = wp::w_close<NS>(cs_.P, sm);
@@ -755,6 +756,10 @@ int dcbf_default_params(int formulation, dcbf_params *P) {
     // Early hand-over to the restoration phase.  LIP formulations: three accepted steps below 1e-2.  Differential drive, where 46 % of
     // the config-4 scenarios are infeasible and crawl for ~10 such steps first: two below 5e-2 (mean iterations 14.8 -> 12.8 on
     // config 4, class agreement with the oracle 99.97 %; the same setting costs the modi formulation 0.06 points, so it keeps 1e-2 / 3).
+    // Warm-started re-plans start at a lower barrier parameter (Ipopt's usual warm-start setting): re-solving a plan at a state 1 cm /
+    // 2 cm/s away takes 12.1 iterations with mu_init and 6.6 with 1e-4 (sig_step; modi 12.8 -> 7.9), same optima; the shifted plan of the
+    // closed loop is infeasible by ~0.37 in its third step and does best with 1e-2 (13.3 -> 12.0).
+    P->mu_warm = 1e-4; P->mu_shift = 1e-2;
     P->tiny_alpha = formulation == DCBF_DD ? 5e-2 : 1e-2;
     P->tiny_count = formulation == DCBF_DD ? 2 : 3;
     if (formulation == DCBF_SIG_STEP) {
@@ -879,7 +884,7 @@ int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, co
     if (!x0 || !goal || !z) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     ENTER(stream);
-    BatchIn in = {x0, goal, nullptr, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F};
+    BatchIn in = {x0, goal, nullptr, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F, nullptr};
     EvalPtrs ev = {z, lambda, f, grad, c, jac, cl, cu, hess, dcbf_num_rows(ctx)};
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->P.formulation == DCBF_DD) eval_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, ev);
@@ -889,15 +894,27 @@ int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, co
     return DCBF_OK;
 }
 
+static int solve_impl(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+                      const double *warm, const double *last_u, const uint8_t *mode, double *u, double *x_plan, double *p_plan, int32_t *status,
+                      int32_t *iters, double *obj, double *viol, uint8_t *close2goal, void *stream);
+
 int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
                const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
                int32_t *iters, double *obj, double *viol, uint8_t *close2goal, void *stream) {
+    return solve_impl(ctx, B, x0, goal, leg, field, warm, last_u, nullptr, u, x_plan, p_plan, status, iters, obj, viol, close2goal, stream);
+}
+
+// `mode` (device, may be NULL = cold everywhere): how each scenario's start vector was made (dcbf_tick), which selects its first
+// barrier parameter (dcbf_params::mu_warm / mu_shift / mu_init)
+static int solve_impl(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+                      const double *warm, const double *last_u, const uint8_t *mode, double *u, double *x_plan, double *p_plan, int32_t *status,
+                      int32_t *iters, double *obj, double *viol, uint8_t *close2goal, void *stream) {
     if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
     if (!x0 || !goal || !warm) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     ENTER(stream);
-    BatchIn in = {x0, goal, warm, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F};
+    BatchIn in = {x0, goal, warm, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F, mode};
     SolveOut out = {u, x_plan, p_plan, obj, viol, status, iters, close2goal};
     cudaStream_t st = (cudaStream_t)stream;
     const bool dd = ctx->P.formulation == DCBF_DD;
@@ -932,7 +949,7 @@ int dcbf_setup_info(dcbf_ctx *ctx, int32_t B, const double *x0, const double *go
     if (!x0 || !goal) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     ENTER(stream);
-    BatchIn in = {x0, goal, nullptr, nullptr, nullptr, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F};
+    BatchIn in = {x0, goal, nullptr, nullptr, nullptr, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F, nullptr};
     cudaStream_t st = (cudaStream_t)stream;
     const bool dd = ctx->P.formulation == DCBF_DD;
     if (ctx->kernel_mode == 1) {
@@ -985,7 +1002,8 @@ int dcbf_tick(dcbf_ctx *ctx, int32_t B, const double *glo_pos, const double *glo
                                                         mode, xn, wm);
     CK(cudaGetLastError());
     ctx->launches++;
-    const int rc = dcbf_solve(ctx, B, xn, goal, leg, field, wm, nullptr, u, xp, pp, status, iters, obj, viol, close2goal, stream);
+    const int rc = solve_impl(ctx, B, xn, goal, leg, field, wm, nullptr, (mode && prev_plan) ? mode : nullptr, u, xp, pp, status, iters, obj, viol,
+                              close2goal, stream);
     if (rc != DCBF_OK) return rc;
     if (pos_det) {
         const size_t n = b * 126;
@@ -1081,7 +1099,7 @@ int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, cons
     if (!x0 || !goal) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     ENTER(stream);
-    BatchIn in = {x0, goal, nullptr, nullptr, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F};
+    BatchIn in = {x0, goal, nullptr, nullptr, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F, nullptr};
     RolloutOut out = {x_final, traj, steps_done, n_infeasible, total_iters};
     if (use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);

@@ -29,6 +29,7 @@ struct BatchIn {
     const double *cir_rec, *elp_rec;
     int Kc, Ke;
     int F;   // number of prepared fields (0: unknown, no range check)
+    const uint8_t *mode;   // per scenario: how the start vector was made (0 previous plan verbatim, 1 shifted plan, 2 / NULL cold start)
 };
 
 // field index of scenario b.  An index outside [0, F) -- a stale or short index array -- must not become an out-of-bounds read:
@@ -102,6 +103,7 @@ DCBF_HD void lip_lane_begin(const dcbf_params &P, const Consts &K, const BatchIn
     DCBF_UNROLL
     for (int i = 0; i < 15; i++) u0[i] = in.warm[15 * (size_t)b + i];
     lip_z_from_u(K, M.pb.x0, u0, S.z);
+    if (in.mode) S.mu = in.mode[b] == 0 ? P.mu_warm : (in.mode[b] == 1 ? P.mu_shift : P.mu_init);
 }
 
 DCBF_HD void lip_lane_finish(const dcbf_params &P, const LipModel<DCBF_KT> &M, const IpmState<9> &S, int b, const SolveOut &out) {
@@ -262,9 +264,7 @@ DCBF_HD void rollout_lip_lane(const dcbf_params &P, const Consts &K, const Batch
     for (int st = 0; st < steps; st++) {
         setup_problem(P, M.pb);                                          // goal shift / selection at the new state
         ipm_init(P, S);
-#ifdef DCBF_MU_WARM
-        if (st > 0) S.mu = DCBF_MU_WARM;
-#endif
+        if (st > 0) S.mu = P.mu_shift;                                   // warm-started re-plan: lower first barrier parameter
         lip_z_from_u(K, M.pb.x0, u0, S.z);
         while (!ipm_iterate(K, P, M, S)) {}
         tot += S.iters;

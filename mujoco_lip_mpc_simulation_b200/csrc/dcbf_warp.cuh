@@ -966,7 +966,7 @@ __device__ __forceinline__ void reduce8_inline(Stat8 &t, int lane) {
 // the solver for one problem (all 32 lanes call it with identical arguments).  Inputs in sm: x0, graw, zc (+ model data).
 // ---------------------------------------------------------------------------------------------------------------
 template <class M, int NS>
-__device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg, WState &S) {
+__device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg, WState &S, double mu0) {
     using Sh = WarpShared<M, NS>;
     constexpr int RP = Sh::RP;
     constexpr int N = M::N, NK = N * (N + 1) / 2;
@@ -1012,7 +1012,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
     const int ln = lane < N ? lane : N - 1;   // clamped lane: keeps the per-variable sections branch-free
     const int rowbase = lane < N + 1 ? lane * (lane + 1) / 2 : 0;
     // ---- solver state ------------------------------------------------------------------------------------------------
-    S.mu = P.mu_init; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4;
+    S.mu = mu0; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4;
     sm.cold[C_RESTO_TARGET] = 0.0; sm.cold[C_RESTO_ENTRY] = 0.0; sm.cold[C_THETA_MAX] = 1e300; sm.cold[C_THETA_MIN] = 0.0;
     S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0; S.tiny = 0;
     S.nresto = 0; S.v2_h1 = 0.0; S.v2_h2 = 0.0;
