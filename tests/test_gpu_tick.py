@@ -49,14 +49,21 @@ def test_tick_matches_host_restatement_and_plain_solve(form):
         p3 = prev[b].reshape(3, 5)
         want = {0: p3, 1: np.stack([p3[1], p3[2], p3[2]]), 2: np.stack([xn[b]] * 3)}[int(mode[b])]
         np.testing.assert_array_equal(warm[b].reshape(3, 5), want)
-    # the re-plan is the plain solve on (x_next, warm)
+    # the re-plan is the plain solve on (x_next, warm): bit for bit where the start is cold (mode 2); a warm-started scenario begins
+    # at a lower barrier parameter (dcbf_params mu_warm / mu_shift), i.e. other iterates towards the same optimum
     ref = s.solve(xn, sc.goal, -sc.leg, warm, field=sc.field)
     torch.cuda.synchronize()
-    assert torch.equal(out["plan"].status, ref.status) and torch.equal(out["plan"].iters, ref.iters)
-    assert torch.equal(out["plan"].p_plan, ref.p_plan) and torch.equal(out["plan"].x_plan, ref.x_plan)
+    cold = torch.as_tensor(mode == 2, device=ref.status.device)
+    pl = out["plan"]
+    assert torch.equal(pl.status[cold], ref.status[cold]) and torch.equal(pl.iters[cold], ref.iters[cold])
+    assert torch.equal(pl.p_plan[cold], ref.p_plan[cold]) and torch.equal(pl.x_plan[cold], ref.x_plan[cold])
+    both = (pl.status == 0) & (ref.status == 0) & ~cold
+    assert float(((pl.status == 2) == (ref.status == 2)).float().mean()) >= 0.98 and int(both.sum()) >= 40
+    d = (pl.p_plan - ref.p_plan).abs().reshape(B, -1).max(dim=1).values
+    assert float((d[both] <= 1e-4).float().mean()) >= 0.95      # `prev` is noise around x0: a few land in another local optimum
     # dense plan trajectory: three segments of 1 + 41 samples (MPC_LIP_modi.py:117-122)
     pd = out["pos_det"].cpu().numpy()
-    xp, pp = ref.x_plan.cpu().numpy(), ref.p_plan.cpu().numpy()
+    xp, pp = pl.x_plan.cpu().numpy(), pl.p_plan.cpu().numpy()
     for b in range(0, B, 7):
         starts = [xn[b], xp[b, 0], xp[b, 1]]
         want = np.concatenate([_lipmodel.track_det(starts[j], pp[b, j], 0.4) for j in range(3)])
