@@ -229,14 +229,17 @@ def main():
     p_plan_last = out.p_plan.cpu().numpy()      # results of the last timed step (the buffers are reused below)
     flop_per_step = float(it_acc.item()) / args.steps * F_ITER_SIG_K6     # mean over the timed steps (the batches rotate when N > 1)
 
-    # ---- pipelined throughput: consecutive batches on two streams (one context each) -------------------------------------------
+    # ---- pipelined throughput: consecutive batches on rotating streams (one context each) -------------------------------------------
     # A step of `value` ends when its slowest scenario ends: 4096 scenarios on 1776 persistent warps are 2.3 per warp, so a third of
     # the warps run three problems while the rest run two and then idle (DESIGN.md "the tail").  A caller with a stream of batches does
     # not have to wait: batch k+1 is launched on a second stream and its warps take over the SM slots batch k's warps vacate.
-    solver_b = DcbfSolver("sig_step", device=local)
-    solver_b.set_fields(cir_all)
-    out_b = SolveResult(*[torch.empty_like(t_) for t_ in (out.u, out.x_plan, out.p_plan, out.status, out.iters, out.obj, out.viol, out.close2goal)])
-    lanes = [(solver, out, torch.cuda.Stream(device=dev)), (solver_b, out_b, torch.cuda.Stream(device=dev))]
+    n_lanes = int(os.environ.get("DCBF_BENCH_LANES", "3"))
+    lanes = [(solver, out, torch.cuda.Stream(device=dev))]
+    for _ in range(n_lanes - 1):
+        sv_ = DcbfSolver("sig_step", device=local)
+        sv_.set_fields(cir_all)
+        o_ = SolveResult(*[torch.empty_like(t_) for t_ in (out.u, out.x_plan, out.p_plan, out.status, out.iters, out.obj, out.viol, out.close2goal)])
+        lanes.append((sv_, o_, torch.cuda.Stream(device=dev)))
 
     def pipelined(n_steps):
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -245,7 +248,7 @@ def main():
         for sv_, _, st_ in lanes:
             st_.wait_event(p0)
         for s_ in range(n_steps):
-            sv_, o_, st_ = lanes[s_ % 2]
+            sv_, o_, st_ = lanes[s_ % n_lanes]
             x0, goal, leg, field, warm = dev_in[(rank + s_) % POOL]
             with torch.cuda.stream(st_):
                 sv_.solve_into(B, x0, goal, leg, field, warm, None, o_)
@@ -261,7 +264,7 @@ def main():
     pipe_ms = max_over_ranks(pipelined(pipe_steps), dev)
     if world > 1:
         dist.barrier()
-    del solver_b
+    del lanes[1:]
 
     # ---- timed region 2: end to end through the host-buffer C-ABI call ----------------------------------------------
     # inputs and results live in page-locked host memory (the copies inside the timed call are DMA transfers from / to them)
@@ -459,7 +462,8 @@ def main():
             "gpu_launches": int(launches),
             "throughput_pipelined": {"value": world * B * pipe_steps / (pipe_ms * 1e-3), "unit": "solves/s", "steps": pipe_steps,
                                      "ms_per_step": pipe_ms / pipe_steps,
-                                     "how": "the same batches launched back to back on two streams (two contexts), device time over all steps; "
+                                     "streams": n_lanes,
+                                     "how": "the same batches launched back to back on rotating streams (one context each), device time over all steps; "
                                             "no L2 flush in between (the batches overlap), inputs rotate through the pool"},
             "p50_solve_us": float(np.median(lat)), "p95_solve_us": float(np.percentile(lat, 95)),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
