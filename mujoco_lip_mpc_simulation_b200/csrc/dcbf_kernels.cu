@@ -58,6 +58,7 @@ struct dcbf_ctx {
     int sched_select;                 // order obstacle-selecting formulations too (env DCBF_ORDER_SELECT)
     int zero_copy;                    // dcbf_solve_host reads / writes page-locked caller buffers from the kernels (env DCBF_ZEROCOPY)
     int dd_generic;                   // differential drive: keep the generic two-slot kernel (env DCBF_DD_GENERIC=1; A/B comparisons and tests)
+    int slots_per_sm;                 // cap on the resident CTAs per SM of the persistent warp kernels (env DCBF_SLOTS; 0 = what the kernel allows; occupancy probes)
 };
 
 #define CK(call)                                                                                        \
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
 // One warp per CTA: the block scheduler hands a freed warp slot to the next problem (iteration counts differ by 3x), and the
 // scratch lives in static shared memory.
 #ifndef DCBF_WARP_MIN_CTAS
-#define DCBF_WARP_MIN_CTAS(NS) (((NS) == 1 ? 12 : 8) / wp::Wpc<wp::LipW, NS>::v)   /* 12 / 8 / 8 warps per SM: register budget 168 / 255 / 255 (spills cost more than the lost warps) */
+#define DCBF_WARP_MIN_CTAS(NS) (((NS) == 1 ? 16 : 8) / wp::Wpc<wp::LipW, NS>::v)   /* 16 / 8 / 8 warps per SM: register budget 128 / 255 / 255.  One slot: 128 registers without spills since the per-lane invariants are recomputed (wp::LaneRefresh) and the cold solver state lives in shared memory; 13.4 KB of shared memory per CTA let 16 CTAs fit */
 #endif
 #ifndef DCBF_WARP_GRID_CAP
 #define DCBF_WARP_GRID_CAP 64   /* CTAs per SM in the grid (grid-stride loop beyond); 0 = one CTA per problem */
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
         const int leg = in.leg ? in.leg[b] : 1;
         const int md = in.mode ? in.mode[b] : 2;   // 0: warm start = previous plan verbatim, 1: shifted plan, 2: cold start
         wp::WState S;
-        wp::solve_warp<wp::LipW, NS>(in, b, lane, wid, leg, S, md == 0 ? cs_.P.mu_warm : (md == 1 ? cs_.P.mu_shift : cs_.P.mu_init));
+        wp::solve_warp<wp::LipW, NS>(P, in, b, lane, wid, leg, S, md == 0 ? P.mu_warm : (md == 1 ? P.mu_shift : P.mu_init));
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
         if (lane < 15) {
             const double v = sm.nd.nodes[lane / 5 + 1][lane % 5];
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
             if (out.obj) out.obj[b] = sm.cold[wp::C_OBJ];
             if (out.viol) out.viol[b] = sm.cold[wp::C_VIOL];
 #endif
-            if (out.close) out.close[b] = wp::w_close<NS>(cs_.P, sm) ? 1 : 0;
+            if (out.close) out.close[b] = wp::w_close<NS>(P, sm) ? 1 : 0;
         }
         __syncwarp();
     }
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, 12 / wp::Wpc<M, NS>::v
         if (lane >= 16 && lane < 22) sm.zc[lane - 16] = in.warm[6 * (size_t)b + lane - 16];
         __syncwarp();
         wp::WState S;
-        wp::solve_warp<M, NS>(in, b, lane, wid, 1, S, cs_.P.mu_init);
+        wp::solve_warp<M, NS>(P, in, b, lane, wid, 1, S, P.mu_init);
         // ---- outputs: plan re-roll of gen_dd_control (MPC_DD_sig_step.py:83-99) = the staged nodes of the final iterate ------
         if (lane < 9 && out.x_plan) out.x_plan[9 * (size_t)b + lane] = sm.nd.nodes[lane / 3 + 1][lane % 3];
         if (lane < 6 && out.u) out.u[6 * (size_t)b + lane] = sm.zc[lane];
@@ -366,10 +367,10 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
         int done = 0, ninf = 0, tot = 0;
         for (int st = 0; st < steps; st++) {
             wp::WState S;
-            wp::solve_warp<wp::LipW, NS>(in, b, lane, wid, leg, S, st == 0 ? cs_.P.mu_init : cs_.P.mu_shift);
+            wp::solve_warp<wp::LipW, NS>(P, in, b, lane, wid, leg, S, st == 0 ? P.mu_init : P.mu_shift);
             tot += S.iters;
             if (S.status == 2) ninf++;
-            const bool close = wp::w_close<NS>(cs_.P, sm);
+            const bool close = wp::w_close<NS>(P, sm);
             if (out.traj && lane < 8) {
                 double v;
                 if (lane < 5) v = sm.nd.nodes[1][lane];
@@ -641,6 +642,7 @@ static int warp_slots(const dcbf_ctx *ctx) {
 template <class M, int NS>
 static int warp_grid(const dcbf_ctx *ctx, int n, int ctas_per_sm) {
     const int W = wp::Wpc<M, NS>::v;
+    if (ctx->slots_per_sm > 0 && ctx->slots_per_sm < ctas_per_sm) ctas_per_sm = ctx->slots_per_sm;
     const int need = (n + W - 1) / W, resident = ctx->sm_count * ctas_per_sm;
     return need < resident ? (need < 1 ? 1 : need) : resident;
 }
@@ -809,7 +811,8 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     { const char *sp = getenv("DCBF_ORDER"); ctx->sched_min_batch = sp ? atoi(sp) : 2048; }
     { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }
-    { const char *sp = getenv("DCBF_DD_GENERIC"); ctx->dd_generic = sp ? atoi(sp) : 0; }   // below ~1 problem per warp slot there is no tail to hide
+    { const char *sp = getenv("DCBF_DD_GENERIC"); ctx->dd_generic = sp ? atoi(sp) : 0; }
+    { const char *sp = getenv("DCBF_SLOTS"); ctx->slots_per_sm = sp ? atoi(sp) : 0; }
     if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }

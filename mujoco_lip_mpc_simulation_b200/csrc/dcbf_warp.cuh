@@ -193,7 +193,11 @@ template <int NS> struct KsMax { static constexpr int v = NS == 1 ? 6 : (NS == 2
 
 // slots of WarpShared::cold.  Every lane stores the same value and nobody reads before the next __syncwarp(); none of these is
 // updated by read-modify-write (that would not be safe if the lanes of a warp drifted apart).
-enum { C_RESTO_TARGET = 0, C_RESTO_ENTRY, C_THETA_MAX, C_THETA_MIN, C_OBJ, C_VIOL, C_ST_THETA, C_ST_LOGSUM, C_ST_V2, C_ST_VMAX };
+enum { C_RESTO_TARGET = 0, C_RESTO_ENTRY, C_THETA_MAX, C_THETA_MIN, C_OBJ, C_VIOL, C_ST_THETA, C_ST_LOGSUM, C_ST_V2, C_ST_VMAX,
+       // solver state that is touched once per iteration or less (was WState, i.e. registers carried across the whole solve).  alpha,
+       // alpha_z, carry_log, delta_last: every lane overwrites them with the same value and reads its own write.  lm_lambda, v2_h1,
+       // v2_h2 depend on their previous value: they are read into locals, the warp synchronises, then they are written.
+       C_ALPHA, C_ALPHA_Z, C_CARRY_LOG, C_DELTA_LAST, C_LM_LAMBDA, C_V2_H1, C_V2_H2, C_NROWS_NZ, C_NZ, C_COUNT };
 
 // model-specific node data -----------------------------------------------------------------------------------------------------
 struct LipNodeData {
@@ -233,7 +237,7 @@ struct alignas(16) WarpShared {
     static constexpr bool ROLLED = NS > 2 || (NS == 2 && M::ROLL2);
     double RS[ROLLED ? 6 : 1][ROLLED ? 32 * NS : 1];
     typename M::NodeData nd;
-    double cold[12];         // replicated scalars that are written once per event and read much later (see C_*): kept out of registers
+    double cold[C_COUNT];    // replicated scalars that are written once per event and read much later (see C_*): kept out of registers
     double filt_th[DCBF_FILT], filt_ph[DCBF_FILT];
 };
 
@@ -268,6 +272,13 @@ template <int NS> struct Wpc<DdW, NS> { static constexpr int v = DCBF_WPC_DD(NS)
 #define DCBF_WPC_DDL 1
 #endif
 template <int NS> struct Wpc<DdL, NS> { static constexpr int v = DCBF_WPC_DDL; };
+
+// kernels built for 128 registers (see solve_warp): the one-slot LIP kernel
+#ifndef DCBF_LANE_REFRESH
+#define DCBF_LANE_REFRESH 1
+#endif
+template <class M, int NS> struct LaneRefresh { static constexpr bool v = false; };
+template <> struct LaneRefresh<LipW, 1> { static constexpr bool v = DCBF_LANE_REFRESH != 0; };
 
 // per-problem scratch (one per warp) and the constants are static shared-memory objects, so every function sees them as
 // shared-space symbols (no generic pointers through the out-of-line calls)
@@ -325,12 +336,17 @@ struct RowBnd { double lo, hi; bool has_lo, has_hi; };
 //   DD : grad = p0 Jx[i+1] + p1 Jy[i+1] + q0 Jx[i] + q1 Jy[i] + t_all e_{v_i} + t_own e_{w_i}
 struct RowEval { double c, p0, p1, q0, q1, t_all, t_own, hq0, hq1, hq2; };
 
-struct WState {   // replicated scalars of one problem (registers)
-    double mu, sf, alpha, alpha_z, delta_last, lm_lambda;
-    double v2_h1, v2_h2;   // windowed stagnation test of the restoration (see ipm_iterate())
-    int nf, iters, acc_cnt, status, phase, nstall, tiny, nresto;
-    bool pending, reinit, first;
+struct WState {   // replicated scalars of one problem (registers); the small counters share one register, the rarely touched doubles
+                  // live in WarpShared::cold (C_ALPHA ...)
+    double mu, sf;
+    int iters, status;
+    unsigned phase : 1, pending : 1, reinit : 1, first : 1;
+    unsigned nf : 4;        // filter entries (<= DCBF_FILT)
+    unsigned acc_cnt : 5;   // consecutive acceptable iterates (15 ends the solve) / stagnating restoration steps (2 do)
+    unsigned nstall : 2, tiny : 4;
+    unsigned nresto : 2;    // restoration steps of this restoration phase, saturating (the windowed stagnation test needs >= 2)
 };
+static_assert(DCBF_FILT <= 15, "WState::nf is a 4-bit field");
 
 // D-CBF row on the staged obstacle record (circle: a' = c' = 1, b' = 0); shared by both models
 template <bool GRAD>
@@ -966,14 +982,15 @@ __device__ __forceinline__ void reduce8_inline(Stat8 &t, int lane) {
 // the solver for one problem (all 32 lanes call it with identical arguments).  Inputs in sm: x0, graw, zc (+ model data).
 // ---------------------------------------------------------------------------------------------------------------
 template <class M, int NS>
-__device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg, WState &S, double mu0) {
+__device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int lane, int wid, int leg, WState &S, double mu0) {
     using Sh = WarpShared<M, NS>;
     constexpr int RP = Sh::RP;
     constexpr int N = M::N, NK = N * (N + 1) / 2;
     constexpr int KQ_RHS_ = KQ_K + NK;   // = packed row N of the system: tri(N, j) = NK + j
     Sh &sm = g_sm<M, NS>[wid];
     const CtaShared &cs_ = g_cs;
-    const dcbf_params &P = cs_.P;
+    // P is the kernel's own parameter (constant bank): its fields are instruction operands of the inlined body, not values loaded
+    // from the shared-memory copy and then carried in registers across the solve (the out-of-line functions read g_cs.P)
     // ---- problem setup -------------------------------------------------------------------------------------------
     const int Ks = M::template setup<NS>(sm, P, in, b, lane);
     const int ms = M::rows_per_step(P, Ks);   // rows per step
@@ -1009,21 +1026,31 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
     int dlin[M::NROUND];
 #pragma unroll
     for (int t = 0; t < M::NROUND; t++) dlin[t] = M::LIN2 ? __ldg(cs_.tab->desc_lin + 32 * t + lane) : 0;
-    const int ln = lane < N ? lane : N - 1;   // clamped lane: keeps the per-variable sections branch-free
-    const int rowbase = lane < N + 1 ? lane * (lane + 1) / 2 : 0;
+    int ln = lane < N ? lane : N - 1;   // clamped lane: keeps the per-variable sections branch-free
+    int rowbase = lane < N + 1 ? lane * (lane + 1) / 2 : 0;
     // ---- solver state ------------------------------------------------------------------------------------------------
-    S.mu = mu0; S.sf = 1.0; S.alpha = 0.0; S.alpha_z = 0.0; S.delta_last = 0.0; S.lm_lambda = 1e-4;
+    S.mu = mu0; S.sf = 1.0; sm.cold[C_ALPHA] = 0.0; sm.cold[C_ALPHA_Z] = 0.0; sm.cold[C_DELTA_LAST] = 0.0; sm.cold[C_LM_LAMBDA] = 1e-4;
     sm.cold[C_RESTO_TARGET] = 0.0; sm.cold[C_RESTO_ENTRY] = 0.0; sm.cold[C_THETA_MAX] = 1e300; sm.cold[C_THETA_MIN] = 0.0;
     S.nf = 0; S.iters = 0; S.acc_cnt = 0; S.status = -1; S.nstall = 0; S.tiny = 0;
-    S.nresto = 0; S.v2_h1 = 0.0; S.v2_h2 = 0.0;
+    S.nresto = 0; sm.cold[C_V2_H1] = 0.0; sm.cold[C_V2_H2] = 0.0;
+    sm.cold[C_NROWS_NZ] = (double)(nrows + nz); sm.cold[C_NZ] = (double)(nz > 0 ? nz : 1);
     S.phase = PH_MAIN; S.pending = false; S.reinit = true; S.first = true; sm.cold[C_OBJ] = 0.0; sm.cold[C_VIOL] = 0.0;
     const double tol = P.tol;
     const double *stf = &sm.ST[0][0];
 
     bool nodes_valid = false;      // the node data (with Hessian terms) already describe zc (staged by the accepted trial)
-    double carry_log = 0.0;        // sum of log(gaps) at the accepted trial point = barrier term of the next full pass
-    bool carry_ok = false;
+    bool carry_ok = false;         // sm.cold[C_CARRY_LOG] holds the sum of log(gaps) at the accepted trial point = barrier term of the next full pass
     for (;;) {
+        if (LaneRefresh<M, NS>::v) {
+            // 128-register kernels (16 warps per SM): the lane index is re-read at the top of every iteration, so nothing derived from
+            // it is loop-invariant for the compiler.  Left alone, ~40 registers hold hoisted per-lane indices, predicates and
+            // addresses across the whole solve -- and at 128 registers they spill to local memory, which misses the (then 28 KB) L1
+            // and costs an L2 round trip each (long_scoreboard 12 % of the stall samples); recomputing them is ~170 integer
+            // instructions per iteration.
+            lane = lane_id();
+            ln = lane < N ? lane : N - 1;
+            rowbase = lane < N + 1 ? lane * (lane + 1) / 2 : 0;
+        }
         if (Wpc<M, NS>::v > 1) cta_tick(1);   // the warps of the CTA start every iteration together (shared instruction fetch)
         const bool resto = S.phase == PH_RESTO;
         if (!nodes_valid) M::template nodes<NS>(sm.zc, lane, wid, S.first ? 1.0 : (resto ? 0.0 : S.sf), true);
@@ -1071,7 +1098,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                         else if (bb.has_hi) sv = fmin(sv, hr - 1e-2 * fmax(1.0, fabs(hr)));
                         rs_ = sv; rzl_ = bb.has_lo ? 1.0 : 0.0; rzu_ = bb.has_hi ? 1.0 : 0.0;
                     } else if (S.pending) {
-                        rs_ += S.alpha * rds_;
+                        rs_ += sm.cold[C_ALPHA] * rds_;
                     }
                     const double rc = e.c - rs_;
                     // both sides in straight-line code (an absent side has gap 1 and multiplier 0): the lanes of a warp hold rows with a
@@ -1080,9 +1107,9 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                     const double gl = bb.has_lo ? rs_ - lr : 1.0, gh = bb.has_hi ? hr - rs_ : 1.0;
                     const double il = frcp(gl), ih = frcp(gh);
                     if (upd) {   // multiplier step with the kappa_sigma safeguard (mu / gap = mu * inv)
-                        const double ml = S.mu * il, mh = S.mu * ih;
-                        const double zl = fmax(fmin(rzl_ + S.alpha_z * rel_, DCBF_KAPPA_SIGMA * ml), ml * (1.0 / DCBF_KAPPA_SIGMA));
-                        const double zu = fmax(fmin(rzu_ + S.alpha_z * reu_, DCBF_KAPPA_SIGMA * mh), mh * (1.0 / DCBF_KAPPA_SIGMA));
+                        const double ml = S.mu * il, mh = S.mu * ih, alpha_z = sm.cold[C_ALPHA_Z];
+                        const double zl = fmax(fmin(rzl_ + alpha_z * rel_, DCBF_KAPPA_SIGMA * ml), ml * (1.0 / DCBF_KAPPA_SIGMA));
+                        const double zu = fmax(fmin(rzu_ + alpha_z * reu_, DCBF_KAPPA_SIGMA * mh), mh * (1.0 / DCBF_KAPPA_SIGMA));
                         rzl_ = bb.has_lo ? zl : 0.0; rzu_ = bb.has_hi ? zu : 0.0;
                     }
                     sig = fma(rzl_, il, rzu_ * ih);
@@ -1114,7 +1141,7 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         if (!ROLLED && NS > 1 && !resto && !carry_ok) st8.s2 = dlog(gap_prod);
         __syncwarp();   // the row branches reconverge here, before the shuffles
         reduce8_inline(st8, lane);
-        const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? carry_log : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
+        const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? sm.cold[C_CARRY_LOG] : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
                      st_cmin = st8.m1, st_cmax = st8.m2, st_vmax = st8.m3;
         carry_ok = false;
         sm.cold[C_ST_THETA] = st_theta; sm.cold[C_ST_LOGSUM] = st_logsum; sm.cold[C_ST_V2] = st_v2; sm.cold[C_ST_VMAX] = st_vmax;
@@ -1160,8 +1187,8 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         if (!resto) {
             if (S.first) { sm.cold[C_THETA_MAX] = 1e4 * fmax(1.0, st_theta); sm.cold[C_THETA_MIN] = 1e-4 * fmax(1.0, st_theta); S.first = false; }
             const double dinf = wmax(lane < N ? fabs(fma(S.sf, grad_a, q[2 * N + ln])) : 0.0);
-            const double sd = fmax(100.0, fdiv(2.0 * st_zsum, (double)(nrows + nz))) * 0.01;
-            const double sc = fmax(100.0, fdiv(st_zsum, (double)(nz > 0 ? nz : 1))) * 0.01;
+            const double sd = fmax(100.0, fdiv(2.0 * st_zsum, sm.cold[C_NROWS_NZ])) * 0.01;
+            const double sc = fmax(100.0, fdiv(st_zsum, sm.cold[C_NZ])) * 0.01;
             const double isd = frcp(sd), isc = frcp(sc);
             double E0;
             for (;;) {
@@ -1177,15 +1204,15 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 break;
             }
             if (E0 <= tol) { S.status = 0; break; }
-            if (E0 <= 1e-6 && st_vmax <= P.constr_viol_tol) { if (++S.acc_cnt >= 15) { S.status = 1; break; } } else S.acc_cnt = 0;
+            if (E0 <= 1e-6 && st_vmax <= P.constr_viol_tol) { S.acc_cnt = S.acc_cnt + 1; if (S.acc_cnt >= 15) { S.status = 1; break; } } else S.acc_cnt = 0;
             if (S.iters >= P.max_iter) { S.status = -1; break; }
-            if (S.tiny >= P.tiny_count) {   // pinned by the fraction-to-boundary rule while still infeasible: restoration now (see ipm_iterate())
+            if ((int)S.tiny >= P.tiny_count) {   // pinned by the fraction-to-boundary rule while still infeasible: restoration now (see ipm_iterate())
                 S.tiny = 0;
                 const int slot = S.nf < DCBF_FILT ? S.nf : (S.iters % DCBF_FILT);
                 if (lane == 0) { sm.filt_th[slot] = (1.0 - 1e-5) * st_theta; sm.filt_ph[slot] = (S.sf * fobj - S.mu * st_logsum) - 1e-5 * st_theta; }
-                if (S.nf < DCBF_FILT) S.nf++;
+                if (S.nf < DCBF_FILT) S.nf = S.nf + 1;
                 __syncwarp();
-                S.phase = PH_RESTO; sm.cold[C_RESTO_ENTRY] = st_vmax; sm.cold[C_RESTO_TARGET] = fmax(0.1 * st_vmax, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0; S.nresto = 0;
+                S.phase = PH_RESTO; sm.cold[C_RESTO_ENTRY] = st_vmax; sm.cold[C_RESTO_TARGET] = fmax(0.1 * st_vmax, 1e-9); sm.cold[C_LM_LAMBDA] = 1e-4; S.acc_cnt = 0; S.nresto = 0;
                 S.iters++;
                 continue;
             }
@@ -1193,10 +1220,11 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         } else {
             if (st_vmax <= sm.cold[C_RESTO_TARGET]) { S.phase = PH_MAIN; S.reinit = true; continue; }
             const double gn = wmax(lane < N ? fabs(q[ln]) : 0.0);
-            const bool stationary = gn <= 1e-10 * fmax(1.0, st_vmax) || S.lm_lambda > 1e12;
+            const bool stationary = gn <= 1e-10 * fmax(1.0, st_vmax) || sm.cold[C_LM_LAMBDA] > 1e12;
             if (stationary) {
                 if (st_vmax > P.constr_viol_tol) { S.status = 2; break; }
-                if (sm.cold[C_RESTO_ENTRY] <= 1e-9 || S.nstall++ >= 1) { S.status = -2; break; }   // see ipm_iterate()
+                if (sm.cold[C_RESTO_ENTRY] <= 1e-9 || S.nstall >= 1) { S.status = -2; break; }
+                S.nstall = S.nstall + 1;   // see ipm_iterate()
                 S.phase = PH_MAIN; S.reinit = true; continue;
             }
             if (S.iters >= P.max_iter) { S.status = -1; break; }
@@ -1208,8 +1236,9 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
         // ---- main phase: one factorisation with inertia correction by delta ----------------------------------------------------
         bool lm_accept = false;
         double v2t = 0.0, vmt = 0.0;
+        double lam = resto ? sm.cold[C_LM_LAMBDA] : 0.0;   // Levenberg-Marquardt parameter of this restoration step (written back below)
         for (int rt = 0; rt < 20; rt++) {
-            double shift = resto ? S.lm_lambda : 0.0;
+            double shift = lam;
             bool ok = false;
             for (int tr = 0; tr < 48; tr++) {
                 // lanes 0..N-1 own the rows of K, lane N the right-hand side (its "row" of the factor is L^-1 rhs).  Branch-free:
@@ -1231,16 +1260,17 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                     __syncwarp();
                 }
                 if (ok || resto) break;
-                if (shift == 0.0) shift = S.delta_last == 0.0 ? 1e-4 : fmax(1e-20, S.delta_last * (1.0 / 3.0));
-                else shift *= (S.delta_last == 0.0 ? 100.0 : 8.0);
+                const double dl = sm.cold[C_DELTA_LAST];
+                if (shift == 0.0) shift = dl == 0.0 ? 1e-4 : fmax(1e-20, dl * (1.0 / 3.0));
+                else shift *= (dl == 0.0 ? 100.0 : 8.0);
             }
             if (!ok) {
                 if (!resto) { S.status = -3; break; }
-                S.lm_lambda *= 10.0;
-                if (S.lm_lambda > 1e12) break;
+                lam *= 10.0;
+                if (lam > 1e12) break;
                 continue;
             }
-            if (!resto && shift > 0.0) S.delta_last = shift;
+            if (!resto && shift > 0.0) sm.cold[C_DELTA_LAST] = shift;
             // backward substitution: lane i holds component i, starting from y = L^-1 rhs (row N of the factor); branch-free
             {
                 double bi = sm.Lf[NK + ln];
@@ -1279,8 +1309,8 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             for (int o = 16; o > 0; o >>= 1) v2t += __shfl_xor_sync(FULL, v2t, o);
             vmt = wmax(vmt);
             if (v2t < sm.cold[C_ST_V2] * (1.0 - 1e-12)) { lm_accept = true; break; }
-            S.lm_lambda *= 10.0;
-            if (S.lm_lambda > 1e12) break;
+            lam *= 10.0;
+            if (lam > 1e12) break;
         }
         if (S.status == -3) break;
         if (resto) {
@@ -1288,14 +1318,18 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
                 const double dn = wmax(lane < N ? fabs(sm.dz[ln]) : 0.0);
                 sm.zc[ln] = sm.zt[ln];
                 S.iters++;
-                S.lm_lambda = fmax(S.lm_lambda * 0.2, 1e-12);
+                lam = fmax(lam * 0.2, 1e-12);
                 const double v2c = sm.cold[C_ST_V2];
-                if (v2c - v2t <= 1e-4 * v2c) S.acc_cnt++; else S.acc_cnt = 0;
-                const bool crawl = S.nresto >= 2 && S.v2_h2 - v2t <= DCBF_RESTO_WINDOW * S.v2_h2;
-                S.v2_h2 = S.v2_h1; S.v2_h1 = v2c; S.nresto++;
-                if ((dn < 1e-12 || S.acc_cnt >= 2 || crawl) && vmt > sm.cold[C_RESTO_TARGET]) S.lm_lambda = 1e13;
+                if (v2c - v2t <= 1e-4 * v2c) S.acc_cnt = S.acc_cnt < 31 ? S.acc_cnt + 1 : 31; else S.acc_cnt = 0;
+                const double h1 = sm.cold[C_V2_H1], h2 = sm.cold[C_V2_H2];
+                const bool crawl = S.nresto >= 2 && h2 - v2t <= DCBF_RESTO_WINDOW * h2;
+                __syncwarp();   // every lane has read the window before anyone shifts it
+                sm.cold[C_V2_H2] = h1; sm.cold[C_V2_H1] = v2c;
+                if (S.nresto < 3) S.nresto = S.nresto + 1;
+                if ((dn < 1e-12 || S.acc_cnt >= 2 || crawl) && vmt > sm.cold[C_RESTO_TARGET]) lam = 1e13;
             }
-            __syncwarp();
+            __syncwarp();   // (also: every lane has read the old lambda at the top of this step)
+            sm.cold[C_LM_LAMBDA] = lam;
             continue;
         }
         // ---- direction pass (main phase): ds, dz_L, dz_U, step sizes -----------------------------------------------------------
@@ -1383,25 +1417,25 @@ __device__ void solve_warp(const BatchIn &in, int b, int lane, int wid, int leg,
             const bool sw = dphi < 0.0 && theta <= sm.cold[C_THETA_MIN] && switch_cond_fast(alpha, -dphi, theta);
             if (sw) { if (ph_t <= phi + 1e-8 * alpha * dphi + eps_phi) accepted = 1; }
             else if (th_t <= (1.0 - 1e-5) * theta || ph_t <= phi - 1e-5 * theta + eps_phi) accepted = 2;
-            if (accepted) { carry_log = lg_t; break; }
+            if (accepted) { sm.cold[C_CARRY_LOG] = lg_t; break; }
         }
         if (accepted != 1) {   // filter augmentation (also before entering restoration)
             const int slot = S.nf < DCBF_FILT ? S.nf : (S.iters % DCBF_FILT);
             if (lane == 0) { sm.filt_th[slot] = (1.0 - 1e-5) * theta; sm.filt_ph[slot] = phi - 1e-5 * theta; }
-            if (S.nf < DCBF_FILT) S.nf++;
+            if (S.nf < DCBF_FILT) S.nf = S.nf + 1;
             __syncwarp();
         }
         if (!accepted) {
             const double vm = sm.cold[C_ST_VMAX];
-            S.phase = PH_RESTO; sm.cold[C_RESTO_ENTRY] = vm; sm.cold[C_RESTO_TARGET] = fmax(0.1 * vm, 1e-9); S.lm_lambda = 1e-4; S.acc_cnt = 0; S.nresto = 0;
+            S.phase = PH_RESTO; sm.cold[C_RESTO_ENTRY] = vm; sm.cold[C_RESTO_TARGET] = fmax(0.1 * vm, 1e-9); sm.cold[C_LM_LAMBDA] = 1e-4; S.acc_cnt = 0; S.nresto = 0;
             S.iters++;
             continue;
         }
         sm.zc[ln] = sm.zt[ln];
         __syncwarp();
-        S.alpha = alpha; S.alpha_z = az; S.pending = true;
+        sm.cold[C_ALPHA] = alpha; sm.cold[C_ALPHA_Z] = az; S.pending = true;
         nodes_valid = true; carry_ok = true;   // the accepted trial staged the nodes (with Hessian terms) and the barrier sum of the new point
-        if (alpha < P.tiny_alpha && sm.cold[C_ST_VMAX] > P.constr_viol_tol) S.tiny++; else S.tiny = 0;
+        if (alpha < P.tiny_alpha && sm.cold[C_ST_VMAX] > P.constr_viol_tol) S.tiny = S.tiny < 15 ? S.tiny + 1 : 15; else S.tiny = 0;
         S.iters++;
     }
     // every exit leaves the loop right after a full pass (or before any trial), so the node data are the rollout of the final iterate
