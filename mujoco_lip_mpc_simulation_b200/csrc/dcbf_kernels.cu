@@ -50,14 +50,15 @@ struct dcbf_ctx {
     int *d_counter;          // work counters of the persistent warp kernels (one per concurrently running launch)
     double *d_tick; size_t tick_cap;   // scratch of dcbf_tick: [x_next | warm | x_plan | p_plan] when the caller passes NULL
     double *d_flow;                    // cosh / sinh table of pos_det_kernel (2 x 41)
-    int *d_order; size_t order_cap;   // size-class split of obstacle-selecting formulations: [counts(2) | small list | large list]
-    cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
+    int *d_order; size_t order_cap;   // size-class split of obstacle-selecting formulations: [counts(3) + pad | class 0 list | class 1 list | class 2 list]
+    cudaStream_t aux_stream, aux_stream2; cudaEvent_t ev_fork, ev_join, ev_join2;
     int split_classes;   // smallest batch that is split by size class (env DCBF_SPLIT; 0 = never)
     int *d_sched; size_t sched_cap;   // longest-expected-first order of a batch: [counts(16) | rank(B) | order(B)]
     int sched_min_batch;              // smallest batch that is ordered (env DCBF_ORDER; 0 = never)
     int sched_select;                 // order obstacle-selecting formulations too (env DCBF_ORDER_SELECT)
     int zero_copy;                    // dcbf_solve_host reads / writes page-locked caller buffers from the kernels (env DCBF_ZEROCOPY)
     int dd_generic;                   // differential drive: keep the generic two-slot kernel (env DCBF_DD_GENERIC=1; A/B comparisons and tests)
+    int lipl_class;                   // size-class split: a class of its own for the problems wp::LipL covers (env DCBF_LIPL; 0 = two classes)
     int slots_per_sm;                 // cap on the resident CTAs per SM of the persistent warp kernels (env DCBF_SLOTS; 0 = what the kernel allows; occupancy probes)
 };
 
@@ -121,9 +122,19 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
 // ---------------------------------------------------------------------------------------------------------------
 // One warp per CTA: the block scheduler hands a freed warp slot to the next problem (iteration counts differ by 3x), and the
 // scratch lives in static shared memory.
+// Resident CTAs (= warps) per SM the kernels are built for (register budget 64 K / (32 x CTAs)):
+//   one slot (sig_step, small modi class): 16 warps at 128 registers -- without spills since the per-lane invariants are recomputed
+//   (wp::LaneRefresh) and the cold solver state lives in shared memory; 13.4 KB of shared memory per CTA let 16 CTAs fit;
+//   generic two / four slots: 8 warps at 255 registers;  typed turn-row slot (wp::LipL): 12 warps at 168 registers.
 #ifndef DCBF_WARP_MIN_CTAS
-#define DCBF_WARP_MIN_CTAS(NS) (((NS) == 1 ? 16 : 8) / wp::Wpc<wp::LipW, NS>::v)   /* 16 / 8 / 8 warps per SM: register budget 128 / 255 / 255.  One slot: 128 registers without spills since the per-lane invariants are recomputed (wp::LaneRefresh) and the cold solver state lives in shared memory; 13.4 KB of shared memory per CTA let 16 CTAs fit */
+#define DCBF_WARP_MIN_CTAS(NS) (((NS) == 1 ? 16 : 8) / wp::Wpc<wp::LipW, NS>::v)
 #endif
+#ifndef DCBF_LIPL_MIN_CTAS
+#define DCBF_LIPL_MIN_CTAS 12
+#endif
+template <class M, int NS> struct MinCtas;
+template <int NS> struct MinCtas<wp::LipW, NS> { static constexpr int v = DCBF_WARP_MIN_CTAS(NS); };
+template <int NS> struct MinCtas<wp::LipL, NS> { static constexpr int v = DCBF_LIPL_MIN_CTAS; };
 #ifndef DCBF_WARP_GRID_CAP
 #define DCBF_WARP_GRID_CAP 64   /* CTAs per SM in the grid (grid-stride loop beyond); 0 = one CTA per problem */
 #endif
@@ -189,8 +200,8 @@ __global__ void sched_scatter_kernel(int B, const int *__restrict__ counts, cons
 // Size classes for formulations with obstacle selection (MPC_LIP_modi.py:325-338): the number of rows of a problem is known
 // once its obstacles are selected, and half of the config-3 scenarios fit the 32-row kernel.  One thread per scenario counts the
 // selected obstacles and appends the scenario to the list of its class.
-__global__ void classify_lip_kernel(dcbf_params P, int B, BatchIn in, int small_max_obs, int *__restrict__ counts,
-                                    int *__restrict__ small, int *__restrict__ large) {
+__global__ void classify_lip_kernel(dcbf_params P, int B, BatchIn in, int max_obs0, int max_obs1, int *__restrict__ counts,
+                                    int *__restrict__ list0, int *__restrict__ list1, int *__restrict__ list2) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double px = in.x0[5 * (size_t)b], py = in.x0[5 * (size_t)b + 1];
@@ -207,23 +218,23 @@ __global__ void classify_lip_kernel(dcbf_params P, int B, BatchIn in, int small_
         const double *o = elp + DCBF_ELP_REC * j;
         if ((px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]) - o[6] <= P.detect_sq) ks++;
     }
-    const bool is_small = ks <= small_max_obs;
+    const int cls = ks <= max_obs0 ? 0 : (ks <= max_obs1 ? 1 : 2);
     // warp-aggregated append
     const unsigned act = __activemask();
-    const unsigned ms = __ballot_sync(act, is_small), ml = act & ~ms;
+    const unsigned m0 = __ballot_sync(act, cls == 0), m1 = __ballot_sync(act, cls == 1);
     const int lane = threadIdx.x & 31;
-    const unsigned mine = is_small ? ms : ml;
+    const unsigned mine = cls == 0 ? m0 : (cls == 1 ? m1 : act & ~(m0 | m1));
     const int leader = __ffs(mine) - 1;
     int base = 0;
-    if (lane == leader) base = atomicAdd(&counts[is_small ? 0 : 1], __popc(mine));
+    if (lane == leader) base = atomicAdd(&counts[cls], __popc(mine));
     base = __shfl_sync(mine, base, leader);
-    (is_small ? small : large)[base + __popc(mine & ((1u << lane) - 1u))] = b;
+    (cls == 0 ? list0 : (cls == 1 ? list1 : list2))[base + __popc(mine & ((1u << lane) - 1u))] = b;
 }
 
 // lane 0 stages the scenario state, the start point z0 (from the reference's u0) and the free response of the LIP
 // (positions / velocities at nodes 1..3 for zero foot placements) in shared memory
-template <int NS>
-__device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<wp::LipW, NS> &sm, const double *x0, const double *graw, const double *u0, int lane) {
+template <class M, int NS>
+__device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<M, NS> &sm, const double *x0, const double *graw, const double *u0, int lane) {
     if (lane == 0) {
         double z[9];
         lip_z_from_u(K, x0, u0, z);
@@ -246,15 +257,15 @@ __device__ __forceinline__ void stage_problem(const Consts &K, wp::WarpShared<wp
 
 // Persistent CTAs of WPC warps; every warp pulls its next problem from `counter` (problem i of the index list `order` when the
 // batch was split by size class) and the warps of a CTA meet at the top of every interior-point iteration (wp::cta_tick).
-template <int NS>
-__global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_CTAS(NS)) solve_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out,
+template <class M, int NS>
+__global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, MinCtas<M, NS>::v) solve_lip_warp_kernel(dcbf_params P, Consts K, const wp::WarpTables *tab, int B, BatchIn in, SolveOut out,
                                                                                        const int *__restrict__ order, const int *__restrict__ count, int *counter) {
-    constexpr int W = wp::Wpc<wp::LipW, NS>::v;
+    constexpr int W = wp::Wpc<M, NS>::v;
     const int lane = wp::lane_id(), wid = W > 1 ? wp::warp_in_cta() : 0;
-    wp::WarpShared<wp::LipW, NS> &sm = wp::g_sm<wp::LipW, NS>[wid];
+    wp::WarpShared<M, NS> &sm = wp::g_sm<M, NS>[wid];
     const wp::CtaShared &cs_ = wp::g_cs;
     const int n = count ? *count : B;
-    wp::stage_cta<wp::LipW, NS>(P, K, tab, lane, wid);
+    wp::stage_cta<M, NS>(P, K, tab, lane, wid);
     for (;;) {
         const int i_ = wp::next_problem(counter, lane);
         if (i_ >= n) break;
@@ -270,14 +281,14 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
 #pragma unroll
             for (int i = 0; i < 15; i++) u0[i] = sm.dz[5 + i];
             g[0] = sm.dz[20]; g[1] = sm.dz[21];
-            stage_problem<NS>(cs_.K, sm, x0, g, u0, 0);
+            stage_problem<M, NS>(cs_.K, sm, x0, g, u0, 0);
         } else {
             __syncwarp();
         }
         const int leg = in.leg ? in.leg[b] : 1;
         const int md = in.mode ? in.mode[b] : 2;   // 0: warm start = previous plan verbatim, 1: shifted plan, 2: cold start
         wp::WState S;
-        wp::solve_warp<wp::LipW, NS>(P, in, b, lane, wid, leg, S, md == 0 ? P.mu_warm : (md == 1 ? P.mu_shift : P.mu_init));
+        wp::solve_warp<M, NS>(P, in, b, lane, wid, leg, S, md == 0 ? P.mu_warm : (md == 1 ? P.mu_shift : P.mu_init));
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
         if (lane < 15) {
             const double v = sm.nd.nodes[lane / 5 + 1][lane % 5];
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
             if (out.obj) out.obj[b] = sm.cold[wp::C_OBJ];
             if (out.viol) out.viol[b] = sm.cold[wp::C_VIOL];
 #endif
-            if (out.close) out.close[b] = wp::w_close<NS>(P, sm) ? 1 : 0;
+            if (out.close) out.close[b] = wp::w_close<M, NS>(P, sm) ? 1 : 0;
         }
         __syncwarp();
     }
@@ -360,7 +371,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
 #pragma unroll
             for (int i = 0; i < 15; i++) u0[i] = x0[i % 5];                  // cold start [x, x, x]
             g[0] = in.goal[2 * (size_t)b]; g[1] = in.goal[2 * (size_t)b + 1];
-            stage_problem<NS>(cs_.K, sm, x0, g, u0, 0);
+            stage_problem<wp::LipW, NS>(cs_.K, sm, x0, g, u0, 0);
         } else {
             __syncwarp();
         }
@@ -370,7 +381,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
             wp::solve_warp<wp::LipW, NS>(P, in, b, lane, wid, leg, S, st == 0 ? P.mu_init : P.mu_shift);
             tot += S.iters;
             if (S.status == 2) ninf++;
-            const bool close = wp::w_close<NS>(P, sm);
+            const bool close = wp::w_close<wp::LipW, NS>(P, sm);
             if (out.traj && lane < 8) {
                 double v;
                 if (lane < 5) v = sm.nd.nodes[1][lane];
@@ -385,7 +396,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<wp::LipW, NS>::v, DCBF_WARP_MIN_C
                 double x0[5], u0[15], g[2] = {sm.graw[0], sm.graw[1]};
 #pragma unroll
                 for (int j = 0; j < 5; j++) { u0[j] = sm.nd.nodes[2][j]; u0[5 + j] = sm.nd.nodes[3][j]; u0[10 + j] = sm.nd.nodes[3][j]; x0[j] = sm.nd.nodes[1][j]; }
-                stage_problem<NS>(cs_.K, sm, x0, g, u0, 0);
+                stage_problem<wp::LipW, NS>(cs_.K, sm, x0, g, u0, 0);
             } else {
                 __syncwarp();
             }
@@ -667,7 +678,7 @@ static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t 
     return DCBF_OK;
 }
 
-template <int NS>
+template <int NS, class M = wp::LipW>
 static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st, int slot = 0, const int *order = nullptr,
                              const int *count = nullptr) {
     if (!order) {
@@ -676,8 +687,8 @@ static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const Solv
     }
     int *counter = ctx->d_counter + 1 + slot;
     CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    const int grid = warp_grid<wp::LipW, NS>(ctx, B, DCBF_WARP_MIN_CTAS(NS));
-    solve_lip_warp_kernel<NS><<<grid, 32 * wp::Wpc<wp::LipW, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, count, counter);
+    const int grid = warp_grid<M, NS>(ctx, B, MinCtas<M, NS>::v);
+    solve_lip_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, count, counter);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -695,32 +706,45 @@ static int launch_solve_dd_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const S
     return DCBF_OK;
 }
 
-// obstacle-selecting formulations: split the batch by row count and run the 32-row kernel and the NS-slot kernel side by side
+// obstacle-selecting formulations: split the batch by row count into three classes that run side by side on forked streams --
+//   class 0: all rows fit one slot (with the fen rows: up to four selected obstacles)            -> one-slot kernel
+//   class 1: the non-linear rows fit one slot (five selected obstacles), turn rows in a typed slot -> wp::LipL
+//   class 2: everything else                                                                      -> generic NS-slot kernel
 template <int NS>
 static int launch_solve_split(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
     if (ctx->order_cap < (size_t)B) {
         CK(cudaFree(ctx->d_order));
         ctx->d_order = nullptr; ctx->order_cap = 0;
-        CK(cudaMalloc(&ctx->d_order, sizeof(int) * (2 * (size_t)B + 2)));
+        CK(cudaMalloc(&ctx->d_order, sizeof(int) * (3 * (size_t)B + 4)));
         ctx->order_cap = (size_t)B;
     }
-    int *counts = ctx->d_order, *small = ctx->d_order + 2, *large = small + ctx->order_cap;
-    const int small_max_obs = 32 / 3 - (ctx->P.has_fen ? 6 : 4);
-    CK(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
-    classify_lip_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->P, B, in, small_max_obs, counts, small, large);
+    int *counts = ctx->d_order, *list0 = ctx->d_order + 4, *list1 = list0 + ctx->order_cap, *list2 = list1 + ctx->order_cap;
+    const int fixed = ctx->P.has_fen ? 6 : 4;          // rows of a step besides the D-CBF rows (one of them the linear turn row)
+    const int max_obs0 = 32 / 3 - fixed, max_obs1 = ctx->lipl_class ? 32 / 3 - (fixed - 1) : max_obs0;
+    CK(cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
+    classify_lip_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->P, B, in, max_obs0, max_obs1, counts, list0, list1, list2);
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(ctx->d_counter + 2, 0, sizeof(int), st));   // the aux stream's counter is cleared before the fork
+    CK(cudaMemsetAsync(ctx->d_counter + 2, 0, 2 * sizeof(int), st));   // the aux streams' counters are cleared before the fork
     CK(cudaEventRecord(ctx->ev_fork, st));
     CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-    int rc = launch_solve_warp<NS>(ctx, B, in, out, st, 0, large, counts + 1);          // the long problems first
+    if (ctx->lipl_class) CK(cudaStreamWaitEvent(ctx->aux_stream2, ctx->ev_fork, 0));
+    int rc = launch_solve_warp<NS>(ctx, B, in, out, st, 0, list2, counts + 2);          // the long problems first
     if (rc != DCBF_OK) return rc;
+    if (ctx->lipl_class) {
+        const int grid = warp_grid<wp::LipL, 2>(ctx, B, MinCtas<wp::LipL, 2>::v);
+        solve_lip_warp_kernel<wp::LipL, 2><<<grid, 32 * wp::Wpc<wp::LipL, 2>::v, 0, ctx->aux_stream2>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, list1, counts + 1, ctx->d_counter + 3);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_join2, ctx->aux_stream2));
+        ctx->launches++;
+    }
     {
-        const int grid = warp_grid<wp::LipW, 1>(ctx, B, DCBF_WARP_MIN_CTAS(1));
-        solve_lip_warp_kernel<1><<<grid, 32 * wp::Wpc<wp::LipW, 1>::v, 0, ctx->aux_stream>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, small, counts, ctx->d_counter + 2);
+        const int grid = warp_grid<wp::LipW, 1>(ctx, B, MinCtas<wp::LipW, 1>::v);
+        solve_lip_warp_kernel<wp::LipW, 1><<<grid, 32 * wp::Wpc<wp::LipW, 1>::v, 0, ctx->aux_stream>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, list0, counts, ctx->d_counter + 2);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (ctx->lipl_class) CK(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
     ctx->launches += 2;
     return DCBF_OK;
 }
@@ -807,13 +831,15 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
         delete W;
         if (!ok) { cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); delete ctx; return DCBF_ERR_CUDA; }
     }
-    { const char *sp = getenv("DCBF_SPLIT"); ctx->split_classes = sp ? atoi(sp) : 16384; }
+    { const char *sp = getenv("DCBF_SPLIT"); ctx->split_classes = sp ? atoi(sp) : 8192; }   // measured: 8192 scenarios 3.78 -> 3.20 ms, 4096 scenarios 1.89 -> 2.09 ms
     { const char *sp = getenv("DCBF_ORDER"); ctx->sched_min_batch = sp ? atoi(sp) : 2048; }
     { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }
     { const char *sp = getenv("DCBF_DD_GENERIC"); ctx->dd_generic = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_SLOTS"); ctx->slots_per_sm = sp ? atoi(sp) : 0; }
+    { const char *sp = getenv("DCBF_LIPL"); ctx->lipl_class = sp ? atoi(sp) : 1; }
     if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->aux_stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DCBF_ERR_CUDA; }
     ctx->warp_max_batch = wb ? atoi(wb) : 0x7fffffff;   // round 2: the warp kernels win at every batch size (profiles/r02_summary.md)
@@ -830,6 +856,8 @@ void dcbf_destroy(dcbf_ctx *ctx) {
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux_stream2) cudaStreamDestroy(ctx->aux_stream2);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
@@ -933,7 +961,7 @@ static int solve_impl(dcbf_ctx *ctx, int32_t B, const double *x0, const double *
     else if (dd) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
     else if (use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);
-        const bool split = ns > 1 && ctx->P.select_obs && ctx->split_classes > 0 && B >= ctx->split_classes;   // measured: pays from ~16 k scenarios
+        const bool split = ns > 1 && ctx->P.select_obs && ctx->split_classes > 0 && B >= ctx->split_classes;   // measured: pays from ~8 k scenarios
         const int rc = ns == 1 ? launch_solve_warp<1>(ctx, B, in, out, st)
                      : split ? (ns == 2 ? launch_solve_split<2>(ctx, B, in, out, st) : launch_solve_split<4>(ctx, B, in, out, st))
                              : (ns == 2 ? launch_solve_warp<2>(ctx, B, in, out, st) : launch_solve_warp<4>(ctx, B, in, out, st));

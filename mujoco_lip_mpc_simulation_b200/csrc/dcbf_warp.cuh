@@ -50,6 +50,7 @@ struct WarpTables {
     double sm_dd[24];         // DD: constant Hessian pattern of the control-smoothness cost (per unit 2 w_t)
     int desc_lin[64];         // DD, linear rows in their own slot (DdL): closed-form contribution of the four linear rows of a step to the
                               // lane's entry: flags (bits 0..4, see DdWT::lin_term) | source row << 8 | first column << 16
+    int desc_lin_lip[96];     // LIP, turn rows in their own slot (LipL): the entry gets staged weight [source row][column] (bit 0 set) or nothing
 };
 
 // variable order (fx0, fy0, fx1, fy1, fx2, fy2, t0, t1, t2): step of a variable
@@ -96,6 +97,18 @@ inline bool build_warp_tables(const Consts &k, WarpTables &W) {
     }
     if (n != 72) return false;
     for (int t = 0; t < 96; t++) W.desc[t] = t < 72 ? (ent[t].rowP | ent[t].rowQ << 8 | ent[t].cls << 16 | ent[t].out << 20) : -1;
+    // LipL: the turn row of step i (column 32 + i of the staged weights) has the gradient e_{6+i}: sigma goes to the diagonal entry of
+    // variable 6 + i, the weight rows w1 / binv / y (staged rows 19 + v) to component 6 + i of the three J^T vectors
+    for (int t = 0; t < 96; t++) {
+        int d = 0;
+        if (t < 72) {
+            if (ent[t].rowP < 18) {
+                const int a = ent[t].rowP - 9, b = ent[t].rowQ;
+                if (a == b && a >= 6) d = 1 | 18 << 8 | (32 + a - 6) << 16;
+            } else if (ent[t].rowQ >= 6) d = 1 | ent[t].rowP << 8 | (32 + ent[t].rowQ - 6) << 16;
+        }
+        W.desc_lin_lip[t] = d;
+    }
     // ---- Lagrangian Hessian map: sources = NH[kn][0..7] (xx, xy, yy, xt, yt, tt, vxt, vyt) for kn = 1..3, then legy[0..2] --
     double T[24][9];
     build_feature_map(k, T);
@@ -222,7 +235,8 @@ struct DdNodeData {
 template <class M, int NS>
 struct alignas(16) WarpShared {
     static constexpr int N = M::N;
-    static constexpr int RP = 32 * NS + 2;   // padded row length: class starts / ends are rounded to even rows
+    // padded row length (a linear slot only stages its first NLINP columns)
+    static constexpr int RP = (M::LIN2 ? 32 + M::NLINP : 32 * NS) + 2;
     static constexpr int NST = 2 * N + 4;
     double ST[NST][RP];      // staged rows, transposed: [0, N) gradient, [N, 2N) sigma * gradient, then sigma, w1, binv, y
     double HQ[M::LIN2 ? 32 : 32 * NS][M::NHQ];   // y * (second-order / first-order row coefficients) of the D-CBF rows
@@ -262,7 +276,9 @@ struct CtaShared {
 #ifndef DCBF_WPC_DD
 #define DCBF_WPC_DD(NS) ((NS) == 2 ? 2 : 1)
 #endif
-struct LipW;
+template <bool LIN> struct LipWT;
+using LipW = LipWT<false>;   // LIP formulations, generic row slots
+using LipL = LipWT<true>;    // LIP formulations, at most 32 non-linear rows: they fill slot 0, the three turn rows (linear) get slot 1
 template <bool LIN> struct DdWT;
 using DdW = DdWT<false>;   // differential drive, generic row slots
 using DdL = DdWT<true>;    // differential drive, at most 10 obstacles: D-CBF rows in slot 0, the twelve linear rows in slot 1
@@ -277,8 +293,19 @@ template <int NS> struct Wpc<DdL, NS> { static constexpr int v = DCBF_WPC_DDL; }
 #ifndef DCBF_LANE_REFRESH
 #define DCBF_LANE_REFRESH 1
 #endif
+#ifndef DCBF_REFRESH_BOUNDS
+#define DCBF_REFRESH_BOUNDS(NS) ((NS) > 1)
+#endif
 template <class M, int NS> struct LaneRefresh { static constexpr bool v = false; };
 template <> struct LaneRefresh<LipW, 1> { static constexpr bool v = DCBF_LANE_REFRESH != 0; };
+#ifndef DCBF_LANE_REFRESH_LIPL
+#define DCBF_LANE_REFRESH_LIPL 0
+#endif
+template <> struct LaneRefresh<LipL, 2> { static constexpr bool v = DCBF_LANE_REFRESH_LIPL != 0; };
+#ifndef DCBF_LANE_REFRESH_LIP2
+#define DCBF_LANE_REFRESH_LIP2 0
+#endif
+template <> struct LaneRefresh<LipW, 2> { static constexpr bool v = DCBF_LANE_REFRESH_LIP2 != 0; };
 
 // per-problem scratch (one per warp) and the constants are static shared-memory objects, so every function sees them as
 // shared-space symbols (no generic pointers through the out-of-line calls)
@@ -402,27 +429,33 @@ __device__ __forceinline__ int stage_obstacles(const dcbf_params &P, WarpShared<
 // ===============================================================================================================
 // LIP model (sig_step / modi): z = (fx0, fy0, fx1, fy1, fx2, fy2, t0, t1, t2)
 // ===============================================================================================================
-struct LipW {
+template <bool LIN>
+struct LipWT {
+    using Self = LipWT<LIN>;
     static constexpr int N = 9;
     static constexpr int NHQ = 3;
     static constexpr int NROUND = 3;
     static constexpr bool HAS_CURV = false;
     static constexpr bool ROLL2 = false;   // two-slot kernel: unrolled slot loop, row state in registers (measured faster for modi)
-    static constexpr bool LIN2 = false;
+    static constexpr bool LIN2 = LIN;      // slot 1 holds the three turn rows only (closed-form contributions, 32-column dot products)
+    static constexpr int NLINP = 4;        // columns of the linear slot that are staged (rows 32..34, padded to an even count)
     using NodeData = LipNodeData;
     enum { RT_NONE = 0, RT_CBF, RT_VBX, RT_VBY, RT_LEG, RT_DTH, RT_FENP, RT_FENM };
 
     static __device__ __forceinline__ const int *desc(const WarpTables *tab) { return tab->desc; }
+    static __device__ __forceinline__ const int *desc_lin(const WarpTables *tab) { return tab->desc_lin_lip; }
     static __device__ __forceinline__ int rows_per_step(const dcbf_params &P, int Ks) { return Ks + (P.has_fen ? 6 : 4); }
     static __device__ __forceinline__ int class_start(int cls, int, int ms) { return cls * ms; }   // first row that can touch a variable of step cls
+    // rows of a step that sit in the generic slots (LipL: all but the turn row) and the offset of the fen rows behind the D-CBF rows
+    static __device__ __forceinline__ int slot_rows_per_step(int ms) { return LIN ? ms - 1 : ms; }
 
     // problem setup: obstacle selection + compaction, detour heuristic (MPC_LIP_sig_step.py:229-253), node 0
     template <int NS>
-    static __device__ __forceinline__ int setup(WarpShared<LipW, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane, unsigned *mask_out = nullptr) {
+    static __device__ __forceinline__ int setup(WarpShared<Self, NS> &sm, const dcbf_params &P, const BatchIn &in, int b, int lane, unsigned *mask_out = nullptr) {
         const double px = sm.x0[0], py = sm.x0[1];
         double rec[6];
         bool sel, is_c;
-        const int Ks = stage_obstacles<LipW, NS>(P, sm, in, b, lane, px, py, rec, sel, is_c, mask_out);
+        const int Ks = stage_obstacles<Self, NS>(P, sm, in, b, lane, px, py, rec, sel, is_c, mask_out);
         bool hit = false;
         double ngx = 0.0, ngy = 0.0;
         const double gx = sm.graw[0], gy = sm.graw[1];
@@ -459,9 +492,26 @@ struct LipW {
     }
 
     // step-major row order: step i holds  [D-CBF x Ks, v_bx, v_by, leg, turn, (fen+, fen-)]
+    // LipL: slot 0 holds  [D-CBF x Ks, v_bx, v_by, leg, (fen+, fen-)]  per step (at most 32 rows), the turn row of step i is row 32 + i
     static __device__ __forceinline__ RowDesc row_desc(int r, int Ks, int ms, int m) {
         RowDesc d;
         d.type = RT_NONE; d.step = 0; d.obs = 0; d.cls = 9;
+        if (LIN) {
+            const int ms0 = ms - 1;
+            if (r < 32) {
+                if (r < 3 * ms0) {
+                    d.step = r / ms0;
+                    const int w = r - d.step * ms0;
+                    if (w < Ks) { d.type = RT_CBF; d.obs = w; d.cls = d.step; }
+                    else {
+                        const int k = w - Ks;
+                        d.type = k < 3 ? RT_VBX + k : RT_FENP + (k - 3);
+                        d.cls = d.type == RT_LEG ? 6 + d.step : 3 + d.step;
+                    }
+                }
+            } else if (r < 35) { d.type = RT_DTH; d.step = r - 32; }
+            return d;
+        }
         if (r >= m) return d;
         d.step = r / ms;
         const int w = r - d.step * ms;
@@ -489,8 +539,21 @@ struct LipW {
         return b;
     }
 
+    // a turn row: the value of the linear form on z (the direction pass calls it on dz)
+    static __device__ __forceinline__ double eval_lin(const dcbf_params &, const RowDesc &rd, const double *z) {
+        return rd.type == RT_DTH ? z[6 + rd.step] : 0.0;
+    }
+    // closed-form contribution of the turn rows to the lane's entry of the assembled system (descriptor: WarpTables::desc_lin_lip)
+    template <int NS>
+    static __device__ __forceinline__ double lin_term(const WarpShared<Self, NS> &sm, const dcbf_params &, int dl) {
+        constexpr int RP = WarpShared<Self, NS>::RP;
+        DCBF_ASSERT(((dl >> 8) & 0xff) < (WarpShared<Self, NS>::NST) && (dl >> 16) < RP);
+        const double v = (&sm.ST[0][0])[((dl >> 8) & 0xff) * RP + (dl >> 16)];   // dl == 0 reads ST[0][0]: always initialised
+        return (dl & 1) ? v : 0.0;
+    }
+
     template <int NS, bool GRAD>
-    static __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<LipW, NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
+    static __device__ __forceinline__ void eval_row(const dcbf_params &P, const WarpShared<Self, NS> &sm, const RowDesc &rd, const double *z, RowEval &e) {
         e.c = 0.0;
         if (GRAD) { e.p0 = e.p1 = e.q0 = e.q1 = e.t_all = e.t_own = 0.0; e.hq0 = e.hq1 = e.hq2 = 0.0; }
         const int i = rd.step, kn = i + 1;
@@ -518,8 +581,8 @@ struct LipW {
 
     // transposed staging of one row: gradient, sigma * gradient (rows beyond m stage zeros), D-CBF curvature weights
     template <int NS>
-    static __device__ __forceinline__ void stage_row(WarpShared<LipW, NS> &sm, const CtaShared &cs_, const RowDesc &rd, const RowEval &e, double sig, double y, int r) {
-        constexpr int RP = WarpShared<LipW, NS>::RP;
+    static __device__ __forceinline__ void stage_row(WarpShared<Self, NS> &sm, const CtaShared &cs_, const RowDesc &rd, const RowEval &e, double sig, double y, int r) {
+        constexpr int RP = WarpShared<Self, NS>::RP;
         const double *ab = cs_.cab[rd.cls];
         const int i = rd.step;
         double *col = &sm.ST[0][r];
@@ -539,7 +602,7 @@ struct LipW {
     // trigonometry and objective terms; collective, out of line
     template <int NS>
     static __device__ __noinline__ void nodes(const double *z, int lane, int wid, double sf, bool want_hess) {
-        WarpShared<LipW, NS> &sm = g_sm<LipW, NS>[wid];
+        WarpShared<Self, NS> &sm = g_sm<Self, NS>[wid];
         const CtaShared &cs_ = g_cs;
         const dcbf_params &P = cs_.P;
         if (lane < 3) {
@@ -564,11 +627,11 @@ struct LipW {
 
     // objective value at the staged nodes and its gradient component for lane a < 9 (0 on the other lanes)
     template <int NS>
-    static __device__ __forceinline__ double objective(const WarpShared<LipW, NS> &sm) {
+    static __device__ __forceinline__ double objective(const WarpShared<Self, NS> &sm) {
         return sm.nd.nobj[1][0] + sm.nd.nobj[2][0] + sm.nd.nobj[3][0];
     }
     template <int NS>
-    static __device__ __forceinline__ double grad(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int lane, int ln) {
+    static __device__ __forceinline__ double grad(const WarpShared<Self, NS> &sm, const CtaShared &cs_, int lane, int ln) {
         // d node_kn / d foot_l = gx[kn-1-l],  d th_kn / d turn_l = 1; branch-free: lanes >= 9 compute on clamped indices, select 0
         const int l = ln < 6 ? ln >> 1 : ln - 6;
         const int c = ln < 6 ? 1 + (ln & 1) : 3;
@@ -582,7 +645,7 @@ struct LipW {
         return lane < 9 ? g : 0.0;
     }
     template <int NS>
-    static __device__ __forceinline__ void rescale_objective_hessian(WarpShared<LipW, NS> &sm, int lane, double sf) {
+    static __device__ __forceinline__ void rescale_objective_hessian(WarpShared<Self, NS> &sm, int lane, double sf) {
         if (lane < 3) {
 #pragma unroll
             for (int c = 4; c < 10; c++) sm.nd.nobj[lane + 1][c] *= sf;
@@ -591,17 +654,19 @@ struct LipW {
 
     // node Hessians -> the 27 sources of the Hessian table
     template <int NS>
-    static __device__ __forceinline__ void hess_sources(WarpShared<LipW, NS> &sm, const dcbf_params &P, int lane, int Ks, int ms) {
+    static __device__ __forceinline__ void hess_sources(WarpShared<Self, NS> &sm, const dcbf_params &P, int lane, int Ks, int ms_all) {
         const double gm1 = P.gamma - 1.0;
         const double *yv = sm.ST[2 * N + 3];
         const bool has_fen = P.has_fen != 0;
+        const int ms = slot_rows_per_step(ms_all);   // rows of a step in the generic slots
+        constexpr int FEN = LIN ? 3 : 4;             // fen+ / fen- behind the D-CBF rows of their step (LipL has no turn row in between)
         const int lp = lane - 16;
         if ((unsigned)lp < 9u) {   // position block on lanes 16..24: node kn = lp/3 + 1, component lp % 3
             const int kn = lp / 3 + 1, c = lp % 3;
             double acc = sm.nd.nobj[kn][4 + c];
             const int r0 = (kn - 1) * ms, r1 = kn < 3 ? kn * ms : r0;
             const double g1 = kn < 3 ? gm1 : 0.0;
-            if (NS == 1) {   // at most six D-CBF rows per step: fixed trip count, rows beyond Ks masked (no loop bookkeeping)
+            if (NS == 1 || LIN) {   // at most six D-CBF rows per step: fixed trip count, rows beyond Ks masked (no loop bookkeeping)
 #pragma unroll
                 for (int j = 0; j < KsMax<1>::v; j++) {
                     const int jj = j < Ks ? j : 0;
@@ -615,7 +680,7 @@ struct LipW {
         } else if (lane < 3) {     // heading / velocity entries of node kn = lane + 1 (rows of step kn - 1)
             const int kn = lane + 1, i = kn - 1, base = i * ms + Ks;
             double Yx = yv[base], Yy = yv[base + 1];
-            if (has_fen) Yx += yv[base + 4] + yv[base + 5];
+            if (has_fen) Yx += yv[base + FEN] + yv[base + FEN + 1];
             const double sn = sm.nd.trig[kn][0], cs = sm.nd.trig[kn][1];
             const double vx = sm.nd.nodes[kn][2], vy = sm.nd.nodes[kn][3];
             const double vbx = cs * vx + sn * vy, vby = -sn * vx + cs * vy;
@@ -627,12 +692,12 @@ struct LipW {
         }
     }
     template <int NS>
-    static __device__ __forceinline__ void hess_curvature(WarpShared<LipW, NS> &, int, double, const double *) {}
+    static __device__ __forceinline__ void hess_curvature(WarpShared<Self, NS> &, int, double, const double *) {}
     // Lagrangian Hessian of matrix entry e (packed index) through the table.  TERMS = the largest number of table terms an entry of
     // this assembly round has (round 0 holds the entries among the variables of step 0: up to 6; round 1: 2; round 2 has vector
     // entries only) -- build_warp_tables() verifies the bound
     template <int NS>
-    static __device__ __forceinline__ double hess_entry(const WarpShared<LipW, NS> &sm, const CtaShared &cs_, int e, double sf, int terms, int) {
+    static __device__ __forceinline__ double hess_entry(const WarpShared<Self, NS> &sm, const CtaShared &cs_, int e, double sf, int terms, int) {
         double acc = 0.0;
 #pragma unroll
         for (int h = 0; h < NHT; h++) if (h < terms) { DCBF_ASSERT(e >= 0 && e < 48 && cs_.hs[h][e] <= NSRC); acc = fma(cs_.hc[h][e], sm.nd.NHf[cs_.hs[h][e]], acc); }   // `terms` is a constant after unrolling
@@ -679,7 +744,9 @@ struct DdWT {
     using NodeData = DdNodeData;
     enum { RT_NONE = 0, RT_CBF, RT_FENP, RT_FENM, RT_BV, RT_BW };
 
+    static constexpr int NLINP = 32;       // every column of the linear slot is staged (rows without a type stage zeros)
     static __device__ __forceinline__ const int *desc(const WarpTables *tab) { return tab->desc_dd; }
+    static __device__ __forceinline__ const int *desc_lin(const WarpTables *tab) { return tab->desc_lin; }
     static __device__ __forceinline__ int rows_per_step(const dcbf_params &, int Ks) { return Ks + 4; }
     static __device__ __forceinline__ int class_start(int cls, int Ks, int) { return cls * Ks; }
 
@@ -1025,7 +1092,7 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
     for (int t = 0; t < M::NROUND; t++) hab[t] = dsc[t] >= 0 ? (((dsc[t] & 0xff) - N) & 0xff) | (((dsc[t] >> 8) & 0xff) << 8) : 0;
     int dlin[M::NROUND];
 #pragma unroll
-    for (int t = 0; t < M::NROUND; t++) dlin[t] = M::LIN2 ? __ldg(cs_.tab->desc_lin + 32 * t + lane) : 0;
+    for (int t = 0; t < M::NROUND; t++) dlin[t] = M::LIN2 ? __ldg(M::desc_lin(cs_.tab) + 32 * t + lane) : 0;
     int ln = lane < N ? lane : N - 1;   // clamped lane: keeps the per-variable sections branch-free
     int rowbase = lane < N + 1 ? lane * (lane + 1) / 2 : 0;
     // ---- solver state ------------------------------------------------------------------------------------------------
@@ -1050,6 +1117,10 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
             lane = lane_id();
             ln = lane < N ? lane : N - 1;
             rowbase = lane < N + 1 ? lane * (lane + 1) / 2 : 0;
+            if (!ROLLED && DCBF_REFRESH_BOUNDS(NS)) {   // same for what is derived from the row bounds (relaxed bounds, pushes): opaque to the optimiser from here on
+#pragma unroll
+                for (int s = 0; s < NREG; s++) asm volatile("" : "+d"(rbA[s].lo), "+d"(rbA[s].hi));
+            }
         }
         if (Wpc<M, NS>::v > 1) cta_tick(1);   // the warps of the CTA start every iteration together (shared instruction fetch)
         const bool resto = S.phase == PH_RESTO;
@@ -1129,8 +1200,8 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
             }
             // stage the transposed row (rows beyond m stage zeros so that the dot products need no guards)
             if (!lin) M::template stage_row<NS>(sm, cs_, rd, e, sig, y, r);   // linear rows: only the four weights below are staged
-            {
-                DCBF_ASSERT(r >= 0 && r < 32 * NS && Ks >= 0 && Ks <= KsMax<NS>::v && m <= 32 * NS + (M::LIN2 ? 32 : 0));
+            if (!lin || lane < M::NLINP) {   // (a linear slot stages its first NLINP columns only)
+                DCBF_ASSERT(r >= 0 && r < RP - 2 && Ks >= 0 && Ks <= KsMax<NS>::v && m <= 32 * NS + (M::LIN2 ? 32 : 0));
                 double *col = &sm.ST[2 * N][r];
                 col[0] = sig; col[RP] = w1; col[2 * RP] = binv; col[3 * RP] = y;
             }
@@ -1441,8 +1512,8 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
     // every exit leaves the loop right after a full pass (or before any trial), so the node data are the rollout of the final iterate
 }
 
-template <int NS>
-__device__ __forceinline__ bool w_close(const dcbf_params &P, const WarpShared<LipW, NS> &sm) {
+template <class M, int NS>
+__device__ __forceinline__ bool w_close(const dcbf_params &P, const WarpShared<M, NS> &sm) {
     bool close = false;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -1464,7 +1535,7 @@ __device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K,
     for (int t = t0; t < NHT * 48 / 4; t += 32 * W)
         reinterpret_cast<unsigned *>(&g_cs.hs[0][0])[t] = __ldg(reinterpret_cast<const unsigned *>(&tab->hs[0][0]) + t);
     if constexpr (M::N == 6) { if (lane < 24) sm.nd.sm_dd[lane] = __ldg(&tab->sm_dd[lane]); }
-    for (int t = lane; t < 2 * WarpShared<M, NS>::NST; t += 32) sm.ST[t >> 1][32 * NS + (t & 1)] = 0.0;
+    for (int t = lane; t < 2 * WarpShared<M, NS>::NST; t += 32) sm.ST[t >> 1][WarpShared<M, NS>::RP - 2 + (t & 1)] = 0.0;
     __syncthreads();
 }
 

@@ -373,13 +373,16 @@ def test_host_buffer_entry_point_equals_device_entry_point(gpu):
 
 
 def test_size_class_split_is_transparent(gpu, monkeypatch):
-    """modi batches from 16 384 scenarios on are split by selected-obstacle count (classify pre-pass, 32-row kernel and two-slot
-    kernel on forked streams); every scenario must get the result of the unsplit launch"""
+    """modi batches from 8 192 scenarios on are split by selected-obstacle count (classify pre-pass; one-slot kernel, typed
+    turn-row slot kernel wp::LipL and generic two-slot kernel on forked streams).  With two classes (DCBF_LIPL=0) every scenario
+    gets the result of the unsplit launch bit for bit; the LipL class adds the turn rows to the condensed system in closed form
+    instead of through the dot products, i.e. in a different summation order: same status everywhere, same plans to rounding"""
     B = 16384
     sc = scenarios.make_batch("modi", B, seed=41)
     monkeypatch.setenv("DCBF_SPLIT", "0")
     ref = _solver(gpu, "modi", sc).solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
     monkeypatch.setenv("DCBF_SPLIT", "16384")
+    monkeypatch.setenv("DCBF_LIPL", "0")
     s = _solver(gpu, "modi", sc)
     l0 = s.launches
     res = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
@@ -387,6 +390,21 @@ def test_size_class_split_is_transparent(gpu, monkeypatch):
     assert s.launches - l0 == 3                      # classify + two solve kernels
     assert torch.equal(res.status, ref.status) and torch.equal(res.iters, ref.iters)
     assert torch.equal(res.p_plan, ref.p_plan) and torch.equal(res.x_plan, ref.x_plan)
+    monkeypatch.delenv("DCBF_LIPL")
+    s = _solver(gpu, "modi", sc)
+    l0 = s.launches
+    res = s.solve(sc.x0, sc.goal, sc.leg, sc.warm, field=sc.field)
+    torch.cuda.synchronize()
+    assert s.launches - l0 == 4                      # classify + three solve kernels
+    assert torch.equal(res.status, ref.status)
+    assert (res.iters == ref.iters).double().mean().item() >= 0.99
+    both = (res.status == 0) & (ref.status == 0)
+    dp = (res.p_plan - ref.p_plan).abs().reshape(B, -1).max(dim=1).values[both]
+    assert dp.max().item() <= 1e-4 and (dp <= 1e-9).double().mean().item() >= 0.97, (dp.max().item(), (dp <= 1e-9).double().mean().item())
+    # the classes the typed slot does not touch are still bit-identical
+    other = s.setup_info(sc.x0, sc.goal, field=sc.field)["count"] != 5
+    assert 0.1 < (~other).double().mean().item() < 0.4           # (a quarter of the batch selects five obstacles)
+    assert torch.equal(res.p_plan[other], ref.p_plan[other]) and torch.equal(res.iters[other], ref.iters[other])
 
 
 @pytest.mark.parametrize("form", ["sig_step", "dd"])
