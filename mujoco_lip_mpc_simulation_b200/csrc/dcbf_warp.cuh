@@ -306,6 +306,10 @@ template <> struct LaneRefresh<LipL, 2> { static constexpr bool v = DCBF_LANE_RE
 #define DCBF_LANE_REFRESH_LIP2 0
 #endif
 template <> struct LaneRefresh<LipW, 2> { static constexpr bool v = DCBF_LANE_REFRESH_LIP2 != 0; };
+#ifndef DCBF_LANE_REFRESH_DDL
+#define DCBF_LANE_REFRESH_DDL 1
+#endif
+template <> struct LaneRefresh<DdL, 2> { static constexpr bool v = DCBF_LANE_REFRESH_DDL != 0; };
 
 // per-problem scratch (one per warp) and the constants are static shared-memory objects, so every function sees them as
 // shared-space symbols (no generic pointers through the out-of-line calls)
@@ -744,7 +748,10 @@ struct DdWT {
     using NodeData = DdNodeData;
     enum { RT_NONE = 0, RT_CBF, RT_FENP, RT_FENM, RT_BV, RT_BW };
 
-    static constexpr int NLINP = 32;       // every column of the linear slot is staged (rows without a type stage zeros)
+#ifndef DCBF_DDL_NLINP
+#define DCBF_DDL_NLINP 12
+#endif
+    static constexpr int NLINP = LIN ? DCBF_DDL_NLINP : 32;   // staged columns of the linear slot (twelve linear rows; 32: rows without a type stage zeros)
     static __device__ __forceinline__ const int *desc(const WarpTables *tab) { return tab->desc_dd; }
     static __device__ __forceinline__ const int *desc_lin(const WarpTables *tab) { return tab->desc_lin; }
     static __device__ __forceinline__ int rows_per_step(const dcbf_params &, int Ks) { return Ks + 4; }
