@@ -230,8 +230,9 @@ def main():
     flop_per_step = float(it_acc.item()) / args.steps * F_ITER_SIG_K6     # mean over the timed steps (the batches rotate when N > 1)
 
     # ---- pipelined throughput: consecutive batches on rotating streams (one context each) -------------------------------------------
-    # A step of `value` ends when its slowest scenario ends: 4096 scenarios on 1776 persistent warps are 2.3 per warp, so a third of
-    # the warps run three problems while the rest run two and then idle (DESIGN.md "the tail").  A caller with a stream of batches does
+    # A step of `value` ends when its slowest chain of scenarios ends: 4096 scenarios on 2368 persistent warps are 1.73 per warp, so
+    # three quarters of the warps run two problems while the rest run one and then idle, and a 29-iteration problem alone is most of
+    # the step (DESIGN.md "the tail").  A caller with a stream of batches does
     # not have to wait: batch k+1 is launched on a second stream and its warps take over the SM slots batch k's warps vacate.
     n_lanes = int(os.environ.get("DCBF_BENCH_LANES", "3"))
     lanes = [(solver, out, torch.cuda.Stream(device=dev))]
@@ -348,6 +349,30 @@ def main():
                     "checksum": {"steps_done_sum": int(sd.sum()), "n_infeasible_sum": int(g5["n_infeasible"].sum()),
                                  "x_final_nansum": float(torch.nan_to_num(xf).sum())}}
         del r5, g5, inp5, sv5
+
+    # ---- the same kernel at throughput: one 65 536-scenario batch (16 x the step's batch; no tail to speak of) -- the roofline of the
+    # kernel itself next to the roofline of the 4096-scenario step -------------------------------------------------------------------
+    sat = None
+    if rank == 0:
+        Bs = 65536
+        s2 = scenarios.make_batch("sig_step", Bs, seed=SEED + 1)
+        sv = DcbfSolver("sig_step", device=local)
+        sv.set_fields(s2.cir)
+        a = [t(s2.x0, torch.float64), t(s2.goal, torch.float64), t(s2.leg, torch.int32), t(s2.warm, torch.float64), t(s2.field, torch.int32)]
+        ts = []
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            e0.record()
+            r = sv.solve(a[0], a[1], a[2], a[3], field=a[4])
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.mean(ts[1:]))
+        tf = float(r.iters.sum().item()) * F_ITER_SIG_K6 / (ms * 1e-3) * 1e-12
+        sat = {"batch": Bs, "ms": ms, "solves_per_s": Bs / (ms * 1e-3), "achieved": tf, "frac": tf / fp64_peak if fp64_peak > 0 else None,
+               "mean_iters": float(r.iters.float().mean()), "how": "mean of 3 launches after one warm-up, L2 flushed, CUDA events"}
+        del sv, r, a
 
     extra = {}
     if args.sweep and rank == 0:
@@ -469,12 +494,14 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
                          "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
-                         "kernel": "solve_lip_warp_kernel<1> (one problem per warp)", "algorithmic_bytes": B * io_bytes_per_solve(6),
+                         "kernel": "solve_lip_warp_kernel<LipW, 1> (one problem per warp, 16 warps per SM)", "algorithmic_bytes": B * io_bytes_per_solve(6),
                          "peak_source": "measured on this GPU by dcbf_fp64_peak_tflops (DFMA loop); MEASURED_PEAKS.json has no FP64 figure",
                          "flop_per_iter": F_ITER_SIG_K6, "iters_per_step": flop_per_step / F_ITER_SIG_K6,
+                         "saturated": sat,
                          "hbm": {"achieved": io_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": io_gbs / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-            "iters": {"mean": float(iters.mean()), "p50": float(np.median(iters)), "p99": float(np.percentile(iters, 99)), "max": int(iters.max())},
+            "iters": {"mean": float(iters.mean()), "p50": float(np.median(iters)), "p99": float(np.percentile(iters, 99)), "max": int(iters.max()),
+                      "over_40": int((iters > 40).sum()), "of": "the batch of the last timed step"},
             "status_hist": {str(int(k)): int((status == k).sum()) for k in np.unique(status)},
             "clocks": sampler.summary(),
         }

@@ -277,15 +277,15 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, MinCtas<M, NS>::v) sol
         const int b = order ? order[i_] : i_;
         DCBF_ASSERT(b >= 0 && b < B);
         // the 22 input values arrive in three coalesced requests (the buffers may be mapped host memory: dcbf_solve_host)
-        sm.dz[lane] = lane < 5 ? in.x0[5 * (size_t)b + lane] : (lane < 20 ? in.warm[15 * (size_t)b + lane - 5] : (lane < 22 ? in.goal[2 * (size_t)b + lane - 20] : 0.0));
+        sm.ST[0][lane] = lane < 5 ? in.x0[5 * (size_t)b + lane] : (lane < 20 ? in.warm[15 * (size_t)b + lane - 5] : (lane < 22 ? in.goal[2 * (size_t)b + lane - 20] : 0.0));
         __syncwarp();
         if (lane == 0) {
             double x0[5], u0[15], g[2];
 #pragma unroll
-            for (int i = 0; i < 5; i++) x0[i] = sm.dz[i];
+            for (int i = 0; i < 5; i++) x0[i] = sm.ST[0][i];
 #pragma unroll
-            for (int i = 0; i < 15; i++) u0[i] = sm.dz[5 + i];
-            g[0] = sm.dz[20]; g[1] = sm.dz[21];
+            for (int i = 0; i < 15; i++) u0[i] = sm.ST[0][5 + i];
+            g[0] = sm.ST[0][20]; g[1] = sm.ST[0][21];
             stage_problem<M, NS>(cs_.K, sm, x0, g, u0, 0);
         } else {
             __syncwarp();

@@ -38,7 +38,13 @@ constexpr int KQ_Q = 0;
 constexpr int KQ_K = 28;
 constexpr int KQ_RHS = KQ_K + 45;
 constexpr int KQ_LEN = KQ_RHS + 12;   // right-hand side (N entries) + one dump slot (index N) for the lanes beyond N
-constexpr int LF_LEN = 56 + 8;    // factor rows 0..9, then eight dump slots for the branch-free stores (lane & 7)
+// Cholesky factor of the (N + 1) x (N + 1) bordered system, one row per lane at a fixed stride of N entries: rows 0..N-1 of L, row N
+// = L^-1 rhs, row N + 1 = dump row of the lanes beyond N; only the strictly lower triangle is ever written (diagonal and upper
+// triangle stay zero from stage_cta on, which is what lets the backward substitution run without lane tests), the reciprocal
+// diagonal follows at LF_DIAG
+constexpr int LF_STRIDE_MAX = 9;
+constexpr int LF_DIAG = (LF_STRIDE_MAX + 2) * LF_STRIDE_MAX;   // 99
+constexpr int LF_LEN = LF_DIAG + LF_STRIDE_MAX + 2;            // 110
 
 // Host-built constant tables, one copy per context in device memory (build_warp_tables()).
 struct WarpTables {
@@ -242,9 +248,9 @@ struct alignas(16) WarpShared {
     double HQ[M::LIN2 ? 32 : 32 * NS][M::NHQ];   // y * (second-order / first-order row coefficients) of the D-CBF rows
     double obs[KsMax<NS>::v][6];  // selected obstacles: cx, cy, a', b', c', rhs
     double KQ[KQ_LEN];       // assembled system (see KQ_*)
-    double Lf[LF_LEN];       // Cholesky factor (packed rows 0..N-1), the forward-substituted right-hand side (row N), dump slots
-    double dz[32];           // N meaningful entries; all lanes store (also the staging buffer of the problem's 22 input values)
-    double zc[16], zt[16];   // N meaningful entries; lanes >= N store lane N-1's value into slot N-1 (index ln)
+    double Lf[LF_LEN];       // Cholesky factor (see LF_DIAG)
+    double dz[16];           // N meaningful entries; lanes >= 15 store into slot 15
+    double zc[10], zt[10];   // N meaningful entries; lanes >= N store lane N-1's value into slot N-1 (index ln)
     double x0[5], goal[2], graw[2];
     // row state (slack, multipliers, step) of the kernels with more than one row per lane: the slot loop stays rolled there
     // (half the code, a third fewer registers); the single-slot kernel keeps it in registers
@@ -1315,26 +1321,33 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
         bool lm_accept = false;
         double v2t = 0.0, vmt = 0.0;
         double lam = resto ? sm.cold[C_LM_LAMBDA] : 0.0;   // Levenberg-Marquardt parameter of this restoration step (written back below)
+        const int lbase = (lane < N + 1 ? lane : N + 1) * N, diag_ix = ln * (ln + 3) / 2;
+        const double kd = sm.KQ[KQ_K + diag_ix];           // the lane's diagonal entry of the assembled matrix
         for (int rt = 0; rt < 20; rt++) {
             double shift = lam;
             bool ok = false;
             for (int tr = 0; tr < 48; tr++) {
                 // lanes 0..N-1 own the rows of K, lane N the right-hand side (its "row" of the factor is L^-1 rhs).  Branch-free:
-                // every lane runs the column arithmetic (idle lanes on harmless operands), only the store address is selected,
-                // so the warp reaches each shuffle converged.
+                // every lane runs the column arithmetic (idle lanes on harmless operands) and stores below the diagonal of ITS row
+                // of the factor (lanes beyond N: the dump row), so the warp reaches each shuffle converged and a column costs no
+                // per-lane index arithmetic.  A diagonal shift is written into the staged matrix first.
+                if (shift != 0.0) {
+                    sm.KQ[KQ_K + diag_ix] = kd + shift;
+                    __syncwarp();
+                }
                 double Lrow[N];
                 ok = true;
 #pragma unroll
                 for (int j = 0; j < N; j++) {
-                    const bool act = lane >= j && lane < N + 1;
-                    double s_ = sm.KQ[KQ_K + rowbase + j] + (lane == j ? shift : 0.0);
+                    double s_ = sm.KQ[KQ_K + rowbase + j];
 #pragma unroll
-                    for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[tri(j, c)], s_);
+                    for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[j * N + c], s_);
                     const double d = __shfl_sync(FULL, s_, j);
                     if (!(d > 1e-14)) { ok = false; break; }
                     const double rinv = frsqrt(d);
-                    Lrow[j] = lane == j ? rinv : s_ * rinv;   // diagonal stored as its reciprocal
-                    sm.Lf[act ? rowbase + j : 56 + (lane & 7)] = Lrow[j];
+                    Lrow[j] = s_ * rinv;
+                    if (lane > j) sm.Lf[lbase + j] = Lrow[j];
+                    sm.Lf[LF_DIAG + j] = rinv;   // diagonal as its reciprocal (every lane stores the same value)
                     __syncwarp();
                 }
                 if (ok || resto) break;
@@ -1349,16 +1362,16 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                 continue;
             }
             if (!resto && shift > 0.0) sm.cold[C_DELTA_LAST] = shift;
-            // backward substitution: lane i holds component i, starting from y = L^-1 rhs (row N of the factor); branch-free
+            // backward substitution: lane i reduces component i of y = L^-1 rhs (row N of the factor) by L[c][i] x_c -- zero for
+            // i >= c, so there is no lane test -- and scales by its reciprocal pivot at the end
             {
-                double bi = sm.Lf[NK + ln];
+                double bi = sm.Lf[N * N + ln];
 #pragma unroll
                 for (int c = N - 1; c >= 0; c--) {
-                    const double xc = __shfl_sync(FULL, bi * sm.Lf[tri(c, c)], c);
-                    const double lc = sm.Lf[tri(c, 0) + (ln < c ? ln : 0)];
-                    bi = lane == c ? xc : (lane < c ? fma(-lc, xc, bi) : bi);
+                    const double xc = __shfl_sync(FULL, bi * sm.Lf[LF_DIAG + c], c);
+                    bi = fma(-sm.Lf[c * N + ln], xc, bi);
                 }
-                sm.dz[lane] = bi;
+                sm.dz[lane < 15 ? lane : 15] = bi * sm.Lf[LF_DIAG + ln];
             }
             __syncwarp();
             if (!resto) break;
@@ -1543,6 +1556,7 @@ __device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K,
         reinterpret_cast<unsigned *>(&g_cs.hs[0][0])[t] = __ldg(reinterpret_cast<const unsigned *>(&tab->hs[0][0]) + t);
     if constexpr (M::N == 6) { if (lane < 24) sm.nd.sm_dd[lane] = __ldg(&tab->sm_dd[lane]); }
     for (int t = lane; t < 2 * WarpShared<M, NS>::NST; t += 32) sm.ST[t >> 1][WarpShared<M, NS>::RP - 2 + (t & 1)] = 0.0;
+    for (int t = lane; t < LF_LEN; t += 32) sm.Lf[t] = 0.0;   // diagonal and upper triangle of the factor stay zero
     __syncthreads();
 }
 
