@@ -360,7 +360,7 @@ def main():
         sv.set_fields(s2.cir)
         a = [t(s2.x0, torch.float64), t(s2.goal, torch.float64), t(s2.leg, torch.int32), t(s2.warm, torch.float64), t(s2.field, torch.int32)]
         ts = []
-        for _ in range(4):
+        for _ in range(7):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             flush.zero_()
             e0.record()
@@ -368,10 +368,11 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        ms = float(np.mean(ts[1:]))
+        ms = float(np.median(ts[2:]))
         tf = float(r.iters.sum().item()) * F_ITER_SIG_K6 / (ms * 1e-3) * 1e-12
         sat = {"batch": Bs, "ms": ms, "solves_per_s": Bs / (ms * 1e-3), "achieved": tf, "frac": tf / fp64_peak if fp64_peak > 0 else None,
-               "mean_iters": float(r.iters.float().mean()), "how": "mean of 3 launches after one warm-up, L2 flushed, CUDA events"}
+               "mean_iters": float(r.iters.float().mean()), "launch_ms": [round(x, 4) for x in ts],
+               "how": "median of 5 launches after two warm-ups, L2 flushed before each, CUDA events"}
         del sv, r, a
 
     extra = {}
