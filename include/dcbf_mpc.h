@@ -54,7 +54,7 @@
 extern "C" {
 #endif
 
-#define DCBF_ABI_VERSION 3
+#define DCBF_ABI_VERSION 4
 #define DCBF_MAX_OBS 16 /* circles and ellipses each, per field */
 
 enum dcbf_formulation { DCBF_SIG_STEP = 0, DCBF_MODI = 1, DCBF_DD = 2 };
@@ -85,6 +85,9 @@ typedef struct dcbf_params {
     double mu_warm;   /* first barrier parameter of a re-plan warm-started from the previous plan verbatim (dcbf_tick mode 0) */
     double mu_shift;  /* ... from the shifted plan [x_2, x_3, x_3] (dcbf_tick mode 1, dcbf_rollout after the first step), whose third
                          step still violates the velocity rows; a cold start uses mu_init */
+    double resto_window; /* restoration phase: three consecutive accepted steps that together reduce the squared violation by less than
+                            this fraction end the phase at the current point (a stationary point of the violation for the purpose of
+                            the infeasibility verdict; the iterate crawls along a kink of the violation).  ABI version 4 */
 } dcbf_params;
 
 typedef struct dcbf_ctx dcbf_ctx;

@@ -89,7 +89,7 @@ DCBF_CE int THI(int l) { return 6 + l; }
 #define DCBF_KAPPA_EPS 10.0          /* Ipopt barrier_tol_factor */
 #endif
 #ifndef DCBF_RESTO_WINDOW
-#define DCBF_RESTO_WINDOW 1e-2       /* restoration: relative decrease of the squared violation over three steps */
+#define DCBF_RESTO_WINDOW 1e-2       /* restoration: relative decrease of the squared violation over three steps (default of dcbf_params::resto_window for modi) */
 #endif
 #ifdef DCBF_COUNT
 static long g_trials = 0;
@@ -1386,7 +1386,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
                 if (A.v2 - V.v2 <= 1e-4 * A.v2) S.acc_cnt++; else S.acc_cnt = 0;
                 // ... or three consecutive accepted steps that together gained less than DCBF_RESTO_WINDOW (the iterate
                 // crawls along a kink of the violation: rows entering and leaving the violated set)
-                const bool crawl = S.nresto >= 2 && S.v2_h2 - V.v2 <= DCBF_RESTO_WINDOW * S.v2_h2;
+                const bool crawl = S.nresto >= 2 && S.v2_h2 - V.v2 <= P.resto_window * S.v2_h2;
                 S.v2_h2 = S.v2_h1; S.v2_h1 = A.v2; S.nresto++;
                 if ((dn < 1e-12 || S.acc_cnt >= 2 || crawl) && V.vmax > S.resto_target) S.lm_lambda = 1e13;
                 return false;

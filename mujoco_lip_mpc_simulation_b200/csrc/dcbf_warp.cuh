@@ -1413,7 +1413,7 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                 const double v2c = sm.cold[C_ST_V2];
                 if (v2c - v2t <= 1e-4 * v2c) S.acc_cnt = S.acc_cnt < 31 ? S.acc_cnt + 1 : 31; else S.acc_cnt = 0;
                 const double h1 = sm.cold[C_V2_H1], h2 = sm.cold[C_V2_H2];
-                const bool crawl = S.nresto >= 2 && h2 - v2t <= DCBF_RESTO_WINDOW * h2;
+                const bool crawl = S.nresto >= 2 && h2 - v2t <= P.resto_window * h2;
                 __syncwarp();   // every lane has read the window before anyone shifts it
                 sm.cold[C_V2_H2] = h1; sm.cold[C_V2_H1] = v2c;
                 if (S.nresto < 3) S.nresto = S.nresto + 1;

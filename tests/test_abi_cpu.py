@@ -15,7 +15,7 @@ def test_library_builds_and_exports_header_symbols(built):
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dcbf_abi_version() == 3
+    assert lib.dcbf_abi_version() == 4
 
 
 def test_default_params_match_reference_constants(built):
