@@ -88,6 +88,8 @@ typedef struct dcbf_params {
     double resto_window; /* restoration phase: three consecutive accepted steps that together reduce the squared violation by less than
                             this fraction end the phase at the current point (a stationary point of the violation for the purpose of
                             the infeasibility verdict; the iterate crawls along a kink of the violation).  ABI version 4 */
+    double kappa_eps;    /* barrier tolerance factor (Ipopt barrier_tol_factor, default 10 there): the barrier parameter is lowered once
+                            the error of the barrier problem is below kappa_eps * mu.  ABI version 4 */
 } dcbf_params;
 
 typedef struct dcbf_ctx dcbf_ctx;

@@ -27,7 +27,7 @@ class DcbfParams(C.Structure):
                 ("bvx_min", C.c_double), ("bvx_max", C.c_double), ("bvy_min", C.c_double), ("bvy_max", C.c_double),
                 ("leg_sq", C.c_double), ("ang_max", C.c_double), ("detect_sq", C.c_double), ("close_radius", C.c_double),
                 ("tol", C.c_double), ("constr_viol_tol", C.c_double), ("mu_init", C.c_double), ("tiny_alpha", C.c_double),
-                ("mu_warm", C.c_double), ("mu_shift", C.c_double), ("resto_window", C.c_double)]
+                ("mu_warm", C.c_double), ("mu_shift", C.c_double), ("resto_window", C.c_double), ("kappa_eps", C.c_double)]
 
 
 # every symbol include/dcbf_mpc.h declares

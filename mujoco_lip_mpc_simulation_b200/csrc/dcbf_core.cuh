@@ -86,7 +86,7 @@ DCBF_CE int THI(int l) { return 6 + l; }
 #define DCBF_MU_POW(mu) ((mu) * sqrt(mu))   /* Ipopt mu_superlinear_decrease_power = 1.5 */
 #endif
 #ifndef DCBF_KAPPA_EPS
-#define DCBF_KAPPA_EPS 10.0          /* Ipopt barrier_tol_factor */
+#define DCBF_KAPPA_EPS 10.0          /* Ipopt barrier_tol_factor (default of dcbf_params::kappa_eps for the differential drive) */
 #endif
 #ifndef DCBF_RESTO_WINDOW
 #define DCBF_RESTO_WINDOW 1e-2       /* restoration: relative decrease of the squared violation over three steps (default of dcbf_params::resto_window for modi) */
@@ -1316,7 +1316,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
             E0 = dmax(dmax(dinf / sd, A.pinf), A.cmax / sc);
             const double Emu = dmax(dmax(dinf / sd, A.pinf), compm / sc);
             if (E0 <= tol) break;
-            if (Emu <= DCBF_KAPPA_EPS * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
+            if (Emu <= P.kappa_eps * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
                 S.mu = dmax(tol * 0.1, dmin(DCBF_KAPPA_MU * S.mu, DCBF_MU_POW(S.mu)));
                 S.nf = 0;
                 continue;

@@ -799,6 +799,15 @@ int dcbf_default_params(int formulation, dcbf_params *P) {
     // 13.3 iterations on the infeasible ones, same verdicts.  The obstacle-selecting formulation keeps 1 %: 10 % costs it 0.04 points
     // of class agreement (measured on the host build of the per-thread code, 32 768 scenarios).
     P->resto_window = formulation == DCBF_MODI ? DCBF_RESTO_WINDOW : 0.1;
+    // Barrier tolerance factor.  Ipopt's 10 asks for ~2 Newton steps per barrier problem; the exact-Hessian iteration does not need
+    // that much centring on these problems.  Host build of the per-thread code against the oracle: sig_step 14.15 -> 13.17 (30) ->
+    // 12.55 (100) -> 11.95 (300) -> 11.65 (1000) iterations with the same verdicts and plans up to 300 (65 536 scenarios: class
+    // 99.939 -> 99.942 %, plans 99.918 -> 99.908 %), the first 58-iteration outlier at 1000 -- but from 70 on the closed loop of the
+    // reference's own config 1 takes a different local optimum in one of its five steps and leaves the golden trajectory
+    // (tests/golden/config1_closed_loop.npz; reproduced to 1e-9 up to 50): 30.  modi 16.03 -> 15.38 (30) -> 14.86 (100), plans 99.897 ->
+    // 99.918 -> 99.887 %: 30.  Differential drive 12.19 -> 11.91 (30) -> 11.62 (100) but plans within 1e-4 fall 99.989 -> 99.943 ->
+    // 99.898 % (more distinct local optima): stays at 10.
+    P->kappa_eps = formulation == DCBF_DD ? DCBF_KAPPA_EPS : 30.0;
     if (formulation == DCBF_SIG_STEP) {
         P->w_p = 2.0; P->w_r = 15.0; P->gamma = 0.4; P->s_turn = 0.014 * 180.0 / PI; P->bvy_max = 0.3;
         P->goal_shift = 1; P->close_radius = 0.35; P->close_any = 1;

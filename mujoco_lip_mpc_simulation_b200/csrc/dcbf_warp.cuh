@@ -1280,7 +1280,7 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                 E0 = fmax(fmax(dinf * isd, st_pinf), st_cmax * isc);
                 const double Emu = fmax(fmax(dinf * isd, st_pinf), compm * isc);
                 if (E0 <= tol) break;
-                if (Emu <= DCBF_KAPPA_EPS * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
+                if (Emu <= P.kappa_eps * S.mu && S.mu > tol * 0.1 * (1.0 + 1e-12)) {
                     S.mu = fmax(tol * 0.1, fmin(DCBF_KAPPA_MU * S.mu, DCBF_MU_POW(S.mu)));
                     S.nf = 0;
                     continue;

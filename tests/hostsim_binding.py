@@ -20,7 +20,7 @@ class DcbfParams(C.Structure):
                 ("bvx_min", C.c_double), ("bvx_max", C.c_double), ("bvy_min", C.c_double), ("bvy_max", C.c_double),
                 ("leg_sq", C.c_double), ("ang_max", C.c_double), ("detect_sq", C.c_double), ("close_radius", C.c_double),
                 ("tol", C.c_double), ("constr_viol_tol", C.c_double), ("mu_init", C.c_double), ("tiny_alpha", C.c_double),
-                ("mu_warm", C.c_double), ("mu_shift", C.c_double), ("resto_window", C.c_double)]
+                ("mu_warm", C.c_double), ("mu_shift", C.c_double), ("resto_window", C.c_double), ("kappa_eps", C.c_double)]
 
 
 FORMS = {"sig_step": 0, "modi": 1, "dd": 2}
@@ -52,6 +52,7 @@ def default_params(form) -> DcbfParams:
     P.tiny_alpha, P.tiny_count = (5e-2, 2) if f == 2 else (1e-2, 3)
     P.mu_warm, P.mu_shift = 1e-4, 1e-2
     P.resto_window = 1e-2 if f == 1 else 0.1
+    P.kappa_eps = (30.0, 30.0, 10.0)[f]
     if f == 0:
         P.w_p, P.w_r, P.gamma, P.s_turn, P.bvy_max = 2.0, 15.0, 0.4, 0.014 * 180 / math.pi, 0.3
         P.goal_shift, P.close_radius, P.close_any = 1, 0.35, 1
