@@ -144,6 +144,16 @@ int dcbf_rollout(dcbf_ctx *ctx, int32_t B, int32_t steps, const double *x0, cons
                  const int32_t *field, double *x_final, int32_t *steps_done, int32_t *n_infeasible,
                  int32_t *total_iters, double *traj, void *stream);
 
+/* dcbf_solve_host without the final wait, for callers with a stream of batches (ABI version 4): the work is enqueued on the
+ * context's own stream and the call returns; dcbf_wait(ctx) returns when every call enqueued on the context has finished and its
+ * results are in the caller's buffers.  Requires page-locked buffers on both sides (the copy-free path of dcbf_solve_host; DCBF_ERR_ARG
+ * otherwise).  The buffers must stay untouched until dcbf_wait.  Two or three contexts used round-robin overlap the drain of one
+ * batch with the head of the next (what the reference's per-tick loop over robots, main_sim_mpc.py:85-88, would batch). */
+int dcbf_solve_host_async(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg,
+                          const int32_t *field, const double *warm, const double *last_u, double *u, double *x_plan,
+                          double *p_plan, int32_t *status, int32_t *iters, double *obj, double *viol, uint8_t *close2goal);
+int dcbf_wait(dcbf_ctx *ctx);
+
 /* dcbf_solve for host buffers; returns when the results are in the caller's buffers.  Pageable buffers are staged through one
  * pinned block (one copy each way).  If every buffer is page-locked (cudaHostAlloc / cudaHostRegister) and the batch runs on a
  * warp kernel, nothing is copied: the kernels read the inputs from and write the results to the mapped host memory directly

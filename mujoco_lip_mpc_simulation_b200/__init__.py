@@ -6,11 +6,11 @@ ALIP_plan/planner.py of shaygong322/Mujoco-LIP-MPC-Simulation): same call surfac
 """
 from . import _lib, scenarios  # noqa: F401
 
-__all__ = ["_lib", "scenarios", "DcbfSolver", "default_params"]
+__all__ = ["_lib", "scenarios", "DcbfSolver", "HostPipeline", "default_params"]
 
 
 def __getattr__(name):
-    if name in ("DcbfSolver", "default_params", "SolveResult"):
+    if name in ("DcbfSolver", "HostPipeline", "default_params", "SolveResult"):
         from . import batch
         return getattr(batch, name)
     raise AttributeError(name)

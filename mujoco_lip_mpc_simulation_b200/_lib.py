@@ -34,7 +34,7 @@ class DcbfParams(C.Structure):
 EXPORTS = ["dcbf_abi_version", "dcbf_default_params", "dcbf_create", "dcbf_destroy", "dcbf_last_error",
            "dcbf_set_fields", "dcbf_num_rows", "dcbf_num_vars", "dcbf_eval", "dcbf_solve", "dcbf_rollout",
            "dcbf_set_fields_host", "dcbf_solve_host", "dcbf_launch_count", "dcbf_fp64_peak_tflops", "dcbf_tick", "dcbf_alip_foot", "dcbf_math_probe",
-           "dcbf_gen_fields", "dcbf_gen_states", "dcbf_heading_input", "dcbf_setup_info", "dcbf_veldes_foot"]
+           "dcbf_gen_fields", "dcbf_gen_states", "dcbf_heading_input", "dcbf_setup_info", "dcbf_veldes_foot", "dcbf_solve_host_async", "dcbf_wait"]
 
 
 def needs_build() -> bool:
@@ -88,6 +88,8 @@ def load():
     lib.dcbf_rollout.argtypes = [vp, C.c_int32, C.c_int32] + [dp] * 9 + [vp]
     lib.dcbf_set_fields_host.argtypes = [vp, C.c_int32, C.c_int32, ip, C.c_int32, ip]
     lib.dcbf_solve_host.argtypes = [vp, C.c_int32] + [ip] * 14
+    lib.dcbf_solve_host_async.argtypes = [vp, C.c_int32] + [ip] * 14
+    lib.dcbf_wait.argtypes = [vp]
     lib.dcbf_tick.argtypes = [vp, C.c_int32] + [dp] * 21 + [vp]
     lib.dcbf_alip_foot.argtypes = [vp, C.c_int32] + [dp] * 5 + [C.c_int32] + [C.c_double] * 4 + [dp] * 3 + [vp]
     lib.dcbf_math_probe.argtypes = [vp, C.c_int32, dp, dp, dp, vp]

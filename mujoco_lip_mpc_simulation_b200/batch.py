@@ -368,8 +368,9 @@ class DcbfSolver:
         self._check(rc, "dcbf_set_fields_host")
         self.F, self.Kc, self.Ke = F, int(cir.shape[1]), int(elp.shape[1])
 
-    def solve_host(self, x0, goal, leg, warm, field=None, last_u=None, out: SolveResult | None = None) -> SolveResult:
-        """numpy in / numpy out through dcbf_solve_host (copies + kernel + copies, synchronous)."""
+    def solve_host(self, x0, goal, leg, warm, field=None, last_u=None, out: SolveResult | None = None, wait: bool = True) -> SolveResult:
+        """numpy in / numpy out through dcbf_solve_host (copies + kernel + copies, synchronous).  wait=False enqueues only
+        (dcbf_solve_host_async: every buffer, `out` included, must be page-locked and stay untouched until wait())."""
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
         x0 = f64(x0).reshape(-1, self.nx)
         B = x0.shape[0]
@@ -383,11 +384,65 @@ class DcbfSolver:
         if out is None:
             out = SolveResult(np.empty((B, self.nu)), np.empty((B, 3, self.nx)), None if self.dd else np.empty((B, 3, 3)),
                               np.empty(B, np.int32), np.empty(B, np.int32), np.empty(B), np.empty(B), np.empty(B, np.uint8))
-        rc = self.lib.dcbf_solve_host(self._ctx, B, _ptr(x0), _ptr(goal), _ptr(leg), _ptr(field), _ptr(warm), _ptr(last_u),
-                                      _ptr(out.u), _ptr(out.x_plan), _ptr(out.p_plan), _ptr(out.status), _ptr(out.iters),
-                                      _ptr(out.obj), _ptr(out.viol), _ptr(out.close2goal))
-        self._check(rc, "dcbf_solve_host")
+        fn = self.lib.dcbf_solve_host_async if wait is False else self.lib.dcbf_solve_host
+        rc = fn(self._ctx, B, _ptr(x0), _ptr(goal), _ptr(leg), _ptr(field), _ptr(warm), _ptr(last_u),
+                _ptr(out.u), _ptr(out.x_plan), _ptr(out.p_plan), _ptr(out.status), _ptr(out.iters),
+                _ptr(out.obj), _ptr(out.viol), _ptr(out.close2goal))
+        self._check(rc, "dcbf_solve_host_async" if wait is False else "dcbf_solve_host")
+        if wait is False:
+            self._pending = (x0, goal, leg, field, warm, last_u, out)   # keep the buffers alive until wait()
         return out
+
+    def wait(self):
+        """dcbf_wait: returns when every solve_host(..., wait=False) of this solver has delivered its results."""
+        rc = self.lib.dcbf_wait(self._ctx)
+        self._check(rc, "dcbf_wait")
+        self._pending = None
 
     def fp64_peak_tflops(self, repeats: int = 3) -> float:
         return float(self.lib.dcbf_fp64_peak_tflops(self._ctx, repeats))
+
+
+class HostPipeline:
+    """A stream of host-buffer batches through `lanes` contexts used round-robin (dcbf_solve_host_async / dcbf_wait): the drain of
+    one batch overlaps the head of the next, so a caller with many small batches gets the throughput of a large one.  Every buffer
+    must be page-locked (`pin(...)` below); submit() returns the SolveResult the batch will be written to and the lane it runs
+    on; its contents are valid after that lane's wait() (or after drain())."""
+
+    def __init__(self, form="sig_step", lanes: int = 3, device: int | None = None, **overrides):
+        self.solvers = [DcbfSolver(form, device=device, **overrides) for _ in range(lanes)]
+        self._busy = [False] * lanes
+        self._next = 0
+
+    @staticmethod
+    def pin(a):
+        """page-locked copy of a numpy array (what the copy-free host path needs)"""
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    def set_fields_host(self, cir, elp=None):
+        for s in self.solvers:
+            s.set_fields_host(cir, elp)
+
+    def submit(self, x0, goal, leg, warm, field=None, last_u=None, out: SolveResult | None = None):
+        lane = self._next
+        self._next = (lane + 1) % len(self.solvers)
+        s = self.solvers[lane]
+        if self._busy[lane]:
+            s.wait()
+        if out is None:
+            B = np.asarray(x0).reshape(-1, s.nx).shape[0]
+            out = SolveResult(self.pin(np.empty((B, s.nu))), self.pin(np.empty((B, 3, s.nx))), None if s.dd else self.pin(np.empty((B, 3, 3))),
+                              self.pin(np.empty(B, np.int32)), self.pin(np.empty(B, np.int32)), self.pin(np.empty(B)), self.pin(np.empty(B)),
+                              self.pin(np.empty(B, np.uint8)))
+        s.solve_host(x0, goal, leg, warm, field=field, last_u=last_u, out=out, wait=False)
+        self._busy[lane] = True
+        return out, lane
+
+    def wait(self, lane: int):
+        if self._busy[lane]:
+            self.solvers[lane].wait()
+            self._busy[lane] = False
+
+    def drain(self):
+        for lane in range(len(self.solvers)):
+            self.wait(lane)

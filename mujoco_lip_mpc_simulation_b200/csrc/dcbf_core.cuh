@@ -88,6 +88,12 @@ DCBF_CE int THI(int l) { return 6 + l; }
 #ifndef DCBF_KAPPA_EPS
 #define DCBF_KAPPA_EPS 10.0          /* Ipopt barrier_tol_factor (default of dcbf_params::kappa_eps for the differential drive) */
 #endif
+#ifndef DCBF_LM_UP
+#define DCBF_LM_UP 10.0              /* restoration: Levenberg-Marquardt parameter after a rejected trial ... */
+#endif
+#ifndef DCBF_LM_DOWN
+#define DCBF_LM_DOWN 0.2             /* ... and after an accepted one */
+#endif
 #ifndef DCBF_RESTO_WINDOW
 #define DCBF_RESTO_WINDOW 1e-2       /* restoration: relative decrease of the squared violation over three steps (default of dcbf_params::resto_window for modi) */
 #endif
@@ -1365,7 +1371,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
         // Levenberg-Marquardt trials: the assembled K and right-hand side are reused while lambda is escalated
         double L[N * (N + 1) / 2];
         for (int rt = 0; rt < 20 && S.lm_lambda <= 1e12; rt++) {
-            if (!chol_packed<N>(A.K, S.lm_lambda, L)) { S.lm_lambda *= 10.0; continue; }
+            if (!chol_packed<N>(A.K, S.lm_lambda, L)) { S.lm_lambda *= DCBF_LM_UP; continue; }
             DCBF_UNROLL
             for (int i = 0; i < N; i++) S.dz[i] = -A.q1[i];
             chol_solve_packed<N>(L, S.dz);
@@ -1380,7 +1386,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
                 DCBF_UNROLL
                 for (int i = 0; i < N; i++) { dn = dmax(dn, fabs(S.dz[i])); S.z[i] += S.dz[i]; }
                 S.iters++;
-                S.lm_lambda = dmax(S.lm_lambda * 0.2, 1e-12);
+                S.lm_lambda = dmax(S.lm_lambda * DCBF_LM_DOWN, 1e-12);
                 // stagnation: the squared violation has stopped decreasing (two consecutive accepted steps with a relative
                 // decrease below 1e-4) -> the iterate is (numerically) a stationary point of the violation
                 if (A.v2 - V.v2 <= 1e-4 * A.v2) S.acc_cnt++; else S.acc_cnt = 0;
@@ -1391,7 +1397,7 @@ DCBF_HD bool ipm_iterate(const Consts &k, const dcbf_params &P, Model &M, IpmSta
                 if ((dn < 1e-12 || S.acc_cnt >= 2 || crawl) && V.vmax > S.resto_target) S.lm_lambda = 1e13;
                 return false;
             }
-            S.lm_lambda *= 10.0;
+            S.lm_lambda *= DCBF_LM_UP;
         }
         return false;   // lambda exhausted: the next call classifies the point as stationary
     }

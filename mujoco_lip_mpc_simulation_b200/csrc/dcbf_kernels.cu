@@ -1205,9 +1205,32 @@ int dcbf_set_fields_host(dcbf_ctx *ctx, int32_t F, int32_t Kc, const double *cir
 
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static int solve_host_impl(dcbf_ctx *ctx, bool async, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+                           const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
+                           int32_t *iters, double *obj, double *viol, uint8_t *close2goal);
+
 int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
                     const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
                     int32_t *iters, double *obj, double *viol, uint8_t *close2goal) {
+    return solve_host_impl(ctx, false, B, x0, goal, leg, field, warm, last_u, u, x_plan, p_plan, status, iters, obj, viol, close2goal);
+}
+
+int dcbf_solve_host_async(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+                          const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
+                          int32_t *iters, double *obj, double *viol, uint8_t *close2goal) {
+    return solve_host_impl(ctx, true, B, x0, goal, leg, field, warm, last_u, u, x_plan, p_plan, status, iters, obj, viol, close2goal);
+}
+
+int dcbf_wait(dcbf_ctx *ctx) {
+    if (!ctx) return DCBF_ERR_ARG;
+    ENTER(ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DCBF_OK;
+}
+
+static int solve_host_impl(dcbf_ctx *ctx, bool async, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,
+                           const double *warm, const double *last_u, double *u, double *x_plan, double *p_plan, int32_t *status,
+                           int32_t *iters, double *obj, double *viol, uint8_t *close2goal) {
     if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
     if (!x0 || !goal || !warm) return DCBF_ERR_ARG;
@@ -1259,10 +1282,14 @@ int dcbf_solve_host(dcbf_ctx *ctx, int32_t B, const double *x0, const double *go
                             (const double *)dptr[3], (double *)dptr[6], (double *)dptr[7], (double *)dptr[8], (int32_t *)dptr[11], (int32_t *)dptr[12],
                             (double *)dptr[9], (double *)dptr[10], (uint8_t *)dptr[13], ctx->stream);
             if (rc != DCBF_OK) return rc;
-            CK(cudaStreamSynchronize(ctx->stream));
+            if (!async) CK(cudaStreamSynchronize(ctx->stream));
             return DCBF_OK;
         }
         (void)cudaGetLastError();
+    }
+    if (async) {   // the enqueue-only entry point exists for the copy-free path: page-locked buffers on both sides, warp kernels
+        snprintf(ctx->err, sizeof(ctx->err), "dcbf_solve_host_async needs page-locked (mapped) host buffers and a batch that runs on the warp kernels");
+        return DCBF_ERR_ARG;
     }
     if (in_pinned) {
         for (int i = 0; i < 6; i++)

@@ -1357,7 +1357,7 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
             }
             if (!ok) {
                 if (!resto) { S.status = -3; break; }
-                lam *= 10.0;
+                lam *= DCBF_LM_UP;
                 if (lam > 1e12) break;
                 continue;
             }
@@ -1400,7 +1400,7 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
             for (int o = 16; o > 0; o >>= 1) v2t += __shfl_xor_sync(FULL, v2t, o);
             vmt = wmax(vmt);
             if (v2t < sm.cold[C_ST_V2] * (1.0 - 1e-12)) { lm_accept = true; break; }
-            lam *= 10.0;
+            lam *= DCBF_LM_UP;
             if (lam > 1e12) break;
         }
         if (S.status == -3) break;
@@ -1409,7 +1409,7 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                 const double dn = wmax(lane < N ? fabs(sm.dz[ln]) : 0.0);
                 sm.zc[ln] = sm.zt[ln];
                 S.iters++;
-                lam = fmax(lam * 0.2, 1e-12);
+                lam = fmax(lam * DCBF_LM_DOWN, 1e-12);
                 const double v2c = sm.cold[C_ST_V2];
                 if (v2c - v2t <= 1e-4 * v2c) S.acc_cnt = S.acc_cnt < 31 ? S.acc_cnt + 1 : 31; else S.acc_cnt = 0;
                 const double h1 = sm.cold[C_V2_H1], h2 = sm.cold[C_V2_H2];

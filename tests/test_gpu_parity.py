@@ -444,6 +444,32 @@ def test_host_entry_point_with_page_locked_buffers(gpu):
     assert np.array_equal(out.close2goal, ref.close2goal)
 
 
+def test_host_pipeline_delivers_the_results_of_the_synchronous_call(gpu):
+    """dcbf_solve_host_async / dcbf_wait: consecutive host-buffer batches on three contexts used round-robin; every batch gets the
+    result of the synchronous call bit for bit, pageable buffers are refused"""
+    from mujoco_lip_mpc_simulation_b200.batch import HostPipeline
+    B = 512
+    batches = [scenarios.make_batch("sig_step", B, seed=60 + j) for j in range(5)]
+    F = batches[0].cir.shape[0]
+    cir_all = np.concatenate([b.cir for b in batches], axis=0)
+    s = _solver(gpu, "sig_step", batches[0])
+    s.set_fields_host(cir_all)
+    refs = [s.solve_host(b.x0, b.goal, b.leg, b.warm, field=b.field + j * F) for j, b in enumerate(batches)]
+    pipe = HostPipeline("sig_step", lanes=3, device=0)
+    pipe.set_fields_host(cir_all)
+    pin = HostPipeline.pin
+    outs = []
+    for j, b in enumerate(batches):
+        outs.append(pipe.submit(pin(b.x0), pin(b.goal), pin(b.leg.astype(np.int32)), pin(b.warm), field=pin((b.field + j * F).astype(np.int32))))
+    pipe.drain()
+    for (out, _), ref in zip(outs, refs):
+        assert np.array_equal(out.status, ref.status) and np.array_equal(out.iters, ref.iters)
+        assert np.array_equal(out.p_plan, ref.p_plan) and np.array_equal(out.x_plan, ref.x_plan)
+    b = batches[0]
+    with pytest.raises(RuntimeError):
+        pipe.solvers[0].solve_host(b.x0, b.goal, b.leg, b.warm, field=b.field, wait=False)     # pageable buffers
+
+
 def test_error_codes(gpu):
     lib = _lib.load()
     P = _lib.DcbfParams()
