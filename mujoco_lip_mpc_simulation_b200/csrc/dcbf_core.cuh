@@ -88,6 +88,12 @@ DCBF_CE int THI(int l) { return 6 + l; }
 #ifndef DCBF_KAPPA_EPS
 #define DCBF_KAPPA_EPS 10.0          /* Ipopt barrier_tol_factor (default of dcbf_params::kappa_eps for the differential drive) */
 #endif
+#ifndef DCBF_BOUND_PUSH
+#define DCBF_BOUND_PUSH 1e-2         /* Ipopt bound_push: initial slacks at least this far (times max(1, |bound|)) inside their bounds ... */
+#endif
+#ifndef DCBF_BOUND_FRAC
+#define DCBF_BOUND_FRAC 1e-2         /* ... Ipopt bound_frac: and at most this fraction of the range for two-sided rows */
+#endif
 #ifndef DCBF_LM_UP
 #define DCBF_LM_UP 10.0              /* restoration: Levenberg-Marquardt parameter after a rejected trial ... */
 #endif
@@ -235,13 +241,13 @@ DCBF_HD RowW row_full(const RowCtl &ctl, Acc<N> &A, LogAcc &LA, double c, double
     if (ctl.reinit) {
         double sv = c;
         if (LO && HI) {
-            const double pl = dmin(1e-2 * dmax(1.0, fabs(lr)), 1e-2 * (hr - lr));
-            const double pu = dmin(1e-2 * dmax(1.0, fabs(hr)), 1e-2 * (hr - lr));
+            const double pl = dmin(DCBF_BOUND_PUSH * dmax(1.0, fabs(lr)), DCBF_BOUND_FRAC * (hr - lr));
+            const double pu = dmin(DCBF_BOUND_PUSH * dmax(1.0, fabs(hr)), DCBF_BOUND_FRAC * (hr - lr));
             sv = dmin(dmax(sv, lr + pl), hr - pu);
         } else if (LO) {
-            sv = dmax(sv, lr + 1e-2 * dmax(1.0, fabs(lr)));
+            sv = dmax(sv, lr + DCBF_BOUND_PUSH * dmax(1.0, fabs(lr)));
         } else if (HI) {
-            sv = dmin(sv, hr - 1e-2 * dmax(1.0, fabs(hr)));
+            sv = dmin(sv, hr - DCBF_BOUND_PUSH * dmax(1.0, fabs(hr)));
         }
         s = sv;
         if (LO) zl = 1.0;

@@ -1175,11 +1175,11 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                     if (S.reinit) {
                         double sv = e.c;
                         if (bb.has_lo && bb.has_hi) {
-                            const double pl = fmin(1e-2 * fmax(1.0, fabs(lr)), 1e-2 * (hr - lr));
-                            const double pu = fmin(1e-2 * fmax(1.0, fabs(hr)), 1e-2 * (hr - lr));
+                            const double pl = fmin(DCBF_BOUND_PUSH * fmax(1.0, fabs(lr)), DCBF_BOUND_FRAC * (hr - lr));
+                            const double pu = fmin(DCBF_BOUND_PUSH * fmax(1.0, fabs(hr)), DCBF_BOUND_FRAC * (hr - lr));
                             sv = fmin(fmax(sv, lr + pl), hr - pu);
-                        } else if (bb.has_lo) sv = fmax(sv, lr + 1e-2 * fmax(1.0, fabs(lr)));
-                        else if (bb.has_hi) sv = fmin(sv, hr - 1e-2 * fmax(1.0, fabs(hr)));
+                        } else if (bb.has_lo) sv = fmax(sv, lr + DCBF_BOUND_PUSH * fmax(1.0, fabs(lr)));
+                        else if (bb.has_hi) sv = fmin(sv, hr - DCBF_BOUND_PUSH * fmax(1.0, fabs(hr)));
                         rs_ = sv; rzl_ = bb.has_lo ? 1.0 : 0.0; rzu_ = bb.has_hi ? 1.0 : 0.0;
                     } else if (S.pending) {
                         rs_ += sm.cold[C_ALPHA] * rds_;
