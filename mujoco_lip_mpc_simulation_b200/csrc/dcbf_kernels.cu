@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
 // Resident CTAs (= warps) per SM the kernels are built for (register budget 64 K / (32 x CTAs)):
 //   one slot (sig_step, small modi class): 16 warps at 128 registers -- without spills since the per-lane invariants are recomputed
 //   (wp::LaneRefresh) and the cold solver state lives in shared memory; 13.4 KB of shared memory per CTA let 16 CTAs fit;
-//   generic two / four slots: 8 warps at 255 registers;  typed turn-row slot (wp::LipL): 12 warps at 168 registers.
+//   generic two / four slots: 8 warps at 255 registers;  typed turn-row slot (wp::LipL): 12 warps at 168 registers;
+//   differential drive with typed slots (wp::DdL): 16 warps at 128 registers, 12.3 KB.
 #ifndef DCBF_WARP_MIN_CTAS
 #define DCBF_WARP_MIN_CTAS(NS) (((NS) == 1 ? 16 : 8) / wp::Wpc<wp::LipW, NS>::v)
 #endif
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(DCBF_BLOCK) rollout_lip_kernel(dcbf_params P, 
 #define DCBF_LIPL_MIN_CTAS 12
 #endif
 #ifndef DCBF_DDL_MIN_CTAS
-#define DCBF_DDL_MIN_CTAS 14   /* wp::DdL: 128 registers (lane refresh), 15.2 KB of shared memory: measured +2 % over 12 warps at 168 registers */
+#define DCBF_DDL_MIN_CTAS 16   /* wp::DdL: 128 registers (lane refresh), 12.3 KB of shared memory (twelve staged columns in the linear slot, no LIP tables): 12 -> 14 -> 16 warps per SM measured +2 % / +6 % */
 #endif
 #define DCBF_DD_MIN_CTAS(M, NS) ((std::is_same<M, wp::DdL>::value ? DCBF_DDL_MIN_CTAS : 12) / wp::Wpc<M, NS>::v)
 template <class M, int NS> struct MinCtas;

@@ -265,10 +265,14 @@ struct alignas(16) WarpShared {
 struct CtaShared {
     dcbf_params P;
     Consts K;
+    const WarpTables *tab;
+};
+// constant tables of the LIP models (a shared-memory object of their kernels only: the differential-drive kernels, which do not
+// reference it, are 3 KB lighter per CTA)
+struct LipTabShared {
     double cab[10][6];
     double hc[NHT][48];          // copy of the Hessian table (global loads in the assembly loop cost a long-scoreboard stall each)
     unsigned char hs[NHT][48];
-    const WarpTables *tab;
 };
 
 // Warps per CTA.  The kernel body is ~130 KB, several times the SM's instruction cache: with independent warps every warp streams
@@ -321,6 +325,7 @@ template <> struct LaneRefresh<DdL, 2> { static constexpr bool v = DCBF_LANE_REF
 // shared-space symbols (no generic pointers through the out-of-line calls)
 template <class M, int NS> __shared__ WarpShared<M, NS> g_sm[Wpc<M, NS>::v];
 __shared__ CtaShared g_cs;
+__shared__ LipTabShared g_lt;
 
 // iteration barrier of a CTA: returns the number of threads that still have work (a warp without work keeps arriving until the
 // count is zero).  One out-of-line copy so that every arrival is the same instruction.
@@ -593,7 +598,7 @@ struct LipWT {
     template <int NS>
     static __device__ __forceinline__ void stage_row(WarpShared<Self, NS> &sm, const CtaShared &cs_, const RowDesc &rd, const RowEval &e, double sig, double y, int r) {
         constexpr int RP = WarpShared<Self, NS>::RP;
-        const double *ab = cs_.cab[rd.cls];
+        const double *ab = g_lt.cab[rd.cls];
         const int i = rd.step;
         double *col = &sm.ST[0][r];
 #pragma unroll
@@ -618,7 +623,7 @@ struct LipWT {
         if (lane < 3) {
             const int kn = lane + 1;
             double x = sm.nd.fr[kn][0], y = sm.nd.fr[kn][1], vx = sm.nd.fr[kn][2], vy = sm.nd.fr[kn][3], th = sm.x0[4];
-            const double *cx = cs_.cab[lane], *cv = cs_.cab[3 + lane];   // gx[kn-1-l], gv[kn-1-l] for l < kn, else 0
+            const double *cx = g_lt.cab[lane], *cv = g_lt.cab[3 + lane];   // gx[kn-1-l], gv[kn-1-l] for l < kn, else 0
 #pragma unroll
             for (int l = 0; l < 3; l++) {
                 const double fx = z[2 * l], fy = z[2 * l + 1];
@@ -648,7 +653,7 @@ struct LipWT {
         double g = 0.0;
 #pragma unroll
         for (int kn = 1; kn <= 3; kn++) {
-            const double wf = cs_.cab[kn - 1][l];
+            const double wf = g_lt.cab[kn - 1][l];
             const double w = ln < 6 ? wf : (l < kn ? 1.0 : 0.0);
             g = fma(sm.nd.nobj[kn][c], w, g);
         }
@@ -710,7 +715,7 @@ struct LipWT {
     static __device__ __forceinline__ double hess_entry(const WarpShared<Self, NS> &sm, const CtaShared &cs_, int e, double sf, int terms, int) {
         double acc = 0.0;
 #pragma unroll
-        for (int h = 0; h < NHT; h++) if (h < terms) { DCBF_ASSERT(e >= 0 && e < 48 && cs_.hs[h][e] <= NSRC); acc = fma(cs_.hc[h][e], sm.nd.NHf[cs_.hs[h][e]], acc); }   // `terms` is a constant after unrolling
+        for (int h = 0; h < NHT; h++) if (h < terms) { DCBF_ASSERT(e >= 0 && e < 48 && g_lt.hs[h][e] <= NSRC); acc = fma(g_lt.hc[h][e], sm.nd.NHf[g_lt.hs[h][e]], acc); }   // `terms` is a constant after unrolling
         return acc;
     }
     static __host__ __device__ constexpr int round_terms(int t) { return t == 0 ? 6 : (t == 1 ? 2 : 0); }
@@ -1550,10 +1555,12 @@ __device__ __forceinline__ void stage_cta(const dcbf_params &P, const Consts &K,
     WarpShared<M, NS> &sm = g_sm<M, NS>[wid];
     const int t0 = wid * 32 + lane;
     if (t0 == 0) { g_cs.P = P; g_cs.K = K; g_cs.tab = tab; }
-    for (int t = t0; t < 60; t += 32 * W) (&g_cs.cab[0][0])[t] = __ldg(&tab->cab[0][0] + t);
-    for (int t = t0; t < NHT * 48; t += 32 * W) (&g_cs.hc[0][0])[t] = __ldg(&tab->hc[0][0] + t);
-    for (int t = t0; t < NHT * 48 / 4; t += 32 * W)
-        reinterpret_cast<unsigned *>(&g_cs.hs[0][0])[t] = __ldg(reinterpret_cast<const unsigned *>(&tab->hs[0][0]) + t);
+    if constexpr (M::N == 9) {
+        for (int t = t0; t < 60; t += 32 * W) (&g_lt.cab[0][0])[t] = __ldg(&tab->cab[0][0] + t);
+        for (int t = t0; t < NHT * 48; t += 32 * W) (&g_lt.hc[0][0])[t] = __ldg(&tab->hc[0][0] + t);
+        for (int t = t0; t < NHT * 48 / 4; t += 32 * W)
+            reinterpret_cast<unsigned *>(&g_lt.hs[0][0])[t] = __ldg(reinterpret_cast<const unsigned *>(&tab->hs[0][0]) + t);
+    }
     if constexpr (M::N == 6) { if (lane < 24) sm.nd.sm_dd[lane] = __ldg(&tab->sm_dd[lane]); }
     for (int t = lane; t < 2 * WarpShared<M, NS>::NST; t += 32) sm.ST[t >> 1][WarpShared<M, NS>::RP - 2 + (t & 1)] = 0.0;
     for (int t = lane; t < LF_LEN; t += 32) sm.Lf[t] = 0.0;   // diagonal and upper triangle of the factor stay zero
