@@ -85,6 +85,16 @@ int hostsim_warp_tables(int *desc, double *hc, int *hs, double *cab, double *T) 
     return 0;
 }
 
+// closed-form descriptors of the typed linear slots (wp::LipL turn rows, wp::DdL linear rows)
+int hostsim_lin_descriptors(int *lin_lip, int *lin_dd, int *desc_dd) {
+    const Consts K = make_consts();
+    wp::WarpTables W;
+    if (!wp::build_warp_tables(K, W)) return -1;
+    for (int t = 0; t < 96; t++) lin_lip[t] = W.desc_lin_lip[t];
+    for (int t = 0; t < 64; t++) { lin_dd[t] = W.desc_lin[t]; desc_dd[t] = W.desc_dd[t]; }
+    return 0;
+}
+
 // scenario generator of csrc/dcbf_gen.cuh on the host (the kernels call the same two functions)
 int hostsim_philox(uint32_t *c, uint32_t k0, uint32_t k1) { gen::philox4x32_10(c, k0, k1); return 0; }
 

@@ -154,6 +154,13 @@ def warp_tables():
     return dict(desc=desc, hc=hc, hs=hs, cab=cab, T=T)
 
 
+def lin_descriptors():
+    """closed-form descriptors of the typed linear slots (WarpTables::desc_lin_lip, desc_lin) and the DD dot-product descriptors"""
+    lip, dd, ddd = np.zeros(96, np.int32), np.zeros(64, np.int32), np.zeros(64, np.int32)
+    assert lib().hostsim_lin_descriptors(_p(lip, C.c_int32), _p(dd, C.c_int32), _p(ddd, C.c_int32)) == 0
+    return dict(lin_lip=lip, lin_dd=dd, desc_dd=ddd)
+
+
 def philox(counter, k0, k1):
     c = np.ascontiguousarray(counter, dtype=np.uint32).copy()
     lib().hostsim_philox(_p(c, C.c_uint32), C.c_uint32(k0), C.c_uint32(k1))

@@ -106,3 +106,30 @@ def test_gradient_coefficients_equal_feature_map():
             assert abs(cab[6 + i, 3 + l] * q0 - g[2 * l]) <= 1e-14 and abs(cab[6 + i, 3 + l] * q1 - g[2 * l + 1]) <= 1e-14
             assert cab[6 + i, l] == 0.0
     assert np.all(cab[9] == 0.0)
+
+
+def test_turn_row_descriptors_equal_the_dot_products_they_replace():
+    """wp::LipL keeps the three turn rows (gradient e_{6+i}) out of the dot products and adds their contribution in closed
+    form (WarpTables::desc_lin_lip): replaying the descriptors on random staged weights must give exactly what the generic dot
+    products over those three rows give"""
+    W, L = hs.warp_tables(), hs.lin_descriptors()
+    desc, lin = W["desc"], L["lin_lip"]
+    rng = np.random.default_rng(5)
+    N, NST, RP = 9, 22, 38
+    ST = np.zeros((NST, RP))
+    sig, wts = rng.uniform(0.1, 2.0, 3), rng.standard_normal((3, 3))
+    for i in range(3):                       # the turn row of step i is staged column 32 + i
+        ST[6 + i, 32 + i] = 1.0              # gradient e_{6+i}
+        ST[N + 6 + i, 32 + i] = sig[i]       # sigma * gradient
+        ST[2 * N, 32 + i] = sig[i]           # the weights sigma, w1, binv, y
+        ST[2 * N + 1:2 * N + 4, 32 + i] = wts[:, i]
+    n_used = 0
+    for t in range(72):
+        d = int(desc[t])
+        rowP, rowQ = d & 0xff, (d >> 8) & 0xff
+        want = float(ST[rowP, 32:35] @ ST[rowQ, 32:35])          # generic dot product restricted to the turn rows
+        dl = int(lin[t])
+        got = ST[(dl >> 8) & 0xff, dl >> 16] if dl & 1 else 0.0
+        assert got == want, (t, rowP, rowQ, got, want)
+        n_used += dl & 1
+    assert n_used == 3 + 9 and not lin[72:].any()                 # three diagonal entries, three components of three vectors
