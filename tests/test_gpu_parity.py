@@ -407,6 +407,35 @@ def test_size_class_split_is_transparent(gpu, monkeypatch):
     assert torch.equal(res.p_plan[other], ref.p_plan[other]) and torch.equal(res.iters[other], ref.iters[other])
 
 
+def test_size_class_split_with_empty_classes(gpu, monkeypatch):
+    """the three-class split when a class is empty: every obstacle out of detection range (all scenarios in the one-slot class) and
+    a batch made of five-obstacle scenarios only (typed turn-row slot class alone); same results as the unsplit launch"""
+    B = 8192
+    sc = scenarios.make_batch("modi", B, seed=44)
+    far_c, far_e = sc.cir.copy(), sc.elp.copy()
+    far_c[:, :, :2] += 100.0
+    far_e[:, :, :2] += 100.0
+    for cir, elp, idx in ((far_c, far_e, np.arange(B)), (sc.cir, sc.elp, None)):
+        monkeypatch.setenv("DCBF_SPLIT", "0")
+        s0 = gpu("modi", device=0)
+        s0.set_fields(cir, elp)
+        if idx is None:   # keep the scenarios that select exactly five obstacles
+            cnt = s0.setup_info(sc.x0, sc.goal, field=sc.field)["count"].cpu().numpy()
+            idx = np.nonzero(cnt == 5)[0]
+            assert len(idx) > 1000
+        a = (sc.x0[idx], sc.goal[idx], sc.leg[idx], sc.warm[idx])
+        ref = s0.solve(*a, field=sc.field[idx])
+        monkeypatch.setenv("DCBF_SPLIT", "1")
+        s1 = gpu("modi", device=0)
+        s1.set_fields(cir, elp)
+        res = s1.solve(*a, field=sc.field[idx])
+        torch.cuda.synchronize()
+        assert torch.equal(res.status, ref.status)
+        both = (res.status == 0) & (ref.status == 0)
+        dp = (res.p_plan - ref.p_plan).abs().reshape(len(idx), -1).max(dim=1).values[both]
+        assert both.any() and dp.max().item() <= 1e-4 and (dp <= 1e-9).double().mean().item() >= 0.97
+
+
 @pytest.mark.parametrize("form", ["sig_step", "dd"])
 def test_scheduling_order_is_transparent(gpu, monkeypatch, form):
     """batches of 2048+ scenarios are started in the order of their predicted clearance (hard problems first, so that none of them
