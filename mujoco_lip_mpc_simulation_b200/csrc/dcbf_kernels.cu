@@ -791,7 +791,12 @@ int dcbf_default_params(int formulation, dcbf_params *P) {
     // Warm-started re-plans start at a lower barrier parameter (Ipopt's usual warm-start setting): re-solving a plan at a state 1 cm /
     // 2 cm/s away takes 12.1 iterations with mu_init and 6.6 with 1e-4 (sig_step; modi 12.8 -> 7.9), same optima; the shifted plan of the
     // closed loop is infeasible by ~0.37 in its third step and does best with 1e-2 (13.3 -> 12.0).
-    P->mu_warm = 1e-4; P->mu_shift = 1e-2;
+    // With kappa_eps = 30 (below) the best first barrier parameter of the shifted plan moved from 1e-2 to 2.5e-3 (one barrier problem
+    // less: 11.05 -> 10.51 iterations per re-plan of the closed loop; the step is between 3e-3 and 4e-3).  The verbatim warm start
+    // stays at 1e-4: 3e-5 / 1e-5 lower the MEAN (sig_step 6.75 -> 6.27 / 6.06 iterations, modi 8.20 -> 7.95) but lengthen the tail --
+    // on 65 536 warm modi ticks the slowest problem goes from 152 to 181 / 200 iterations and the batch from 8.2 to 10.1 / 11.5 ms
+    // (tools/probe_warm_tick.py).
+    P->mu_warm = 1e-4; P->mu_shift = 2.5e-3;
     P->tiny_alpha = formulation == DCBF_DD ? 5e-2 : 1e-2;
     P->tiny_count = formulation == DCBF_DD ? 2 : 3;
     // Stagnation window of the restoration phase.  10 % for sig_step and the differential drive: 32 768 + 65 536 sig_step scenarios keep

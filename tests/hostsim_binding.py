@@ -50,7 +50,7 @@ def default_params(form) -> DcbfParams:
     P.tol, P.constr_viol_tol, P.mu_init = 1e-8, 1e-4, 0.1
     P.max_iter = 200
     P.tiny_alpha, P.tiny_count = (5e-2, 2) if f == 2 else (1e-2, 3)
-    P.mu_warm, P.mu_shift = 1e-4, 1e-2
+    P.mu_warm, P.mu_shift = 1e-4, 2.5e-3
     P.resto_window = 1e-2 if f == 1 else 0.1
     P.kappa_eps = (30.0, 30.0, 10.0)[f]
     if f == 0:
