@@ -1273,7 +1273,7 @@ static int solve_host_impl(dcbf_ctx *ctx, bool async, int32_t B, const double *x
     const Piece outs[8] = {{nullptr, u, o_u, 8 * nu * b}, {nullptr, x_plan, o_xp, 8 * 3 * nx * b}, {nullptr, dd ? nullptr : p_plan, o_pp, 8 * 9 * b},
                            {nullptr, obj, o_obj, 8 * b}, {nullptr, viol, o_viol, 8 * b}, {nullptr, status, o_st, 4 * b},
                            {nullptr, iters, o_it, 4 * b}, {nullptr, close2goal, o_cl, b}};
-    bool in_pinned = B >= 256, out_pinned = B >= 256;
+    bool in_pinned = async || B >= 256, out_pinned = in_pinned;   // (the enqueue-only entry point has no staged path to fall back to)
     for (int i = 0; i < 6 && in_pinned; i++) if (ins[i].src && !is_pinned_host(ins[i].src)) in_pinned = false;
     for (int i = 0; i < 8 && out_pinned; i++) if (outs[i].dst && !is_pinned_host(outs[i].dst)) out_pinned = false;
     // Page-locked buffers on both sides and a warp kernel (coalesced per-problem reads and writes): no copies at all, the kernels

@@ -497,6 +497,9 @@ def test_host_pipeline_delivers_the_results_of_the_synchronous_call(gpu):
     b = batches[0]
     with pytest.raises(RuntimeError):
         pipe.solvers[0].solve_host(b.x0, b.goal, b.leg, b.warm, field=b.field, wait=False)     # pageable buffers
+    small, _ = pipe.submit(pin(b.x0[:7]), pin(b.goal[:7]), pin(b.leg[:7].astype(np.int32)), pin(b.warm[:7]), field=pin(b.field[:7].astype(np.int32)))
+    pipe.drain()                                                                                # a tiny batch takes the same path
+    assert np.array_equal(small.status, refs[0].status[:7]) and np.array_equal(small.p_plan, refs[0].p_plan[:7])
 
 
 def test_error_codes(gpu):
