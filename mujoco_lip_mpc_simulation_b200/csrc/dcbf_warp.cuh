@@ -1454,9 +1454,10 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                 const double dzu = S.mu * ih - rzu_ + rzu_ * ih * d;
                 rel_ = dzl; reu_ = dzu;
                 dphi += S.mu * d * ((bb.has_hi ? ih : 0.0) - (bb.has_lo ? il : 0.0));
-                const double tl = -tau * gl, th = tau * gh;
-                const double a1 = fdiv(tl, d), a2 = fdiv(th, d);
-                amax = fmin(amax, fmin(bb.has_lo && d < 0.0 ? a1 : 1.0, bb.has_hi && d > 0.0 ? a2 : 1.0));
+                // fraction to the boundary of the slack: only the side the slack moves towards can bind, so one division serves both
+                const bool down = d < 0.0;
+                const double a12 = fdiv(down ? -tau * gl : tau * gh, d);
+                amax = fmin(amax, (down ? bb.has_lo : (bb.has_hi && d > 0.0)) ? a12 : 1.0);
                 const double z1 = fdiv(-tau * rzl_, dzl), z2 = fdiv(-tau * rzu_, dzu);
                 az = fmin(az, fmin(bb.has_lo && dzl < 0.0 ? z1 : 1.0, bb.has_hi && dzu < 0.0 ? z2 : 1.0));
                 DCBF_ROW_END
