@@ -101,7 +101,7 @@ DCBF_CE int THI(int l) { return 6 + l; }
 #define DCBF_LM_DOWN 0.2             /* ... and after an accepted one */
 #endif
 #ifndef DCBF_RESTO_WINDOW
-#define DCBF_RESTO_WINDOW 1e-2       /* restoration: relative decrease of the squared violation over three steps (default of dcbf_params::resto_window for modi) */
+#define DCBF_RESTO_WINDOW 1e-2       /* restoration: relative decrease of the squared violation over three steps (round-1 value; now dcbf_params::resto_window) */
 #endif
 #ifdef DCBF_COUNT
 static long g_trials = 0;

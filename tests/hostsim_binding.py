@@ -51,7 +51,7 @@ def default_params(form) -> DcbfParams:
     P.max_iter = 200
     P.tiny_alpha, P.tiny_count = (5e-2, 2) if f == 2 else (1e-2, 3)
     P.mu_warm, P.mu_shift = 1e-4, 2.5e-3
-    P.resto_window = 1e-2 if f == 1 else 0.1
+    P.resto_window = 1e-3 if f == 1 else 0.1
     P.kappa_eps = (30.0, 30.0, 10.0)[f]
     if f == 0:
         P.w_p, P.w_r, P.gamma, P.s_turn, P.bvy_max = 2.0, 15.0, 0.4, 0.014 * 180 / math.pi, 0.3
