@@ -17,10 +17,13 @@
 //     quantities through a host-built sparse table (at most 6 terms per entry);
 //   * norms, merit values and step sizes are warp-shuffle reductions; the 9x9 Cholesky is row-owned (lane i owns row
 //     i, lane 9 carries the right-hand side as a tenth row, which is the forward substitution) with the factor staged
-//     in shared memory; all scalar control flow is replicated and therefore uniform.
+//     in shared memory at a fixed row stride (see LF_DIAG); all scalar control flow is replicated and therefore uniform.
 // The interior-point driver (solve_warp) is written once against a small model interface -- rows, nodes, gradient staging,
-// Hessian sources -- and instantiated for the LIP formulations (LipW, 9 variables) and the differential-drive formulation
-// (DdW, 6 variables; node Jacobians are recomputed per iterate because the unicycle rollout is not affine).
+// Hessian sources -- and instantiated for the LIP formulations (LipW generic row slots, LipL with the three turn rows in a typed
+// linear slot; 9 variables) and the differential-drive formulation (DdW / DdL, 6 variables; node Jacobians are recomputed per
+// iterate because the unicycle rollout is not affine).
+// The one-slot LIP kernel and DdL are built for 128 registers, i.e. 16 warps per SM (LaneRefresh: per-lane invariants are
+// recomputed per iteration instead of being carried in registers; cold solver state lives in WarpShared::cold).
 // The algorithm (barrier rule, filter, restoration, status codes) is the one of ipm_iterate() in dcbf_core.cuh.
 #pragma once
 #include "dcbf_lanes.cuh"
