@@ -500,6 +500,17 @@ def test_host_pipeline_delivers_the_results_of_the_synchronous_call(gpu):
     small, _ = pipe.submit(pin(b.x0[:7]), pin(b.goal[:7]), pin(b.leg[:7].astype(np.int32)), pin(b.warm[:7]), field=pin(b.field[:7].astype(np.int32)))
     pipe.drain()                                                                                # a tiny batch takes the same path
     assert np.array_equal(small.status, refs[0].status[:7]) and np.array_equal(small.p_plan, refs[0].p_plan[:7])
+    pipe.solvers[0].wait()                                                                      # nothing pending: returns at once
+    # differential drive through the same entry points (previous control, no p_plan)
+    sd = scenarios.make_batch("dd", 300, seed=66)
+    ref = _solver(gpu, "dd", sd)
+    ref.set_fields_host(sd.cir, sd.elp)
+    rd = ref.solve_host(sd.x0, sd.goal, sd.leg, sd.warm, field=sd.field, last_u=sd.last_u)
+    pd = HostPipeline("dd", lanes=2, device=0)
+    pd.set_fields_host(sd.cir, sd.elp)
+    od, _ = pd.submit(pin(sd.x0), pin(sd.goal), pin(sd.leg.astype(np.int32)), pin(sd.warm), field=pin(sd.field.astype(np.int32)), last_u=pin(sd.last_u))
+    pd.drain()
+    assert od.p_plan is None and np.array_equal(od.status, rd.status) and np.array_equal(od.u, rd.u) and np.array_equal(od.x_plan, rd.x_plan)
 
 
 def test_error_codes(gpu):
