@@ -859,7 +859,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
         delete W;
         if (!ok) { cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); delete ctx; return DCBF_ERR_CUDA; }
     }
-    { const char *sp = getenv("DCBF_SPLIT"); ctx->split_classes = sp ? atoi(sp) : 8192; }   // measured: 8192 scenarios 3.78 -> 3.20 ms, 4096 scenarios 1.89 -> 2.09 ms
+    { const char *sp = getenv("DCBF_SPLIT"); ctx->split_classes = sp ? atoi(sp) : 5120; }   // measured (unsplit -> split): 4096 scenarios 1.84 -> 2.05 ms, 5120 2.04 -> 1.64, 6144 2.21 -> 1.92, 8192 3.58 -> 3.01
     { const char *sp = getenv("DCBF_ORDER"); ctx->sched_min_batch = sp ? atoi(sp) : 2048; }
     { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }
@@ -989,7 +989,7 @@ static int solve_impl(dcbf_ctx *ctx, int32_t B, const double *x0, const double *
     else if (dd) solve_dd_kernel<<<grid_for(ctx, B), DCBF_BLOCK, 0, st>>>(ctx->P, ctx->K, B, in, out);
     else if (use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);
-        const bool split = ns > 1 && ctx->P.select_obs && ctx->split_classes > 0 && B >= ctx->split_classes;   // measured: pays from ~8 k scenarios
+        const bool split = ns > 1 && ctx->P.select_obs && ctx->split_classes > 0 && B >= ctx->split_classes;   // measured: pays from ~5 k scenarios
         const int rc = ns == 1 ? launch_solve_warp<1>(ctx, B, in, out, st)
                      : split ? (ns == 2 ? launch_solve_split<2>(ctx, B, in, out, st) : launch_solve_split<4>(ctx, B, in, out, st))
                              : (ns == 2 ? launch_solve_warp<2>(ctx, B, in, out, st) : launch_solve_warp<4>(ctx, B, in, out, st));

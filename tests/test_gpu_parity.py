@@ -373,7 +373,7 @@ def test_host_buffer_entry_point_equals_device_entry_point(gpu):
 
 
 def test_size_class_split_is_transparent(gpu, monkeypatch):
-    """modi batches from 8 192 scenarios on are split by selected-obstacle count (classify pre-pass; one-slot kernel, typed
+    """modi batches from 5 120 scenarios on are split by selected-obstacle count (classify pre-pass; one-slot kernel, typed
     turn-row slot kernel wp::LipL and generic two-slot kernel on forked streams).  With two classes (DCBF_LIPL=0) every scenario
     gets the result of the unsplit launch bit for bit; the LipL class adds the turn rows to the condensed system in closed form
     instead of through the dot products, i.e. in a different summation order: same status everywhere, same plans to rounding"""
