@@ -237,7 +237,7 @@ int dcbf_gen_states(dcbf_ctx *ctx, int32_t B, uint64_t seed, const int32_t *fiel
                     int32_t *attempts, void *stream);
 
 /* Test hook: the lean FP64 elementary functions of the kernels (csrc/dcbf_math.cuh) evaluated on the device.
- * out[n][6] = (sin a, cos a, atan2(a, b), 1 / b, a / b, 1 / sqrt(|b|)); a, b, out are device pointers. */
+ * out[n][7] = (sin a, cos a, atan2(a, b), 1 / b, a / b, 1 / sqrt(|b|), log |b|); a, b, out are device pointers. */
 int dcbf_math_probe(dcbf_ctx *ctx, int32_t n, const double *a, const double *b, double *out, void *stream);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

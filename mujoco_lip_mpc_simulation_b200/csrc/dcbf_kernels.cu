@@ -512,8 +512,9 @@ __global__ void math_probe_kernel(int n, const double *__restrict__ a, const dou
     if (i >= n) return;
     double s, c;
     fsincos(a[i], &s, &c);
-    double *o = out + 6 * (size_t)i;
+    double *o = out + 7 * (size_t)i;
     o[0] = s; o[1] = c; o[2] = fatan2(a[i], b[i]); o[3] = dcbf::frcp(b[i]); o[4] = dcbf::fdiv(a[i], b[i]); o[5] = dcbf::frsqrt(fabs(b[i]));
+    o[6] = dcbf::flog(fabs(b[i]));
 }
 
 // Scenario generation (dcbf_gen.cuh): one thread per obstacle field / per start state

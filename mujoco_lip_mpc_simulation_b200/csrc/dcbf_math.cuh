@@ -9,6 +9,7 @@
 //              Cephes atan rational P4/Q5 on |t| <= 0.66                                         < 2e-16 absolute
 //   frcp/fdiv: MUFU.RCP64H seed + two Newton steps (+ one residual step for the quotient)       <= 1 ulp (normal range)
 //   frsqrt   : MUFU.RSQ64H seed + two Newton steps                                              <= 2 ulp (pivots of the Cholesky)
+//   flog     : fdlibm log kernel without the special cases (barrier sums of the warp kernels)    < 1 ulp
 // The file compiles for the host too (tests/hostsim, tests/test_math_cpu.py checks every function against libm).
 #pragma once
 #include <math.h>
@@ -57,6 +58,37 @@ DCBF_MHD double frsqrt(double x) {
 #else
     return 1.0 / sqrt(x);
 #endif
+}
+
+// natural logarithm of a normal positive x (fdlibm __ieee754_log without its special cases: the arguments are products of slack gaps,
+// 1e-40 ... 1e6; a non-positive or non-finite argument returns a meaningless finite number -- the callers reject such trial points on
+// the sign of the gaps).  x = 2^k m, m in [sqrt(1/2), sqrt(2)), log m = 2 s + s R(s^2), s = f / (2 + f), f = m - 1;  < 1 ulp
+DCBF_MHD double flog(double x) {
+    int64_t bits;
+#if defined(__CUDA_ARCH__)
+    bits = __double_as_longlong(x);
+#else
+    memcpy(&bits, &x, sizeof(bits));
+#endif
+    int hx = (int)(bits >> 32);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;                  // mantissa >= sqrt(2): use m / 2 and k + 1
+    k += i >> 20;
+    bits = ((int64_t)(hx | (i ^ 0x3ff00000)) << 32) | (bits & 0xffffffffll);
+    double m;
+#if defined(__CUDA_ARCH__)
+    m = __longlong_as_double(bits);
+#else
+    memcpy(&m, &bits, sizeof(m));
+#endif
+    const double f = m - 1.0, dk = (double)k;
+    const double s = fdiv(f, 2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double R = t2 + t1, hfsq = 0.5 * f * f;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
 }
 
 // sin and cos of a (|a| < 1e5)

@@ -1213,7 +1213,7 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                     t_z = rzl_ + rzu_;
                     const double lp = gl * gh;
                     rel_ = il; reu_ = ih;
-                    if (!carry_ok) { if (ROLLED || NS == 1) t_log = dlog(lp); else gap_prod *= lp; }
+                    if (!carry_ok) { if (ROLLED || NS == 1) t_log = flog(lp); else gap_prod *= lp; }
                     rds_ = rc;
                     t_rc = fabs(rc);
                     w1 = sig * rc;
@@ -1230,7 +1230,7 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
             st8.m0 = fmax(st8.m0, t_rc); st8.m1 = fmin(st8.m1, t_cmin); st8.m2 = fmax(st8.m2, t_cmax); st8.m3 = fmax(st8.m3, t_v);
             DCBF_ROW_END
         }
-        if (!ROLLED && NS > 1 && !resto && !carry_ok) st8.s2 = dlog(gap_prod);
+        if (!ROLLED && NS > 1 && !resto && !carry_ok) st8.s2 = flog(gap_prod);
         __syncwarp();   // the row branches reconverge here, before the shuffles
         reduce8_inline(st8, lane);
         const double st_theta = st8.s0, st_zsum = st8.s1, st_logsum = carry_ok ? sm.cold[C_CARRY_LOG] : st8.s2, st_v2 = st8.s3, st_pinf = st8.m0,
@@ -1498,9 +1498,9 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                 th_t += fabs(e.c - stv);
                 const double gl = bb.has_lo ? stv - relax_lo(bb.lo) : 1.0, gh = bb.has_hi ? relax_hi(bb.hi) - stv : 1.0;
                 okv = okv && gl > 0.0 && gh > 0.0;
-                if (ROLLED || NS == 1) lg_t += dlog(gl * gh); else gp_t *= gl * gh;
+                if (ROLLED || NS == 1) lg_t += flog(gl * gh); else gp_t *= gl * gh;
             }
-            if (!ROLLED && NS > 1) lg_t = dlog(gp_t);   // (a trial with a non-positive gap is rejected by okv below, whatever this is)
+            if (!ROLLED && NS > 1) lg_t = flog(gp_t);   // (a trial with a non-positive gap is rejected by okv below, whatever this is)
             __syncwarp();
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

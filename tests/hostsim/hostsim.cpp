@@ -71,6 +71,11 @@ int hostsim_math(int n, const double *a, double *sn, double *cs, const double *y
     return 0;
 }
 
+int hostsim_log(int n, const double *x, double *out) {
+    for (int i = 0; i < n; i++) out[i] = flog(x[i]);
+    return 0;
+}
+
 // constant tables of the warp kernels + the dense feature map they are derived from
 int hostsim_warp_tables(int *desc, double *hc, int *hs, double *cab, double *T) {
     const Consts K = make_consts();

@@ -145,6 +145,14 @@ def lean_math(a, y, x):
     return sn, cs, at
 
 
+def lean_log(x):
+    """flog of csrc/dcbf_math.cuh evaluated on the host."""
+    x = _d(x).ravel()
+    out = np.zeros(len(x))
+    lib().hostsim_log(len(x), _p(x), _p(out))
+    return out
+
+
 def warp_tables():
     """Constant tables of the warp kernels (csrc/dcbf_warp.cuh: build_warp_tables) and the dense feature map."""
     desc, hs = np.zeros(96, np.int32), np.zeros((6, 48), np.int32)

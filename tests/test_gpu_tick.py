@@ -125,7 +125,7 @@ def test_lean_elementary_functions_on_the_device():
     b = np.concatenate([rng.uniform(-12, 12, n // 2), 10.0 ** rng.uniform(-12, 3, n // 2) * rng.choice([-1, 1], n // 2)])
     s = DcbfSolver("sig_step", device=0)
     ta, tb = torch.as_tensor(a, device="cuda"), torch.as_tensor(b, device="cuda")
-    out = torch.empty((n, 6), dtype=torch.float64, device="cuda")
+    out = torch.empty((n, 7), dtype=torch.float64, device="cuda")
     assert s.lib.dcbf_math_probe(s._ctx, n, _ptr(ta), _ptr(tb), _ptr(out), s._stream()) == 0
     torch.cuda.synchronize()
     o = out.cpu().numpy()
@@ -134,6 +134,8 @@ def test_lean_elementary_functions_on_the_device():
     assert np.max(np.abs(o[:, 3] * b - 1.0)) <= 3e-16
     assert np.max(np.abs(o[:, 4] - a / b) / np.abs(a / b)) <= 3e-16
     assert np.max(np.abs(o[:, 5] * np.sqrt(np.abs(b)) - 1.0)) <= 5e-16
+    lg = np.log(np.abs(b))
+    assert np.max(np.abs(o[:, 6] - lg) / np.spacing(np.abs(lg))) <= 1.0                        # flog: within one ulp of libm
 
 
 def test_eval_kernel_reproduces_recorded_labels():
