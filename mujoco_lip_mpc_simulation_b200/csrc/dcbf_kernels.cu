@@ -54,7 +54,8 @@ struct dcbf_ctx {
     int *d_order; size_t order_cap;   // size-class split of obstacle-selecting formulations: [counts(3) + pad | class 0 list | class 1 list | class 2 list]
     cudaStream_t aux_stream, aux_stream2; cudaEvent_t ev_fork, ev_join, ev_join2;
     int split_classes;   // smallest batch that is split by size class (env DCBF_SPLIT; 0 = never)
-    int *d_sched; size_t sched_cap;   // longest-expected-first order of a batch: [counts(16) | rank(B) | order(B)]
+    int *d_sched; size_t sched_cap;   // longest-expected-first order of a batch: [counts(16) x 2 | rank(B) | order(B)]
+    int sched_flip; bool sched_clean; // which set of bucket counters the next batch uses; false: both sets are cleared first
     int sched_min_batch;              // smallest batch that is ordered (env DCBF_ORDER; 0 = never)
     int sched_select;                 // order obstacle-selecting formulations too (env DCBF_ORDER_SELECT)
     int zero_copy;                    // dcbf_solve_host reads / writes page-locked caller buffers from the kernels (env DCBF_ZEROCOPY)
@@ -194,8 +195,13 @@ __global__ void __launch_bounds__(256) sched_classify_kernel(dcbf_params P, int 
     __syncthreads();
     if (b < B) rank[b] = (s_base[c] + local) | (c << 27);
 }
-__global__ void sched_scatter_kernel(int B, const int *__restrict__ counts, const int *__restrict__ rank, int *__restrict__ order) {
+// (also clears what the next kernels count in: the bucket counters of the NEXT batch's classify pass -- the two sets alternate -- and
+// the work counter of the solve kernel behind it: no memset nodes between the kernels of a step)
+__global__ void sched_scatter_kernel(int B, const int *__restrict__ counts, const int *__restrict__ rank, int *__restrict__ order,
+                                     int *__restrict__ counts_next, int *__restrict__ work_counter) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < DCBF_SCHED_BUCKETS) counts_next[b] = 0;
+    if (b == 0 && work_counter) *work_counter = 0;
     if (b >= B) return;
     const int c = rank[b] >> 27;
     int off = 0;
@@ -666,34 +672,42 @@ static int warp_grid(const dcbf_ctx *ctx, int n, int ctas_per_sm) {
 }
 
 // longest-expected-first order of the batch (see sched_classify_kernel); nullptr when the batch is too small to have a tail
-static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t st, const int **order) {
+static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t st, const int **order, int *work_counter = nullptr, bool *counter_cleared = nullptr) {
     *order = nullptr;
+    if (counter_cleared) *counter_cleared = false;
     if (ctx->sched_min_batch <= 0 || B < ctx->sched_min_batch || B > DCBF_SCHED_MAX_BATCH || in.Kc + in.Ke == 0 || (ctx->P.select_obs && !ctx->sched_select)) return DCBF_OK;
     if (ctx->sched_cap < (size_t)B) {
         CK(cudaFree(ctx->d_sched));
         ctx->d_sched = nullptr; ctx->sched_cap = 0;
-        CK(cudaMalloc(&ctx->d_sched, sizeof(int) * (2 * (size_t)B + DCBF_SCHED_BUCKETS)));
+        CK(cudaMalloc(&ctx->d_sched, sizeof(int) * (2 * (size_t)B + 2 * DCBF_SCHED_BUCKETS)));
         ctx->sched_cap = (size_t)B;
+        ctx->sched_clean = false;
     }
-    int *counts = ctx->d_sched, *rank = counts + DCBF_SCHED_BUCKETS, *ord = rank + ctx->sched_cap;
-    CK(cudaMemsetAsync(counts, 0, DCBF_SCHED_BUCKETS * sizeof(int), st));
+    // two sets of bucket counters used alternately: the scatter kernel of one batch clears the set of the next one
+    if (!ctx->sched_clean) { CK(cudaMemsetAsync(ctx->d_sched, 0, 2 * DCBF_SCHED_BUCKETS * sizeof(int), st)); ctx->sched_flip = 0; }
+    ctx->sched_clean = false;   // (stays false if a launch below fails: the next call starts from cleared counters)
+    int *counts = ctx->d_sched + DCBF_SCHED_BUCKETS * ctx->sched_flip, *counts_next = ctx->d_sched + DCBF_SCHED_BUCKETS * (1 - ctx->sched_flip);
+    int *rank = ctx->d_sched + 2 * DCBF_SCHED_BUCKETS, *ord = rank + ctx->sched_cap;
     sched_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->P, B, in, counts, rank);
-    sched_scatter_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, counts, rank, ord);
+    sched_scatter_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, counts, rank, ord, counts_next, work_counter);
     CK(cudaGetLastError());
+    ctx->sched_flip ^= 1; ctx->sched_clean = true;
     ctx->launches += 2;
     *order = ord;
+    if (counter_cleared) *counter_cleared = work_counter != nullptr;
     return DCBF_OK;
 }
 
 template <int NS, class M = wp::LipW>
 static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st, int slot = 0, const int *order = nullptr,
                              const int *count = nullptr) {
+    int *counter = ctx->d_counter + 1 + slot;
+    bool cleared = false;
     if (!order) {
-        const int rc = schedule_order(ctx, B, in, st, &order);
+        const int rc = schedule_order(ctx, B, in, st, &order, counter, &cleared);
         if (rc != DCBF_OK) return rc;
     }
-    int *counter = ctx->d_counter + 1 + slot;
-    CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    if (!cleared) CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = warp_grid<M, NS>(ctx, B, MinCtas<M, NS>::v);
     solve_lip_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, count, counter);
     CK(cudaGetLastError());
@@ -703,10 +717,11 @@ static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const Solv
 template <class M, int NS>
 static int launch_solve_dd_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const SolveOut &out, cudaStream_t st) {
     const int *order = nullptr;
-    const int rc = schedule_order(ctx, B, in, st, &order);
-    if (rc != DCBF_OK) return rc;
     int *counter = ctx->d_counter + 1;
-    CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    bool cleared = false;
+    const int rc = schedule_order(ctx, B, in, st, &order, counter, &cleared);
+    if (rc != DCBF_OK) return rc;
+    if (!cleared) CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = warp_grid<M, NS>(ctx, B, DCBF_DD_MIN_CTAS(M, NS));
     solve_dd_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, counter);
     CK(cudaGetLastError());

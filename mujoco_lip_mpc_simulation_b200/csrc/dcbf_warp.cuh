@@ -309,6 +309,12 @@ template <int NS> struct Wpc<DdL, NS> { static constexpr int v = DCBF_WPC_DDL; }
 #ifndef DCBF_REFRESH_BOUNDS
 #define DCBF_REFRESH_BOUNDS(NS) ((NS) > 1)
 #endif
+// Cholesky with the next pivot formed ahead of the shared-memory round trip of the column (solve_warp): the one-slot kernels, whose
+// iteration is a chain of dependent latencies (4096-scenario step -1.0 %, identical bits; the multi-slot kernels lose 1-2 % with it).
+#ifndef DCBF_PIVOT_AHEAD
+#define DCBF_PIVOT_AHEAD(NS) ((NS) == 1)
+#endif
+template <class M, int NS> struct PivotAhead { static constexpr bool v = DCBF_PIVOT_AHEAD(NS); };
 template <class M, int NS> struct LaneRefresh { static constexpr bool v = false; };
 template <> struct LaneRefresh<LipW, 1> { static constexpr bool v = DCBF_LANE_REFRESH != 0; };
 #ifndef DCBF_LANE_REFRESH_LIPL
@@ -1343,20 +1349,48 @@ __device__ void solve_warp(const dcbf_params &P, const BatchIn &in, int b, int l
                     sm.KQ[KQ_K + diag_ix] = kd + shift;
                     __syncwarp();
                 }
-                double Lrow[N];
                 ok = true;
+                if constexpr (PivotAhead<M, NS>::v) {
+                    // Right-looking on the lane's own row (sv[k] = K[lane][k] minus the columns done so far, subtracted in the same order
+                    // as a left-looking sweep would: identical bits).  The serial chain of a column is pivot -> shuffle -> rsqrt -> scale:
+                    // the pivot of column j + 1 is formed on its own lane from that lane's own L[j+1][j] (piv), so the round trip of column j
+                    // through shared memory (store, barrier, loads, trailing update of the other entries) runs beside the shuffle and the
+                    // rsqrt of the next column instead of in front of them.
+                    double sv[N];
 #pragma unroll
-                for (int j = 0; j < N; j++) {
-                    double s_ = sm.KQ[KQ_K + rowbase + j];
+                    for (int j = 0; j < N; j++) sv[j] = sm.KQ[KQ_K + rowbase + j];
+                    double piv = sv[0], Lprev = 0.0;
 #pragma unroll
-                    for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[j * N + c], s_);
-                    const double d = __shfl_sync(FULL, s_, j);
-                    if (!(d > 1e-14)) { ok = false; break; }
-                    const double rinv = frsqrt(d);
-                    Lrow[j] = s_ * rinv;
-                    if (lane > j) sm.Lf[lbase + j] = Lrow[j];
-                    sm.Lf[LF_DIAG + j] = rinv;   // diagonal as its reciprocal (every lane stores the same value)
-                    __syncwarp();
+                    for (int j = 0; j < N; j++) {
+                        const double d = __shfl_sync(FULL, piv, j);
+                        if (j > 0) {   // trailing update by column j - 1 (stored and synchronised at the end of the previous column)
+#pragma unroll
+                            for (int k = j; k < N; k++) sv[k] = fma(-Lprev, sm.Lf[k * N + (j - 1)], sv[k]);
+                        }
+                        if (!(d > 1e-14)) { ok = false; break; }
+                        const double rinv = frsqrt(d);
+                        const double Lj = sv[j] * rinv;
+                        if (j + 1 < N) piv = fma(-Lj, Lj, sv[j + 1]);   // = the updated sv[j + 1] of lane j + 1 (L[j+1][j] is its own Lj)
+                        if (lane > j) sm.Lf[lbase + j] = Lj;
+                        sm.Lf[LF_DIAG + j] = rinv;   // diagonal as its reciprocal (every lane stores the same value)
+                        __syncwarp();
+                        Lprev = Lj;
+                    }
+                } else {   // left-looking sweep: fewer live registers; the multi-slot kernels are bound by instruction supply, not by this chain
+                    double Lrow[N];
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        double s_ = sm.KQ[KQ_K + rowbase + j];
+#pragma unroll
+                        for (int c = 0; c < j; c++) s_ = fma(-Lrow[c], sm.Lf[j * N + c], s_);
+                        const double d = __shfl_sync(FULL, s_, j);
+                        if (!(d > 1e-14)) { ok = false; break; }
+                        const double rinv = frsqrt(d);
+                        Lrow[j] = s_ * rinv;
+                        if (lane > j) sm.Lf[lbase + j] = Lrow[j];
+                        sm.Lf[LF_DIAG + j] = rinv;   // diagonal as its reciprocal (every lane stores the same value)
+                        __syncwarp();
+                    }
                 }
                 if (ok || resto) break;
                 const double dl = sm.cold[C_DELTA_LAST];
