@@ -70,9 +70,16 @@ def ncu_traffic():
         return None, None
 
 
+# config 2 is a COLD start: the start vector is the reference's rule for init_guess = None, [x_k, x_k, x_k]
+# (MPC_LIP_sig_step.py:185-187).  The entry points form it on the device when no start vector is passed (warm = NULL), so neither arm
+# of the bench ships 120 bytes per scenario that are a copy of x0 (identical results: tests/test_gpu_parity.py,
+# test_cold_start_rule_without_a_start_vector).
+COLD_RULE_ON_DEVICE = True
+
+
 def io_bytes_per_solve(kc: int) -> int:
-    """batch I/O of one sig_step solve: x0, goal, warm, leg, field + the obstacle records read + all outputs."""
-    return (5 + 2 + 15) * 8 + 4 + 4 + 24 * kc + (15 + 15 + 9 + 1 + 1) * 8 + 4 + 4 + 1
+    """batch I/O of one sig_step solve: x0, goal, (warm,) leg, field + the obstacle records read + all outputs."""
+    return (5 + 2 + (0 if COLD_RULE_ON_DEVICE else 15)) * 8 + 4 + 4 + 24 * kc + (15 + 15 + 9 + 1 + 1) * 8 + 4 + 4 + 1
 
 
 class ClockSampler(threading.Thread):
@@ -198,7 +205,7 @@ def main():
         x0, goal, leg, field, warm = dev_in[(rank + s_) % POOL]
         flush.zero_()                      # L2 flush between timed iterations (inputs are far smaller than L2)
         ev0.record()
-        solver.solve_into(B, x0, goal, leg, field, warm, None, out)
+        solver.solve_into(B, x0, goal, leg, field, None if COLD_RULE_ON_DEVICE else warm, None, out)
         ev1.record()
         it_acc.add_(out.iters.sum())       # outside the event bracket: iterations of this step, for the roofline
 
@@ -253,7 +260,7 @@ def main():
             sv_, o_, st_ = lanes[s_ % n_lanes]
             x0, goal, leg, field, warm = dev_in[(rank + s_) % POOL]
             with torch.cuda.stream(st_):
-                sv_.solve_into(B, x0, goal, leg, field, warm, None, o_)
+                sv_.solve_into(B, x0, goal, leg, field, None if COLD_RULE_ON_DEVICE else warm, None, o_)
         for _, _, st_ in lanes:
             cur.wait_stream(st_)
         p1.record(cur)
@@ -278,7 +285,7 @@ def main():
 
     def host_step(s_):
         hx0, hgoal, hleg, hwarm, hfield = host_in[(rank + s_) % POOL]
-        solver.solve_host(hx0, hgoal, hleg, hwarm, field=hfield, out=hres)
+        solver.solve_host(hx0, hgoal, hleg, None if COLD_RULE_ON_DEVICE else hwarm, field=hfield, out=hres)
     for s_ in range(3):
         host_step(s_)
     if world > 1:
@@ -306,7 +313,7 @@ def main():
         t0_ = time.perf_counter()
         for s_ in range(n_steps):
             hx0, hgoal, hleg, hwarm, hfield = host_in[(rank + s_) % POOL]
-            hp_.submit(hx0, hgoal, hleg, hwarm, field=hfield, out=hp_outs[s_ % 3])    # waits for the lane's previous batch first
+            hp_.submit(hx0, hgoal, hleg, None if COLD_RULE_ON_DEVICE else hwarm, field=hfield, out=hp_outs[s_ % 3])    # waits for the lane's previous batch first
         hp_.drain()
         return time.perf_counter() - t0_
     host_pipelined(6)
@@ -318,7 +325,7 @@ def main():
     hx0, hgoal, hleg, hwarm, hfield = host_in[last_b]
     assert np.array_equal(hp_outs[(e2e_pipe_steps - 1) % 3].status, solver.solve_host(hx0, hgoal, hleg, hwarm, field=hfield).status)
     del hp_
-    h2d = B * ((5 + 2 + 15 + 2) * 8 + 4 + 4)
+    h2d = B * ((5 + 2 + (0 if COLD_RULE_ON_DEVICE else 15)) * 8 + 4 + 4)   # x0, goal, (start vector,) leg, field
     d2h = B * ((15 + 15 + 9 + 1 + 1) * 8 + 4 + 4 + 1)
 
     # ---- p50 single-solve latency (B = 1, launch to result, host buffers) ------------------------------------------------
@@ -530,6 +537,9 @@ def main():
                     "transfer": ("page-locked host buffers through dcbf_solve_host; the kernels load the inputs from and store the results to the "
                                  "mapped host memory (no staging copy)" if os.environ.get("DCBF_ZEROCOPY", "1") != "0" else
                                  "page-locked host buffers through dcbf_solve_host, cudaMemcpyAsync each way"),
+                    "inputs": ("x0, goal, leg, field per scenario; the cold-start vector [x_k, x_k, x_k] (reference: init_guess = None, "
+                               "MPC_LIP_sig_step.py:185-187) is formed on the device (warm = NULL)" if COLD_RULE_ON_DEVICE else
+                               "x0, goal, leg, field and the start vector per scenario"),
                     "pipelined": {"value": world * B * e2e_pipe_steps / e2e_pipe_s, "unit": "solves/s", "steps": e2e_pipe_steps, "lanes": 3,
                                   "how": "dcbf_solve_host_async on three contexts used round-robin (HostPipeline), wall clock over all steps incl. the "
                                          "final waits; same page-locked inputs and full results per step as `value` of this object"}},

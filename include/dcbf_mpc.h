@@ -119,7 +119,9 @@ int dcbf_eval(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, co
 
 /* K1+K2: one re-plan per scenario.  Inputs: x0[B][5|3], goal[B][2], leg[B] (+1/-1; dd: ignored, may be NULL),
  * field[B] (NULL => field 0 for every scenario), warm[B][15|6] = the reference's u0 (MPC_LIP_sig_step.py:185-189
- * builds it from the previous plan; the caller passes the final vector), last_u[B][2] (dd only).
+ * builds it from the previous plan; the caller passes the final vector; LIP formulations: NULL => [x_k, x_k, x_k], the
+ * reference's start vector for init_guess = None, formed on the device -- 120 bytes per scenario less to read, which is
+ * most of what a host-buffer call moves over PCIe), last_u[B][2] (dd only).
  * Outputs (any may be NULL): u[B][15|6], x_plan[B][3][5|3], p_plan[B][3][3] (LIP only), status[B], iters[B],
  * obj[B], viol[B] (max row violation), close2goal[B] (uint8). */
 int dcbf_solve(dcbf_ctx *ctx, int32_t B, const double *x0, const double *goal, const int32_t *leg, const int32_t *field,

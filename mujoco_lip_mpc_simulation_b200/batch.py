@@ -164,8 +164,10 @@ class DcbfSolver:
         return B, x0, goal, leg, field, last_u
 
     def solve(self, x0, goal, leg, warm, field=None, last_u=None) -> SolveResult:
+        """warm=None (LIP formulations): the reference's start vector for init_guess = None, [x_k, x_k, x_k]
+        (MPC_LIP_sig_step.py:185-187), formed on the device."""
         B, x0, goal, leg, field, last_u = self._inputs(x0, goal, leg, field, last_u)
-        warm = self._dev(warm, torch.float64).reshape(B, self.nu)
+        warm = self._warm(warm, B)
         kw = dict(device=self.tdev)
         u = torch.empty((B, self.nu), dtype=torch.float64, **kw)
         xp = torch.empty((B, 3, self.nx), dtype=torch.float64, **kw)
@@ -181,6 +183,13 @@ class DcbfSolver:
                                      self._stream())
         self._check(rc, "dcbf_solve")
         return SolveResult(u, xp, pp, st, it, obj, viol, cl.bool())
+
+    def _warm(self, warm, B):
+        if warm is None:
+            if self.dd:
+                raise ValueError("the differential-drive formulation has no start rule of its own: pass warm[B, 6]")
+            return None
+        return self._dev(warm, torch.float64).reshape(B, self.nu)
 
     def solve_into(self, B, x0, goal, leg, field, warm, last_u, out: SolveResult):
         """Allocation-free variant for benchmarking: all arguments are resident tensors."""
@@ -389,7 +398,9 @@ class DcbfSolver:
         def ready(a, dt, n):   # already what the C side takes: a C-contiguous array of the right type and size (no conversion, no copy)
             return isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous and a.size == n
         B = x0.shape[0] if isinstance(x0, np.ndarray) and x0.ndim == 2 else -1
-        if not (B > 0 and ready(x0, np.float64, B * self.nx) and ready(goal, np.float64, 2 * B) and ready(warm, np.float64, B * self.nu)
+        if warm is None and self.dd:
+            raise ValueError("the differential-drive formulation has no start rule of its own: pass warm[B, 6]")
+        if not (B > 0 and ready(x0, np.float64, B * self.nx) and ready(goal, np.float64, 2 * B) and (warm is None or ready(warm, np.float64, B * self.nu))
                 and (leg is None or ready(leg, np.int32, B)) and (field is None or ready(field, np.int32, B))
                 and (last_u is None or ready(last_u, np.float64, 2 * B))):
             f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
@@ -400,7 +411,7 @@ class DcbfSolver:
             field = None if field is None else np.ascontiguousarray(field, dtype=np.int32).reshape(-1)
             if field is not None and field.shape[0] != B:
                 raise ValueError(f"field has {field.shape[0]} entries for a batch of {B} scenarios")
-            warm = f64(warm).reshape(B, self.nu)
+            warm = None if warm is None else f64(warm).reshape(B, self.nu)
             last_u = None if last_u is None else f64(last_u).reshape(B, 2)
         if out is None:
             out = SolveResult(np.empty((B, self.nu)), np.empty((B, 3, self.nx)), None if self.dd else np.empty((B, 3, 3)),

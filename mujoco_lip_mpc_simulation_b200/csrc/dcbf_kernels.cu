@@ -58,6 +58,9 @@ struct dcbf_ctx {
     int sched_flip; bool sched_clean; // which set of bucket counters the next batch uses; false: both sets are cleared first
     int sched_min_batch;              // smallest batch that is ordered (env DCBF_ORDER; 0 = never)
     int sched_select;                 // order obstacle-selecting formulations too (env DCBF_ORDER_SELECT)
+    int stage_in;                     // host-buffer calls: copy the inputs to the device in the classify pass (env DCBF_STAGE_IN, default 1)
+    bool stage_inputs;                // set by dcbf_solve_host around its dcbf_solve call: the input arrays are mapped host memory
+    char *d_stage; size_t stage_cap;  // device copies of such inputs, written by the classify pass (StageIn)
     int zero_copy;                    // dcbf_solve_host reads / writes page-locked caller buffers from the kernels (env DCBF_ZEROCOPY)
     int dd_generic;                   // differential drive: keep the generic two-slot kernel (env DCBF_DD_GENERIC=1; A/B comparisons and tests)
     int lipl_class;                   // size-class split: a class of its own for the problems wp::LipL covers (env DCBF_LIPL; 0 = two classes)
@@ -153,25 +156,49 @@ template <int NS> struct MinCtas<wp::LipL, NS> { static constexpr int v = DCBF_L
 // changes which warp solves which problem, never the result of a problem.
 #define DCBF_SCHED_BUCKETS 16
 #define DCBF_SCHED_MAX_BATCH (1 << 18)   /* measured: +20 % at 4096 scenarios, +8 % at 65536, -1.5 % at 1 M (nothing left to hide) */
-__global__ void __launch_bounds__(256) sched_classify_kernel(dcbf_params P, int B, BatchIn in, int *__restrict__ counts, int *__restrict__ rank) {
+// Device copies of a batch's inputs (stage-in of host-buffer calls): when the caller's arrays are mapped host memory, the classify pass
+// -- which reads x0 and the field index of every scenario anyway -- copies all inputs to device scratch with coalesced loads, and the
+// solve kernel behind it reads device memory (its per-problem loads would otherwise be two dependent round trips over PCIe in front
+// of every problem of a warp's chain).  All pointers NULL: nothing is copied.
+struct StageIn { double *x0, *goal, *warm, *last_u; int32_t *leg, *field; };
+
+__global__ void __launch_bounds__(256) sched_classify_kernel(dcbf_params P, int B, BatchIn in, int *__restrict__ counts, int *__restrict__ rank, StageIn sg) {
     __shared__ int s_cnt[DCBF_SCHED_BUCKETS], s_base[DCBF_SCHED_BUCKETS];
+    __shared__ double s_x0[256 * 5];
+    __shared__ int s_fld[256];
     if (threadIdx.x < DCBF_SCHED_BUCKETS) s_cnt[threadIdx.x] = 0;
+    const int nx = P.formulation == DCBF_DD ? 3 : 5, nu = P.formulation == DCBF_DD ? 6 : 15;
+    const int b0 = blockIdx.x * blockDim.x, nb = B - b0 < (int)blockDim.x ? B - b0 : (int)blockDim.x;
+    // the block's slice of every array is contiguous: consecutive threads read consecutive words (the arrays may be mapped host memory)
+    for (int i = threadIdx.x; i < nb * nx; i += blockDim.x) {
+        const double v = in.x0[(size_t)b0 * nx + i];
+        s_x0[i] = v;
+        if (sg.x0) sg.x0[(size_t)b0 * nx + i] = v;
+    }
+    if ((int)threadIdx.x < nb) {
+        const int f = in.field ? in.field[b0 + threadIdx.x] : 0;
+        s_fld[threadIdx.x] = f;
+        if (sg.field) sg.field[b0 + threadIdx.x] = f;
+        if (sg.leg) sg.leg[b0 + threadIdx.x] = in.leg[b0 + threadIdx.x];
+    }
+    if (sg.goal) for (int i = threadIdx.x; i < nb * 2; i += blockDim.x) sg.goal[(size_t)b0 * 2 + i] = in.goal[(size_t)b0 * 2 + i];
+    if (sg.warm) for (int i = threadIdx.x; i < nb * nu; i += blockDim.x) sg.warm[(size_t)b0 * nu + i] = in.warm[(size_t)b0 * nu + i];
+    if (sg.last_u) for (int i = threadIdx.x; i < nb * 2; i += blockDim.x) sg.last_u[(size_t)b0 * 2 + i] = in.last_u[(size_t)b0 * 2 + i];
     __syncthreads();
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = b0 + threadIdx.x;
     int c = 0, local = 0;
     if (b < B) {
         double px, py, vx, vy;
+        const double *x = s_x0 + nx * threadIdx.x;
         if (P.formulation == DCBF_DD) {
-            const double *x = in.x0 + 3 * (size_t)b;
             double sn, cs;
             sincos(x[2], &sn, &cs);
             px = x[0]; py = x[1]; vx = 0.8 * cs; vy = 0.8 * sn;
         } else {
-            const double *x = in.x0 + 5 * (size_t)b;
             px = x[0]; py = x[1]; vx = x[2]; vy = x[3];
         }
-        bool bad;
-        const int fld = batch_field(in, b, bad);
+        int fld = s_fld[threadIdx.x];
+        if (in.F > 0 && (unsigned)fld >= (unsigned)in.F) fld = 0;   // (batch_field: an invalid index reads field 0; the solve reports -13)
         const double *cr = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC, *er = in.elp_rec + (size_t)fld * in.Ke * DCBF_ELP_REC;
         double key = 1e30;
         int nsel = 0;
@@ -283,8 +310,14 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, MinCtas<M, NS>::v) sol
         if (i_ >= n) break;
         const int b = order ? order[i_] : i_;
         DCBF_ASSERT(b >= 0 && b < B);
-        // the 22 input values arrive in three coalesced requests (the buffers may be mapped host memory: dcbf_solve_host)
-        sm.ST[0][lane] = lane < 5 ? in.x0[5 * (size_t)b + lane] : (lane < 20 ? in.warm[15 * (size_t)b + lane - 5] : (lane < 22 ? in.goal[2 * (size_t)b + lane - 20] : 0.0));
+        // the 22 input values arrive in three coalesced requests (the buffers may be mapped host memory: dcbf_solve_host), the stance
+        // leg and the start mode travel with them (one round trip over PCIe instead of two).  warm == NULL: the reference's start
+        // vector for init_guess = None, [x_k, x_k, x_k] (MPC_LIP_sig_step.py:185-187) -- nothing to read.
+        sm.ST[0][lane] = lane < 5 ? in.x0[5 * (size_t)b + lane]
+                                  : (lane < 20 ? (in.warm ? in.warm[15 * (size_t)b + lane - 5] : in.x0[5 * (size_t)b + (lane - 5) % 5])
+                                               : (lane < 22 ? in.goal[2 * (size_t)b + lane - 20] : 0.0));
+        const int leg = in.leg ? in.leg[b] : 1;
+        const int md = in.mode ? in.mode[b] : 2;   // 0: warm start = previous plan verbatim, 1: shifted plan, 2: cold start
         __syncwarp();
         if (lane == 0) {
             double x0[5], u0[15], g[2];
@@ -297,8 +330,6 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, MinCtas<M, NS>::v) sol
         } else {
             __syncwarp();
         }
-        const int leg = in.leg ? in.leg[b] : 1;
-        const int md = in.mode ? in.mode[b] : 2;   // 0: warm start = previous plan verbatim, 1: shifted plan, 2: cold start
         wp::WState S;
         wp::solve_warp<M, NS>(P, in, b, lane, wid, leg, S, md == 0 ? P.mu_warm : (md == 1 ? P.mu_shift : P.mu_init));
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
@@ -672,7 +703,8 @@ static int warp_grid(const dcbf_ctx *ctx, int n, int ctas_per_sm) {
 }
 
 // longest-expected-first order of the batch (see sched_classify_kernel); nullptr when the batch is too small to have a tail
-static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t st, const int **order, int *work_counter = nullptr, bool *counter_cleared = nullptr) {
+static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t st, const int **order, int *work_counter = nullptr, bool *counter_cleared = nullptr,
+                          BatchIn *staged = nullptr) {
     *order = nullptr;
     if (counter_cleared) *counter_cleared = false;
     if (ctx->sched_min_batch <= 0 || B < ctx->sched_min_batch || B > DCBF_SCHED_MAX_BATCH || in.Kc + in.Ke == 0 || (ctx->P.select_obs && !ctx->sched_select)) return DCBF_OK;
@@ -688,7 +720,31 @@ static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t 
     ctx->sched_clean = false;   // (stays false if a launch below fails: the next call starts from cleared counters)
     int *counts = ctx->d_sched + DCBF_SCHED_BUCKETS * ctx->sched_flip, *counts_next = ctx->d_sched + DCBF_SCHED_BUCKETS * (1 - ctx->sched_flip);
     int *rank = ctx->d_sched + 2 * DCBF_SCHED_BUCKETS, *ord = rank + ctx->sched_cap;
-    sched_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->P, B, in, counts, rank);
+    StageIn sg = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (staged && ctx->stage_inputs) {   // host-buffer call: the solve kernel reads device copies made by the classify pass
+        const size_t b = (size_t)B, nx = ctx->P.formulation == DCBF_DD ? 3 : 5, nu = ctx->P.formulation == DCBF_DD ? 6 : 15;
+        const size_t need = 8 * b * (nx + 2 + nu + 2) + 4 * b * 2;
+        if (ctx->stage_cap < need) {
+            CK(cudaFree(ctx->d_stage));
+            ctx->d_stage = nullptr; ctx->stage_cap = 0;
+            CK(cudaMalloc(&ctx->d_stage, need));
+            ctx->stage_cap = need;
+        }
+        double *d = (double *)ctx->d_stage;
+        sg.x0 = d; d += b * nx;
+        sg.goal = d; d += b * 2;
+        if (in.warm) sg.warm = d;
+        d += b * nu;
+        if (in.last_u) sg.last_u = d;
+        d += b * 2;
+        int32_t *q = (int32_t *)d;
+        if (in.leg) sg.leg = q;
+        q += b;
+        if (in.field) sg.field = q;
+        *staged = in;
+        staged->x0 = sg.x0; staged->goal = sg.goal; staged->warm = sg.warm; staged->last_u = sg.last_u; staged->leg = sg.leg; staged->field = sg.field;
+    }
+    sched_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->P, B, in, counts, rank, sg);
     sched_scatter_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, counts, rank, ord, counts_next, work_counter);
     CK(cudaGetLastError());
     ctx->sched_flip ^= 1; ctx->sched_clean = true;
@@ -703,13 +759,14 @@ static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const Solv
                              const int *count = nullptr) {
     int *counter = ctx->d_counter + 1 + slot;
     bool cleared = false;
+    BatchIn in2 = in;   // (inputs in mapped host memory: replaced by the device copies the classify pass makes)
     if (!order) {
-        const int rc = schedule_order(ctx, B, in, st, &order, counter, &cleared);
+        const int rc = schedule_order(ctx, B, in, st, &order, counter, &cleared, &in2);
         if (rc != DCBF_OK) return rc;
     }
     if (!cleared) CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = warp_grid<M, NS>(ctx, B, MinCtas<M, NS>::v);
-    solve_lip_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, count, counter);
+    solve_lip_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in2, out, order, count, counter);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -719,11 +776,12 @@ static int launch_solve_dd_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const S
     const int *order = nullptr;
     int *counter = ctx->d_counter + 1;
     bool cleared = false;
-    const int rc = schedule_order(ctx, B, in, st, &order, counter, &cleared);
+    BatchIn in2 = in;
+    const int rc = schedule_order(ctx, B, in, st, &order, counter, &cleared, &in2);
     if (rc != DCBF_OK) return rc;
     if (!cleared) CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = warp_grid<M, NS>(ctx, B, DCBF_DD_MIN_CTAS(M, NS));
-    solve_dd_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in, out, order, counter);
+    solve_dd_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in2, out, order, counter);
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -879,6 +937,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     { const char *sp = getenv("DCBF_ORDER"); ctx->sched_min_batch = sp ? atoi(sp) : 2048; }
     { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }
+    { const char *sp = getenv("DCBF_STAGE_IN"); ctx->stage_in = sp ? atoi(sp) : 1; }
     { const char *sp = getenv("DCBF_DD_GENERIC"); ctx->dd_generic = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_SLOTS"); ctx->slots_per_sm = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_LIPL"); ctx->lipl_class = sp ? atoi(sp) : 1; }
@@ -896,7 +955,7 @@ void dcbf_destroy(dcbf_ctx *ctx) {
     int prev_dev = -1;
     cudaGetDevice(&prev_dev);
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); cudaFree(ctx->d_order); cudaFree(ctx->d_sched); cudaFree(ctx->d_tick); cudaFree(ctx->d_flow); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
+    cudaFree(ctx->d_counter); cudaFree(ctx->d_tab); cudaFree(ctx->d_order); cudaFree(ctx->d_sched); cudaFree(ctx->d_stage); cudaFree(ctx->d_tick); cudaFree(ctx->d_flow); cudaFree(ctx->cir_rec); cudaFree(ctx->elp_rec); cudaFree(ctx->d_buf); cudaFree(ctx->d_cir_raw); cudaFree(ctx->d_elp_raw);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -986,7 +1045,7 @@ static int solve_impl(dcbf_ctx *ctx, int32_t B, const double *x0, const double *
                       int32_t *iters, double *obj, double *viol, uint8_t *close2goal, void *stream) {
     if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
-    if (!x0 || !goal || !warm) return DCBF_ERR_ARG;
+    if (!x0 || !goal || (!warm && ctx->P.formulation == DCBF_DD)) return DCBF_ERR_ARG;   // (LIP: warm == NULL is the reference's init_guess = None)
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     ENTER(stream);
     BatchIn in = {x0, goal, warm, last_u, leg, field, ctx->cir_rec, ctx->elp_rec, ctx->Kc, ctx->Ke, ctx->F, mode};
@@ -1257,7 +1316,7 @@ static int solve_host_impl(dcbf_ctx *ctx, bool async, int32_t B, const double *x
                            int32_t *iters, double *obj, double *viol, uint8_t *close2goal) {
     if (!ctx || B < 0) return DCBF_ERR_ARG;
     if (B == 0) return DCBF_OK;
-    if (!x0 || !goal || !warm) return DCBF_ERR_ARG;
+    if (!x0 || !goal || (!warm && ctx->P.formulation == DCBF_DD)) return DCBF_ERR_ARG;
     if (!ctx->cir_rec) return DCBF_ERR_NO_FIELDS;
     ENTER(ctx->stream);
     const bool dd = ctx->P.formulation == DCBF_DD;
@@ -1302,9 +1361,11 @@ static int solve_host_impl(dcbf_ctx *ctx, bool async, int32_t B, const double *x
         for (int i = 0; i < 6 && mapped; i++) { void *d = nullptr; if (ins[i].src && cudaHostGetDevicePointer(&d, (void *)ins[i].src, 0) != cudaSuccess) mapped = false; dptr[i] = d; }
         for (int i = 0; i < 8 && mapped; i++) { void *d = nullptr; if (outs[i].dst && cudaHostGetDevicePointer(&d, outs[i].dst, 0) != cudaSuccess) mapped = false; dptr[6 + i] = d; }
         if (mapped) {
+            ctx->stage_inputs = ctx->stage_in != 0;
             rc = dcbf_solve(ctx, B, (const double *)dptr[0], (const double *)dptr[1], (const int32_t *)dptr[4], (const int32_t *)dptr[5], (const double *)dptr[2],
                             (const double *)dptr[3], (double *)dptr[6], (double *)dptr[7], (double *)dptr[8], (int32_t *)dptr[11], (int32_t *)dptr[12],
                             (double *)dptr[9], (double *)dptr[10], (uint8_t *)dptr[13], ctx->stream);
+            ctx->stage_inputs = false;
             if (rc != DCBF_OK) return rc;
             if (!async) CK(cudaStreamSynchronize(ctx->stream));
             return DCBF_OK;
@@ -1323,7 +1384,7 @@ static int solve_host_impl(dcbf_ctx *ctx, bool async, int32_t B, const double *x
         CK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     rc = dcbf_solve(ctx, B, (double *)(dp + o_x0), (double *)(dp + o_goal), leg ? (int32_t *)(dp + o_leg) : nullptr,
-                    field ? (int32_t *)(dp + o_field) : nullptr, (double *)(dp + o_warm), last_u ? (double *)(dp + o_lastu) : nullptr,
+                    field ? (int32_t *)(dp + o_field) : nullptr, warm ? (double *)(dp + o_warm) : nullptr, last_u ? (double *)(dp + o_lastu) : nullptr,
                     (double *)(dp + o_u), (double *)(dp + o_xp), dd ? nullptr : (double *)(dp + o_pp), (int32_t *)(dp + o_st),
                     (int32_t *)(dp + o_it), (double *)(dp + o_obj), (double *)(dp + o_viol), (uint8_t *)(dp + o_cl), ctx->stream);
     if (rc != DCBF_OK) return rc;

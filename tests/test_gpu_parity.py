@@ -528,6 +528,39 @@ def test_error_codes(gpu):
     lib.dcbf_destroy(ctx)
 
 
+@pytest.mark.parametrize("mode", ["warp", "thread"])
+def test_cold_start_rule_without_a_start_vector(gpu, monkeypatch, mode):
+    """warm = NULL is the reference's init_guess = None, u0 = [x_k, x_k, x_k] (MPC_LIP_sig_step.py:185-187), formed on the device:
+    bit for bit the result of passing that vector, through the device entry point, the host-buffer entry point (pageable and
+    page-locked buffers) and both kernel families; the differential drive has no such rule and rejects the call"""
+    monkeypatch.setenv("DCBF_KERNEL", mode)
+    sc = scenarios.make_batch("sig_step", 3000, seed=31)
+    s = _solver(gpu, "sig_step", sc)
+    ref = s.solve(sc.x0, sc.goal, sc.leg, np.tile(sc.x0, (1, 3)), field=sc.field)
+    res = s.solve(sc.x0, sc.goal, sc.leg, None, field=sc.field)
+    for a, b in ((ref.u, res.u), (ref.p_plan, res.p_plan), (ref.status, res.status), (ref.iters, res.iters)):
+        assert torch.equal(a, b)
+    h = s.solve_host(sc.x0, sc.goal, sc.leg, None, field=sc.field)
+    np.testing.assert_array_equal(h.u, ref.u.cpu().numpy())
+    np.testing.assert_array_equal(h.iters, ref.iters.cpu().numpy())
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    pe = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()           # noqa: E731
+    B = 3000
+    from mujoco_lip_mpc_simulation_b200.batch import SolveResult
+    out = SolveResult(pe((B, 15), torch.float64), pe((B, 3, 5), torch.float64), pe((B, 3, 3), torch.float64), pe((B,), torch.int32),
+                      pe((B,), torch.int32), pe((B,), torch.float64), pe((B,), torch.float64), pe((B,), torch.uint8))
+    s.solve_host(pin(sc.x0), pin(sc.goal), pin(sc.leg), None, field=pin(sc.field), out=out)
+    np.testing.assert_array_equal(out.u, ref.u.cpu().numpy())
+    np.testing.assert_array_equal(out.status, ref.status.cpu().numpy())
+    scd = scenarios.make_batch("dd", 64, seed=32)
+    sd = _solver(gpu, "dd", scd)
+    with pytest.raises(ValueError):
+        sd.solve(scd.x0, scd.goal, None, None, field=scd.field, last_u=scd.last_u)
+    lib = _lib.load()
+    x = torch.zeros((64, 3), dtype=torch.float64, device="cuda")
+    assert lib.dcbf_solve(sd._ctx, 64, x.data_ptr(), x.data_ptr(), None, None, None, None, *([None] * 8), None) == -1   # DCBF_ERR_ARG
+
+
 def test_empty_and_single_batches(gpu):
     sc = scenarios.config1()
     s = _solver(gpu, "sig_step", sc)
