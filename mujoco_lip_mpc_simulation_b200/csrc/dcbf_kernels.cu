@@ -162,10 +162,11 @@ template <int NS> struct MinCtas<wp::LipL, NS> { static constexpr int v = DCBF_L
 // of every problem of a warp's chain).  All pointers NULL: nothing is copied.
 struct StageIn { double *x0, *goal, *warm, *last_u; int32_t *leg, *field; };
 
-__global__ void __launch_bounds__(256) sched_classify_kernel(dcbf_params P, int B, BatchIn in, int *__restrict__ counts, int *__restrict__ rank, StageIn sg) {
+#define DCBF_SCHED_BLOCK 64   /* scenarios per CTA of the classify pass: 64 CTAs for a 4096-scenario batch (the pass is a chain of three dependent memory round trips -- inputs, obstacle records, bucket counters -- ~8 us whatever its arithmetic: single precision and 64 instead of 256 scenarios per CTA did not shorten it, nor did L2 prefetches of the solve kernel's first reads shorten the step) */
+__global__ void __launch_bounds__(DCBF_SCHED_BLOCK) sched_classify_kernel(dcbf_params P, int B, BatchIn in, int *__restrict__ counts, int *__restrict__ rank, StageIn sg) {
     __shared__ int s_cnt[DCBF_SCHED_BUCKETS], s_base[DCBF_SCHED_BUCKETS];
-    __shared__ double s_x0[256 * 5];
-    __shared__ int s_fld[256];
+    __shared__ double s_x0[DCBF_SCHED_BLOCK * 5];
+    __shared__ int s_fld[DCBF_SCHED_BLOCK];
     if (threadIdx.x < DCBF_SCHED_BUCKETS) s_cnt[threadIdx.x] = 0;
     const int nx = P.formulation == DCBF_DD ? 3 : 5, nu = P.formulation == DCBF_DD ? 6 : 15;
     const int b0 = blockIdx.x * blockDim.x, nb = B - b0 < (int)blockDim.x ? B - b0 : (int)blockDim.x;
@@ -182,7 +183,11 @@ __global__ void __launch_bounds__(256) sched_classify_kernel(dcbf_params P, int 
         if (sg.leg) sg.leg[b0 + threadIdx.x] = in.leg[b0 + threadIdx.x];
     }
     if (sg.goal) for (int i = threadIdx.x; i < nb * 2; i += blockDim.x) sg.goal[(size_t)b0 * 2 + i] = in.goal[(size_t)b0 * 2 + i];
-    if (sg.warm) for (int i = threadIdx.x; i < nb * nu; i += blockDim.x) sg.warm[(size_t)b0 * nu + i] = in.warm[(size_t)b0 * nu + i];
+    if (sg.warm && in.warm) for (int i = threadIdx.x; i < nb * nu; i += blockDim.x) sg.warm[(size_t)b0 * nu + i] = in.warm[(size_t)b0 * nu + i];
+    if (sg.warm && !in.warm) {   // no start vector (LIP): the reference's rule for init_guess = None, [x_k, x_k, x_k] (MPC_LIP_sig_step.py:185-187)
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * 15; i += blockDim.x) sg.warm[(size_t)b0 * 15 + i] = s_x0[(i / 15) * 5 + (i % 15) % 5];
+    }
     if (sg.last_u) for (int i = threadIdx.x; i < nb * 2; i += blockDim.x) sg.last_u[(size_t)b0 * 2 + i] = in.last_u[(size_t)b0 * 2 + i];
     __syncthreads();
     const int b = b0 + threadIdx.x;
@@ -200,20 +205,23 @@ __global__ void __launch_bounds__(256) sched_classify_kernel(dcbf_params P, int 
         int fld = s_fld[threadIdx.x];
         if (in.F > 0 && (unsigned)fld >= (unsigned)in.F) fld = 0;   // (batch_field: an invalid index reads field 0; the solve reports -13)
         const double *cr = in.cir_rec + (size_t)fld * in.Kc * DCBF_CIR_REC, *er = in.elp_rec + (size_t)fld * in.Ke * DCBF_ELP_REC;
-        double key = 1e30;
+        // single precision is plenty for a key that only decides which warp slot starts which scenario (never a result)
+        float key = 1e30f;
         int nsel = 0;
+        const float fpx = (float)px, fpy = (float)py, fvx = 0.4f * (float)vx, fvy = 0.4f * (float)vy;
         for (int j = 0; j < in.Kc + in.Ke; j++) {
             const double *o = j < in.Kc ? cr + DCBF_CIR_REC * j : er + DCBF_ELP_REC * (j - in.Kc);
-            const double r2 = j < in.Kc ? o[2] : o[6], r = sqrt(r2);
-            nsel += (px - o[0]) * (px - o[0]) + (py - o[1]) * (py - o[1]) - r2 <= P.detect_sq;
+            const double ox = o[0], oy = o[1], r2 = j < in.Kc ? o[2] : o[6];
+            nsel += (px - ox) * (px - ox) + (py - oy) * (py - oy) - r2 <= P.detect_sq;
+            const float r = sqrtf((float)r2), ex = fpx - (float)ox, ey = fpy - (float)oy;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const double dx = px + 0.4 * k * vx - o[0], dy = py + 0.4 * k * vy - o[1];
-                key = fmin(key, sqrt(dx * dx + dy * dy) - r);
+                const float dx = ex + (float)k * fvx, dy = ey + (float)k * fvy;
+                key = fminf(key, sqrtf(dx * dx + dy * dy) - r);
             }
         }
-        if (P.select_obs) c = 17 - (2 * nsel + (key < 0.15 ? 1 : 0));   // rows first (the cost of an iteration), then clearance
-        else c = (int)floor((key + 0.5) * 8.0);
+        if (P.select_obs) c = 17 - (2 * nsel + (key < 0.15f ? 1 : 0));   // rows first (the cost of an iteration), then clearance
+        else c = (int)floorf((key + 0.5f) * 8.0f);
         c = c < 0 ? 0 : (c > DCBF_SCHED_BUCKETS - 1 ? DCBF_SCHED_BUCKETS - 1 : c);
         local = atomicAdd(&s_cnt[c], 1);
     }
@@ -234,6 +242,12 @@ __global__ void sched_scatter_kernel(int B, const int *__restrict__ counts, cons
     int off = 0;
     for (int i = 0; i < c; i++) off += counts[i];
     order[off + (rank[b] & ((1 << 27) - 1))] = b;
+}
+
+// The same rule where no classify pass runs in front of the solve kernel (small and very large batches, size-class split, per-thread kernels)
+__global__ void cold_start_kernel(int B, const double *__restrict__ x0, double *__restrict__ warm) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)B * 15) warm[i] = x0[(i / 15) * 5 + (i % 15) % 5];
 }
 
 // Size classes for formulations with obstacle selection (MPC_LIP_modi.py:325-338): the number of rows of a problem is known
@@ -310,14 +324,9 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, MinCtas<M, NS>::v) sol
         if (i_ >= n) break;
         const int b = order ? order[i_] : i_;
         DCBF_ASSERT(b >= 0 && b < B);
-        // the 22 input values arrive in three coalesced requests (the buffers may be mapped host memory: dcbf_solve_host), the stance
-        // leg and the start mode travel with them (one round trip over PCIe instead of two).  warm == NULL: the reference's start
-        // vector for init_guess = None, [x_k, x_k, x_k] (MPC_LIP_sig_step.py:185-187) -- nothing to read.
-        sm.ST[0][lane] = lane < 5 ? in.x0[5 * (size_t)b + lane]
-                                  : (lane < 20 ? (in.warm ? in.warm[15 * (size_t)b + lane - 5] : in.x0[5 * (size_t)b + (lane - 5) % 5])
-                                               : (lane < 22 ? in.goal[2 * (size_t)b + lane - 20] : 0.0));
-        const int leg = in.leg ? in.leg[b] : 1;
-        const int md = in.mode ? in.mode[b] : 2;   // 0: warm start = previous plan verbatim, 1: shifted plan, 2: cold start
+        // the 22 input values arrive in three coalesced requests (a call without a start vector gets one from the pass in front of this
+        // kernel: StageIn::warm / cold_start_kernel)
+        sm.ST[0][lane] = lane < 5 ? in.x0[5 * (size_t)b + lane] : (lane < 20 ? in.warm[15 * (size_t)b + lane - 5] : (lane < 22 ? in.goal[2 * (size_t)b + lane - 20] : 0.0));
         __syncwarp();
         if (lane == 0) {
             double x0[5], u0[15], g[2];
@@ -330,6 +339,8 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, MinCtas<M, NS>::v) sol
         } else {
             __syncwarp();
         }
+        const int leg = in.leg ? in.leg[b] : 1;
+        const int md = in.mode ? in.mode[b] : 2;   // 0: warm start = previous plan verbatim, 1: shifted plan, 2: cold start
         wp::WState S;
         wp::solve_warp<M, NS>(P, in, b, lane, wid, leg, S, md == 0 ? P.mu_warm : (md == 1 ? P.mu_shift : P.mu_init));
         // ---- outputs (lane-parallel) ------------------------------------------------------------------------------
@@ -703,11 +714,28 @@ static int warp_grid(const dcbf_ctx *ctx, int n, int ctas_per_sm) {
 }
 
 // longest-expected-first order of the batch (see sched_classify_kernel); nullptr when the batch is too small to have a tail
+static bool sched_applies(const dcbf_ctx *ctx, int B, const BatchIn &in) {
+    return !(ctx->sched_min_batch <= 0 || B < ctx->sched_min_batch || B > DCBF_SCHED_MAX_BATCH || in.Kc + in.Ke == 0 || (ctx->P.select_obs && !ctx->sched_select));
+}
+// device scratch for the copies of a batch's inputs: [x0 | goal | warm | last_u | leg | field]
+static int ensure_stage(dcbf_ctx *ctx, int B) {
+    const size_t b = (size_t)B, nx = ctx->P.formulation == DCBF_DD ? 3 : 5, nu = ctx->P.formulation == DCBF_DD ? 6 : 15;
+    const size_t need = 8 * b * (nx + 2 + nu + 2) + 4 * b * 2;
+    if (ctx->stage_cap < need) {
+        CK(cudaFree(ctx->d_stage));
+        ctx->d_stage = nullptr; ctx->stage_cap = 0;
+        CK(cudaMalloc(&ctx->d_stage, need));
+        ctx->stage_cap = need;
+    }
+    return DCBF_OK;
+}
+static double *stage_warm(dcbf_ctx *ctx, int B) { return (double *)ctx->d_stage + (size_t)B * ((ctx->P.formulation == DCBF_DD ? 3 : 5) + 2); }
+
 static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t st, const int **order, int *work_counter = nullptr, bool *counter_cleared = nullptr,
                           BatchIn *staged = nullptr) {
     *order = nullptr;
     if (counter_cleared) *counter_cleared = false;
-    if (ctx->sched_min_batch <= 0 || B < ctx->sched_min_batch || B > DCBF_SCHED_MAX_BATCH || in.Kc + in.Ke == 0 || (ctx->P.select_obs && !ctx->sched_select)) return DCBF_OK;
+    if (!sched_applies(ctx, B, in)) return DCBF_OK;
     if (ctx->sched_cap < (size_t)B) {
         CK(cudaFree(ctx->d_sched));
         ctx->d_sched = nullptr; ctx->sched_cap = 0;
@@ -721,30 +749,29 @@ static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t 
     int *counts = ctx->d_sched + DCBF_SCHED_BUCKETS * ctx->sched_flip, *counts_next = ctx->d_sched + DCBF_SCHED_BUCKETS * (1 - ctx->sched_flip);
     int *rank = ctx->d_sched + 2 * DCBF_SCHED_BUCKETS, *ord = rank + ctx->sched_cap;
     StageIn sg = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (staged && ctx->stage_inputs) {   // host-buffer call: the solve kernel reads device copies made by the classify pass
-        const size_t b = (size_t)B, nx = ctx->P.formulation == DCBF_DD ? 3 : 5, nu = ctx->P.formulation == DCBF_DD ? 6 : 15;
-        const size_t need = 8 * b * (nx + 2 + nu + 2) + 4 * b * 2;
-        if (ctx->stage_cap < need) {
-            CK(cudaFree(ctx->d_stage));
-            ctx->d_stage = nullptr; ctx->stage_cap = 0;
-            CK(cudaMalloc(&ctx->d_stage, need));
-            ctx->stage_cap = need;
-        }
-        double *d = (double *)ctx->d_stage;
-        sg.x0 = d; d += b * nx;
-        sg.goal = d; d += b * 2;
-        if (in.warm) sg.warm = d;
-        d += b * nu;
-        if (in.last_u) sg.last_u = d;
-        d += b * 2;
-        int32_t *q = (int32_t *)d;
-        if (in.leg) sg.leg = q;
-        q += b;
-        if (in.field) sg.field = q;
+    const bool cold = staged && !in.warm && ctx->P.formulation != DCBF_DD;   // no start vector: the classify pass writes the cold-start rule
+    if (staged && (ctx->stage_inputs || cold)) {
+        const int rc = ensure_stage(ctx, B);
+        if (rc != DCBF_OK) return rc;
         *staged = in;
-        staged->x0 = sg.x0; staged->goal = sg.goal; staged->warm = sg.warm; staged->last_u = sg.last_u; staged->leg = sg.leg; staged->field = sg.field;
+        sg.warm = (in.warm && ctx->stage_inputs) || cold ? stage_warm(ctx, B) : nullptr;
+        if (sg.warm) staged->warm = sg.warm;
+        if (ctx->stage_inputs) {   // host-buffer call: the solve kernel reads device copies made by the classify pass
+            const size_t b = (size_t)B, nx = ctx->P.formulation == DCBF_DD ? 3 : 5, nu = ctx->P.formulation == DCBF_DD ? 6 : 15;
+            double *d = (double *)ctx->d_stage;
+            sg.x0 = d; d += b * nx;
+            sg.goal = d; d += b * 2;
+            d += b * nu;
+            if (in.last_u) sg.last_u = d;
+            d += b * 2;
+            int32_t *q = (int32_t *)d;
+            if (in.leg) sg.leg = q;
+            q += b;
+            if (in.field) sg.field = q;
+            staged->x0 = sg.x0; staged->goal = sg.goal; staged->last_u = sg.last_u; staged->leg = sg.leg; staged->field = sg.field;
+        }
     }
-    sched_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(ctx->P, B, in, counts, rank, sg);
+    sched_classify_kernel<<<(B + DCBF_SCHED_BLOCK - 1) / DCBF_SCHED_BLOCK, DCBF_SCHED_BLOCK, 0, st>>>(ctx->P, B, in, counts, rank, sg);
     sched_scatter_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, counts, rank, ord, counts_next, work_counter);
     CK(cudaGetLastError());
     ctx->sched_flip ^= 1; ctx->sched_clean = true;
@@ -1052,6 +1079,18 @@ static int solve_impl(dcbf_ctx *ctx, int32_t B, const double *x0, const double *
     SolveOut out = {u, x_plan, p_plan, obj, viol, status, iters, close2goal};
     cudaStream_t st = (cudaStream_t)stream;
     const bool dd = ctx->P.formulation == DCBF_DD;
+    if (!warm) {   // LIP without a start vector: [x_k, x_k, x_k], written by the classify pass of the start order where one runs, else here
+        const int ns = warp_slots(ctx);
+        const bool split = ns > 1 && ctx->P.select_obs && ctx->split_classes > 0 && B >= ctx->split_classes;
+        if (!(use_warp_kernel(ctx, B) && !split && sched_applies(ctx, B, in))) {
+            const int rc = ensure_stage(ctx, B);
+            if (rc != DCBF_OK) return rc;
+            cold_start_kernel<<<(unsigned)(((size_t)B * 15 + 255) / 256), 256, 0, st>>>(B, x0, stage_warm(ctx, B));
+            CK(cudaGetLastError());
+            ctx->launches++;
+            in.warm = stage_warm(ctx, B);
+        }
+    }
     if (dd && use_warp_kernel(ctx, B)) {
         const int ns = warp_slots(ctx);
         // two slots and at most ten obstacles (3 K <= 32): the D-CBF rows fill slot 0, the twelve linear rows get slot 1 (wp::DdL)

@@ -101,7 +101,7 @@ DCBF_HD void lip_lane_begin(const dcbf_params &P, const Consts &K, const BatchIn
     ipm_init(P, S);
     double u0[15];
     DCBF_UNROLL
-    for (int i = 0; i < 15; i++) u0[i] = in.warm ? in.warm[15 * (size_t)b + i] : M.pb.x0[i % 5];   // NULL: [x_k, x_k, x_k] (MPC_LIP_sig_step.py:185-187)
+    for (int i = 0; i < 15; i++) u0[i] = in.warm[15 * (size_t)b + i];
     lip_z_from_u(K, M.pb.x0, u0, S.z);
     if (in.mode) S.mu = in.mode[b] == 0 ? P.mu_warm : (in.mode[b] == 1 ? P.mu_shift : P.mu_init);
 }

@@ -93,7 +93,7 @@ def solve(P, x0, goal, leg, cir, elp, warm, field=None, last_u=None):
     leg = np.ascontiguousarray(np.broadcast_to(np.asarray(leg, dtype=np.int32), (B,)), dtype=np.int32)
     F, cir, elp = _fields(cir, elp)
     field = None if field is None else np.ascontiguousarray(field, dtype=np.int32)
-    warm, last_u = None if warm is None else _d(warm).reshape(B, nu), _d(last_u)   # None (LIP): [x_k, x_k, x_k] formed by the solver
+    warm, last_u = _d(warm).reshape(B, nu), _d(last_u)
     u, xp, pp = np.zeros((B, nu)), np.zeros((B, 3, nx)), np.zeros((B, 3, 3))
     obj, viol = np.zeros(B), np.zeros(B)
     st, it, cl = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.uint8)

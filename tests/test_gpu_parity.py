@@ -540,6 +540,8 @@ def test_cold_start_rule_without_a_start_vector(gpu, monkeypatch, mode):
     res = s.solve(sc.x0, sc.goal, sc.leg, None, field=sc.field)
     for a, b in ((ref.u, res.u), (ref.p_plan, res.p_plan), (ref.status, res.status), (ref.iters, res.iters)):
         assert torch.equal(a, b)
+    small = s.solve(sc.x0[:100], sc.goal[:100], sc.leg[:100], None, field=sc.field[:100])   # (no start-order pass in front of the kernel)
+    assert torch.equal(small.u, ref.u[:100]) and torch.equal(small.iters, ref.iters[:100])
     h = s.solve_host(sc.x0, sc.goal, sc.leg, None, field=sc.field)
     np.testing.assert_array_equal(h.u, ref.u.cpu().numpy())
     np.testing.assert_array_equal(h.iters, ref.iters.cpu().numpy())

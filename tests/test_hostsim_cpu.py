@@ -101,15 +101,3 @@ def test_edge_cases():
     o2 = c_oracle.solve(c_oracle.params("modi", max_iter=300), x0[0], [10, 10], 1, far[0], np.array([[40.0, 40.0, 1.0, 0.5, 0.3]]), np.tile(x0[0], 3))
     assert r2["status"][0] == o2["status"] == 0
     np.testing.assert_allclose(r2["p_plan"][0], o2["p_plan"], atol=1e-5)
-
-
-def test_cold_start_rule_without_a_start_vector():
-    """warm = None is the reference's init_guess = None: u0 = [x_k, x_k, x_k] (MPC_LIP_sig_step.py:185-187), formed by the solver --
-    bit for bit the result of passing that vector"""
-    sc = scenarios.make_batch("sig_step", 64, seed=5)
-    P = H.default_params("sig_step")
-    a = H.solve(P, sc.x0, sc.goal, sc.leg, sc.cir, None, np.tile(sc.x0, (1, 3)), field=sc.field)
-    b = H.solve(P, sc.x0, sc.goal, sc.leg, sc.cir, None, None, field=sc.field)
-    for k in ("u", "p_plan", "status", "iters", "f"):
-        np.testing.assert_array_equal(a[k], b[k])
-
