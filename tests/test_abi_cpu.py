@@ -47,3 +47,16 @@ def test_sass_is_sm100_fp64(built):
     out = subprocess.run([cuobjdump, "-sass", _lib.SO_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "solve_lip_kernel" in out and "DFMA" in out
+
+
+def test_integration_stub_mirrors_the_params_struct():
+    """the ctypes stub INTEGRATION.md shows a maintainer declares dcbf_params field for field (a shorter struct would let
+    dcbf_default_params write past it)"""
+    import os
+    import re
+    from mujoco_lip_mpc_simulation_b200 import _lib
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    block = text[text.index("class dcbf_params(C.Structure)"):text.index("class GpuSolve")]
+    ints = re.findall(r'\("(\w+)", C\.c_int32\)', block)
+    doubles = " ".join(re.findall(r'"([a-z_ ]+)"', block[block.index("C.c_double"):])).split()
+    assert ints + doubles == [n for n, _ in _lib.DcbfParams._fields_]
