@@ -61,3 +61,14 @@ sc = scenarios.make_batch("sig_step", 512, seed=8, n_fields=16)
 s.set_fields_host(sc.cir)
 h = s.solve_host(pin(sc.x0), pin(sc.goal), pin(sc.leg.astype(np.int32)), pin(sc.warm), field=pin(sc.field.astype(np.int32)))
 print("generation / host entry ok:", int(g["attempts"].min()), int((h.status == 0).sum()), flush=True)
+# host-buffer entry point on a batch the start order applies to: the classify pass stages the inputs on the device and writes the
+# cold-start vector (warm = None); small batch without a start vector: cold_start_kernel
+sc = scenarios.make_batch("sig_step", 2048, seed=9, n_fields=16)
+s = DcbfSolver("sig_step", device=0)
+s.set_fields_host(sc.cir)
+ref = s.solve_host(pin(sc.x0), pin(sc.goal), pin(sc.leg.astype(np.int32)), pin(np.tile(sc.x0, (1, 3))), field=pin(sc.field.astype(np.int32)))
+h = s.solve_host(pin(sc.x0), pin(sc.goal), pin(sc.leg.astype(np.int32)), None, field=pin(sc.field.astype(np.int32)))
+small = s.solve(sc.x0[:100], sc.goal[:100], sc.leg[:100], None, field=sc.field[:100])
+torch.cuda.synchronize()
+assert np.array_equal(h.u, ref.u) and np.array_equal(small.u.cpu().numpy(), ref.u[:100])
+print("staged host entry / cold-start rule ok:", int((h.status == 0).sum()), int((small.status == 0).sum()), flush=True)
