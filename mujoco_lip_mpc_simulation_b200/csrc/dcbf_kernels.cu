@@ -58,6 +58,7 @@ struct dcbf_ctx {
     int sched_flip; bool sched_clean; // which set of bucket counters the next batch uses; false: both sets are cleared first
     int sched_min_batch;              // smallest batch that is ordered (env DCBF_ORDER; 0 = never)
     int sched_select;                 // order obstacle-selecting formulations too (env DCBF_ORDER_SELECT)
+    int pdl;                          // programmatic dependent launch of the kernels of a scheduled step (env DCBF_PDL_LAUNCH, default 1)
     int stage_in;                     // host-buffer calls: copy the inputs to the device in the classify pass (env DCBF_STAGE_IN, default 1)
     bool stage_inputs;                // set by dcbf_solve_host around its dcbf_solve call: the input arrays are mapped host memory
     char *d_stage; size_t stage_cap;  // device copies of such inputs, written by the classify pass (StageIn)
@@ -154,6 +155,9 @@ template <int NS> struct MinCtas<wp::LipL, NS> { static constexpr int v = DCBF_L
 // step.  Hard problems are the ones that start close to an obstacle or walk into one, so the batch is bucketed by the smallest
 // clearance of the straight-line prediction over the next three steps (16 buckets of 12.5 cm) and started smallest first.  The order
 // changes which warp solves which problem, never the result of a problem.
+#ifndef DCBF_PDL
+#define DCBF_PDL 1
+#endif
 #define DCBF_SCHED_BUCKETS 16
 #define DCBF_SCHED_MAX_BATCH (1 << 18)   /* measured: +20 % at 4096 scenarios, +8 % at 65536, -1.5 % at 1 M (nothing left to hide) */
 // Device copies of a batch's inputs (stage-in of host-buffer calls): when the caller's arrays are mapped host memory, the classify pass
@@ -162,11 +166,27 @@ template <int NS> struct MinCtas<wp::LipL, NS> { static constexpr int v = DCBF_L
 // of every problem of a warp's chain).  All pointers NULL: nothing is copied.
 struct StageIn { double *x0, *goal, *warm, *last_u; int32_t *leg, *field; };
 
+// Programmatic dependent launch (sm_90+): the three kernels of a scheduled step are launched with programmatic stream serialisation
+// (launch_pdl), each lets its dependent start as soon as its own CTAs are running (pdl_release) and waits for the kernel in front of it
+// -- complete, memory flushed -- only where it first reads that kernel's results (pdl_wait; a no-op in a normally launched grid).  The
+// launch gaps and the solve kernel's prologue (tables into shared memory) then run beside the start-order pass.
+__device__ __forceinline__ void pdl_wait() {
+#if DCBF_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_release() {
+#if DCBF_PDL
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+
 #define DCBF_SCHED_BLOCK 64   /* scenarios per CTA of the classify pass: 64 CTAs for a 4096-scenario batch (the pass is a chain of three dependent memory round trips -- inputs, obstacle records, bucket counters -- ~8 us whatever its arithmetic: single precision and 64 instead of 256 scenarios per CTA did not shorten it, nor did L2 prefetches of the solve kernel's first reads shorten the step) */
 __global__ void __launch_bounds__(DCBF_SCHED_BLOCK) sched_classify_kernel(dcbf_params P, int B, BatchIn in, int *__restrict__ counts, int *__restrict__ rank, StageIn sg) {
     __shared__ int s_cnt[DCBF_SCHED_BUCKETS], s_base[DCBF_SCHED_BUCKETS];
     __shared__ double s_x0[DCBF_SCHED_BLOCK * 5];
     __shared__ int s_fld[DCBF_SCHED_BLOCK];
+    pdl_release();
     if (threadIdx.x < DCBF_SCHED_BUCKETS) s_cnt[threadIdx.x] = 0;
     const int nx = P.formulation == DCBF_DD ? 3 : 5, nu = P.formulation == DCBF_DD ? 6 : 15;
     const int b0 = blockIdx.x * blockDim.x, nb = B - b0 < (int)blockDim.x ? B - b0 : (int)blockDim.x;
@@ -235,6 +255,8 @@ __global__ void __launch_bounds__(DCBF_SCHED_BLOCK) sched_classify_kernel(dcbf_p
 __global__ void sched_scatter_kernel(int B, const int *__restrict__ counts, const int *__restrict__ rank, int *__restrict__ order,
                                      int *__restrict__ counts_next, int *__restrict__ work_counter) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_release();
+    pdl_wait();   // ranks and bucket counts of the classify pass
     if (b < DCBF_SCHED_BUCKETS) counts_next[b] = 0;
     if (b == 0 && work_counter) *work_counter = 0;
     if (b >= B) return;
@@ -319,6 +341,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, MinCtas<M, NS>::v) sol
     const wp::CtaShared &cs_ = wp::g_cs;
     const int n = count ? *count : B;
     wp::stage_cta<M, NS>(P, K, tab, lane, wid);
+    pdl_wait();   // start order, work counter and staged inputs of the passes in front (programmatic dependent launch)
     for (;;) {
         const int i_ = wp::next_problem(counter, lane);
         if (i_ >= n) break;
@@ -378,6 +401,7 @@ __global__ void __launch_bounds__(32 * wp::Wpc<M, NS>::v, DCBF_DD_MIN_CTAS(M, NS
     wp::WarpShared<M, NS> &sm = wp::g_sm<M, NS>[wid];
     const wp::CtaShared &cs_ = wp::g_cs;
     wp::stage_cta<M, NS>(P, K, tab, lane, wid);
+    pdl_wait();
     for (;;) {
         const int i_ = wp::next_problem(counter, lane);
         if (i_ >= B) break;
@@ -713,6 +737,18 @@ static int warp_grid(const dcbf_ctx *ctx, int n, int ctas_per_sm) {
     return need < resident ? (need < 1 ? 1 : need) : resident;
 }
 
+// kernel launch with programmatic stream serialisation (see pdl_wait)
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // longest-expected-first order of the batch (see sched_classify_kernel); nullptr when the batch is too small to have a tail
 static bool sched_applies(const dcbf_ctx *ctx, int B, const BatchIn &in) {
     return !(ctx->sched_min_batch <= 0 || B < ctx->sched_min_batch || B > DCBF_SCHED_MAX_BATCH || in.Kc + in.Ke == 0 || (ctx->P.select_obs && !ctx->sched_select));
@@ -772,7 +808,7 @@ static int schedule_order(dcbf_ctx *ctx, int B, const BatchIn &in, cudaStream_t 
         }
     }
     sched_classify_kernel<<<(B + DCBF_SCHED_BLOCK - 1) / DCBF_SCHED_BLOCK, DCBF_SCHED_BLOCK, 0, st>>>(ctx->P, B, in, counts, rank, sg);
-    sched_scatter_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, counts, rank, ord, counts_next, work_counter);
+    CK(launch_pdl(sched_scatter_kernel, dim3((B + 255) / 256), dim3(256), st, ctx->pdl != 0, B, (const int *)counts, (const int *)rank, ord, counts_next, work_counter));
     CK(cudaGetLastError());
     ctx->sched_flip ^= 1; ctx->sched_clean = true;
     ctx->launches += 2;
@@ -793,7 +829,7 @@ static int launch_solve_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const Solv
     }
     if (!cleared) CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = warp_grid<M, NS>(ctx, B, MinCtas<M, NS>::v);
-    solve_lip_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in2, out, order, count, counter);
+    CK(launch_pdl(solve_lip_warp_kernel<M, NS>, dim3(grid), dim3(32 * wp::Wpc<M, NS>::v), st, cleared && ctx->pdl != 0, ctx->P, ctx->K, (const wp::WarpTables *)ctx->d_tab, B, in2, out, order, count, counter));   // (cleared: the start-order kernels are in front)
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -808,7 +844,7 @@ static int launch_solve_dd_warp(dcbf_ctx *ctx, int B, const BatchIn &in, const S
     if (rc != DCBF_OK) return rc;
     if (!cleared) CK(cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = warp_grid<M, NS>(ctx, B, DCBF_DD_MIN_CTAS(M, NS));
-    solve_dd_warp_kernel<M, NS><<<grid, 32 * wp::Wpc<M, NS>::v, 0, st>>>(ctx->P, ctx->K, ctx->d_tab, B, in2, out, order, counter);
+    CK(launch_pdl(solve_dd_warp_kernel<M, NS>, dim3(grid), dim3(32 * wp::Wpc<M, NS>::v), st, cleared && ctx->pdl != 0, ctx->P, ctx->K, (const wp::WarpTables *)ctx->d_tab, B, in2, out, order, counter));
     CK(cudaGetLastError());
     return DCBF_OK;
 }
@@ -965,6 +1001,7 @@ int dcbf_create(const dcbf_params *params, int device, dcbf_ctx **out) {
     { const char *sp = getenv("DCBF_ORDER_SELECT"); ctx->sched_select = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_ZEROCOPY"); ctx->zero_copy = sp ? atoi(sp) : 1; }
     { const char *sp = getenv("DCBF_STAGE_IN"); ctx->stage_in = sp ? atoi(sp) : 1; }
+    { const char *sp = getenv("DCBF_PDL_LAUNCH"); ctx->pdl = sp ? atoi(sp) : 1; }
     { const char *sp = getenv("DCBF_DD_GENERIC"); ctx->dd_generic = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_SLOTS"); ctx->slots_per_sm = sp ? atoi(sp) : 0; }
     { const char *sp = getenv("DCBF_LIPL"); ctx->lipl_class = sp ? atoi(sp) : 1; }
